@@ -1,0 +1,621 @@
+// C ABI of phyclone_b200 (see include/phyclone_b200.h).  No torch types, no CPU fallback.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/phyclone_b200.h"
+#include "pcb_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define PCB_CUDA(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess)                                                                          \
+      return fail(PCB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                \
+  } while (0)
+
+#define PCB_LAUNCH_CHECK()                                                                          \
+  do {                                                                                              \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                             \
+    cudaError_t _e = cudaGetLastError();                                                            \
+    if (_e != cudaSuccess) return fail(PCB_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(_e)); \
+  } while (0)
+
+// ---- layout -------------------------------------------------------------------
+const int kStrips[] = {5, 7, 9, 13};
+
+int fill_layout(int S, int G, int L, int P, pcb_layout* out) {
+  if (S < 1 || G < 1 || G > 4096) return fail(PCB_ERR_ARG, "layout: need S >= 1 and 1 <= G <= 4096");
+  bool okL = false;
+  for (int l : kStrips) okL |= (l == L);
+  if (!okL || (P != 4 && P != 8 && P != 16 && P != 32)) return fail(PCB_ERR_ARG, "layout: unsupported strip/lanes");
+  const int Q = (G + L - 1) / L;
+  int pitch = L + Q * L;
+  const int want = (P == 4) ? 4 : 8;  // bank rule: rows sharing a half-warp must not collide
+  while (pitch % 16 != want) ++pitch;
+  int RB = std::min(S, std::max(1, 64 / P));
+  // keep at least one full warp per CTA but stay under 48 KB of shared memory when possible
+  while (RB * P > 32 && 64 + 4ll * RB * pitch * 8 > 48 * 1024) RB = (RB + 1) / 2;
+  while (RB > 1 && 64 + 4ll * RB * pitch * 8 > 200 * 1024) RB = (RB + 1) / 2;
+  if (64 + 4ll * RB * pitch * 8 > 200 * 1024) return fail(PCB_ERR_ARG, "layout: grid too large for shared memory");
+  out->S = S;
+  out->G = G;
+  out->strip = L;
+  out->lanes_per_row = P;
+  out->n_strips = Q;
+  out->pitch = pitch;
+  out->lead = L;
+  out->rows_per_cta = RB;
+  out->tile_elems = (int64_t)S * pitch;
+  return PCB_OK;
+}
+
+long long lane_slots(int G, int L, int P) {
+  const long long Q = (G + L - 1) / L, U = (Q + 1) / 2;
+  return P * ((U + P - 1) / P) * (Q + 1) * L * L;
+}
+
+template <int L>
+int launch_jobs_L(const pcb::JobKernelParams& kp, long long n_jobs, int threads, size_t smem, cudaStream_t st) {
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    PCB_CUDA(cudaFuncSetAttribute(pcb::node_jobs_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const long long grid = n_jobs * kp.row_blocks;
+  if (grid > 2147483647ll) return fail(PCB_ERR_ARG, "too many jobs for one launch");
+  pcb::node_jobs_kernel<L><<<(unsigned)grid, threads, smem, st>>>(kp);
+  PCB_LAUNCH_CHECK();
+  return PCB_OK;
+}
+
+int check_arena(const pcb_arena* a) {
+  if (!a || !a->lg || !a->lin || !a->rmax || a->capacity < 1) return fail(PCB_ERR_ARG, "arena: null");
+  return PCB_OK;
+}
+
+// ---- scratch device memory for the host-buffer entry points --------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return PCB_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? PCB_ERR_NOMEM : PCB_ERR_CUDA,
+                                      std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    cap = want;
+    return PCB_OK;
+  }
+  template <class T>
+  T* as() {
+    return static_cast<T*>(p);
+  }
+};
+
+struct HostScratch {
+  DevBuf in, out, lg, lin, rmax, jobs, kids, ids, rows_a, rows_b, misc, red;
+  pcb_layout layout{};
+  int64_t arena_cap = 0;
+  bool arena_zeroed_for = false;
+};
+thread_local HostScratch g_hs;
+
+int ensure_arena(HostScratch& hs, int S, int G, int64_t tiles, pcb_arena* a) {
+  pcb_layout lay;
+  int rc = pcb_make_layout(S, G, -1, &lay);
+  if (rc) return rc;
+  const bool same = hs.arena_cap >= tiles && memcmp(&hs.layout, &lay, sizeof(lay)) == 0;
+  if (!same) {
+    const size_t tb = (size_t)lay.tile_elems * 8;
+    if ((rc = hs.lg.ensure(tb * tiles))) return rc;
+    if ((rc = hs.lin.ensure(tb * tiles))) return rc;
+    if ((rc = hs.rmax.ensure((size_t)S * 8 * tiles))) return rc;
+    PCB_CUDA(cudaMemsetAsync(hs.lg.p, 0, tb * tiles, 0));
+    PCB_CUDA(cudaMemsetAsync(hs.lin.p, 0, tb * tiles, 0));
+    hs.layout = lay;
+    hs.arena_cap = tiles;
+  }
+  a->layout = hs.layout;
+  a->lg = hs.lg.as<double>();
+  a->lin = hs.lin.as<double>();
+  a->rmax = hs.rmax.as<double>();
+  a->capacity = hs.arena_cap;
+  return PCB_OK;
+}
+
+// Shared driver of the dense host entry points: import `n_in` dense tiles, run B jobs, export B tiles.
+// job b folds input tiles kids[koff[b]..koff[b+1]) ; base[b] (input tile index or -1); flags.
+int run_dense(const double* in_host, int64_t n_in, const std::vector<int32_t>& kids, const std::vector<int64_t>& koff,
+              const std::vector<int32_t>& base, int flags, double prior, int64_t B, int S, int G, double* out_host,
+              double* lse_host, double* last_host) {
+  HostScratch& hs = g_hs;
+  pcb_arena ar;
+  int rc = ensure_arena(hs, S, G, n_in + B, &ar);
+  if (rc) return rc;
+  const size_t dense_tile = (size_t)S * G * 8;
+  if ((rc = hs.in.ensure(dense_tile * std::max<int64_t>(n_in, 1)))) return rc;
+  if ((rc = hs.out.ensure(dense_tile * std::max<int64_t>(B, 1)))) return rc;
+  std::vector<int32_t> ids(n_in + B);
+  for (int64_t i = 0; i < n_in + B; ++i) ids[i] = (int32_t)i;
+  if ((rc = hs.ids.ensure(ids.size() * 4))) return rc;
+  PCB_CUDA(cudaMemcpyAsync(hs.ids.p, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice, 0));
+  PCB_CUDA(cudaMemcpyAsync(hs.in.p, in_host, dense_tile * n_in, cudaMemcpyHostToDevice, 0));
+  if ((rc = pcb_arena_import_dev(&ar, hs.in.as<double>(), hs.ids.as<int32_t>(), n_in, nullptr))) return rc;
+  // jobs with >= 1 child go through the kernel; leaves (0 children) copy their base tile
+  std::vector<int32_t> jobs;
+  std::vector<int32_t> out_ids(B);
+  int64_t n_jobs = 0;
+  for (int64_t b = 0; b < B; ++b) {
+    const int64_t c = koff[b + 1] - koff[b];
+    if (c == 0) {
+      if (base.empty() || base[b] < 0) return fail(PCB_ERR_ARG, "job without children and without log_p");
+      out_ids[b] = base[b];
+      continue;
+    }
+    out_ids[b] = (int32_t)(n_in + b);
+    const int32_t rec[8] = {(int32_t)koff[b], (int32_t)c, base.empty() ? -1 : base[b], out_ids[b], flags,
+                            (lse_host ? (int32_t)b : -1), 0, 0};
+    jobs.insert(jobs.end(), rec, rec + 8);
+    ++n_jobs;
+  }
+  double *rows_l = nullptr, *rows_t = nullptr;
+  if (lse_host) {
+    if ((rc = hs.rows_a.ensure((size_t)B * S * 8))) return rc;
+    if ((rc = hs.rows_b.ensure((size_t)B * S * 8))) return rc;
+    rows_l = hs.rows_a.as<double>();
+    rows_t = hs.rows_b.as<double>();
+  }
+  if (n_jobs) {
+    if ((rc = hs.jobs.ensure(jobs.size() * 4))) return rc;
+    if ((rc = hs.kids.ensure(std::max<size_t>(kids.size(), 1) * 4))) return rc;
+    PCB_CUDA(cudaMemcpyAsync(hs.jobs.p, jobs.data(), jobs.size() * 4, cudaMemcpyHostToDevice, 0));
+    PCB_CUDA(cudaMemcpyAsync(hs.kids.p, kids.data(), kids.size() * 4, cudaMemcpyHostToDevice, 0));
+    if ((rc = pcb_node_jobs_dev(&ar, hs.jobs.as<int32_t>(), hs.kids.as<int32_t>(), n_jobs, prior, rows_l, rows_t,
+                                nullptr)))
+      return rc;
+  }
+  if (out_host) {
+    if ((rc = hs.misc.ensure((size_t)B * 4))) return rc;
+    PCB_CUDA(cudaMemcpyAsync(hs.misc.p, out_ids.data(), (size_t)B * 4, cudaMemcpyHostToDevice, 0));
+    if ((rc = pcb_arena_export_dev(&ar, hs.misc.as<int32_t>(), B, hs.out.as<double>(), nullptr))) return rc;
+    PCB_CUDA(cudaMemcpyAsync(out_host, hs.out.p, dense_tile * B, cudaMemcpyDeviceToHost, 0));
+  }
+  if (lse_host) {
+    // reduce rows -> [B] on device, in sample order
+    if ((rc = hs.red.ensure((size_t)B * 16))) return rc;
+    double* red = hs.red.as<double>();
+    if ((rc = pcb_reduce_rows_dev(rows_l, B, S, red, nullptr))) return rc;
+    if ((rc = pcb_reduce_rows_dev(rows_t, B, S, red + B, nullptr))) return rc;
+    PCB_CUDA(cudaMemcpyAsync(lse_host, red, (size_t)B * 8, cudaMemcpyDeviceToHost, 0));
+    PCB_CUDA(cudaMemcpyAsync(last_host, red + B, (size_t)B * 8, cudaMemcpyDeviceToHost, 0));
+  }
+  PCB_CUDA(cudaStreamSynchronize(0));
+  return PCB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pcb_version(void) { return 100; }
+const char* pcb_last_error(void) { return g_err.c_str(); }
+int64_t pcb_launch_count(void) { return g_launches.load(); }
+
+int pcb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int pcb_set_device(int device) {
+  PCB_CUDA(cudaSetDevice(device));
+  return PCB_OK;
+}
+
+int pcb_make_layout(int32_t S, int32_t G, int32_t variant, pcb_layout* out) {
+  if (!out) return fail(PCB_ERR_ARG, "layout: null out");
+  if (variant < 0) {
+    const char* env = getenv("PCB_VARIANT");
+    if (env && *env) variant = atoi(env);
+  }
+  if (variant >= 0) return fill_layout(S, G, variant / 100, variant % 100, out);
+  // default: fewest executed lane-FMAs among the conflict-free (odd strip) configurations with
+  // at least 7 FMAs per shared-memory operand pair
+  long long best = -1;
+  int bl = 7, bp = 8;
+  for (int L : {7, 13})
+    for (int P : {4, 8, 16, 32}) {
+      if (L == 7 && P == 4) continue;
+      const long long c = lane_slots(G, L, P);
+      if (best < 0 || c <= best) best = c, bl = L, bp = P;  // ties: more lanes per row = less smem per warp
+    }
+  return fill_layout(S, G, bl, bp, out);
+}
+
+int pcb_arena_import_dev(const pcb_arena* a, const double* dense, const int32_t* ids_dev, int64_t n, void* stream) {
+  int rc = check_arena(a);
+  if (rc) return rc;
+  if (n <= 0) return PCB_OK;
+  const pcb_layout& l = a->layout;
+  const long long warps = n * l.S;
+  const int wpb = 4;
+  pcb::import_tiles_kernel<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+      dense, ids_dev, n, a->lg, a->lin, a->rmax, l.S, l.G, l.pitch, l.lead, l.tile_elems);
+  PCB_LAUNCH_CHECK();
+  return PCB_OK;
+}
+
+int pcb_arena_export_dev(const pcb_arena* a, const int32_t* ids_dev, int64_t n, double* dense, void* stream) {
+  int rc = check_arena(a);
+  if (rc) return rc;
+  if (n <= 0) return PCB_OK;
+  const pcb_layout& l = a->layout;
+  const long long warps = n * l.S;
+  const int wpb = 4;
+  pcb::export_tiles_kernel<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+      a->lg, ids_dev, n, dense, l.S, l.G, l.pitch, l.lead, l.tile_elems);
+  PCB_LAUNCH_CHECK();
+  return PCB_OK;
+}
+
+int pcb_tile_add_dev(const pcb_arena* a, const int32_t* a_ids, const int32_t* b_ids, const int32_t* out_ids,
+                     int64_t n, double addend, void* stream) {
+  int rc = check_arena(a);
+  if (rc) return rc;
+  if (n <= 0) return PCB_OK;
+  const pcb_layout& l = a->layout;
+  const long long warps = n * l.S;
+  const int wpb = 4;
+  pcb::tile_add_kernel<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+      a_ids, b_ids, out_ids, n, addend, a->lg, a->lin, a->rmax, l.S, l.G, l.pitch, l.lead, l.tile_elems);
+  PCB_LAUNCH_CHECK();
+  return PCB_OK;
+}
+
+int pcb_node_jobs_dev(const pcb_arena* a, const int32_t* jobs_dev, const int32_t* children_dev, int64_t n_jobs,
+                      double prior, double* rows_lse, double* rows_last, void* stream) {
+  int rc = check_arena(a);
+  if (rc) return rc;
+  if (n_jobs <= 0) return PCB_OK;
+  if (!jobs_dev || !children_dev) return fail(PCB_ERR_ARG, "node_jobs: null job table");
+  const pcb_layout& l = a->layout;
+  pcb::JobKernelParams kp;
+  kp.jobs = jobs_dev;
+  kp.children = children_dev;
+  kp.lg = a->lg;
+  kp.lin = a->lin;
+  kp.rmax = a->rmax;
+  kp.sc_lse = rows_lse;
+  kp.sc_last = rows_last;
+  kp.tile_elems = l.tile_elems;
+  kp.prior = prior;
+  kp.S = l.S;
+  kp.G = l.G;
+  kp.Q = l.n_strips;
+  kp.U = (l.n_strips + 1) / 2;
+  kp.P = l.lanes_per_row;
+  kp.pitch = l.pitch;
+  kp.lead = l.lead;
+  kp.RB = l.rows_per_cta;
+  kp.row_blocks = (l.S + l.rows_per_cta - 1) / l.rows_per_cta;
+  const int threads = ((l.rows_per_cta * l.lanes_per_row + 31) / 32) * 32;
+  const size_t smem = 64 + 4ull * l.rows_per_cta * l.pitch * 8;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (l.strip) {
+    case 5:
+      return launch_jobs_L<5>(kp, n_jobs, threads, smem, st);
+    case 7:
+      return launch_jobs_L<7>(kp, n_jobs, threads, smem, st);
+    case 9:
+      return launch_jobs_L<9>(kp, n_jobs, threads, smem, st);
+    case 13:
+      return launch_jobs_L<13>(kp, n_jobs, threads, smem, st);
+  }
+  return fail(PCB_ERR_ARG, "node_jobs: unsupported strip");
+}
+
+int pcb_reduce_rows_dev(const double* rows_dev, int64_t n_slots, int32_t S, double* out_dev, void* stream) {
+  if (n_slots <= 0) return PCB_OK;
+  pcb::reduce_rows_kernel<<<(unsigned)((n_slots + 127) / 128), 128, 0, (cudaStream_t)stream>>>(rows_dev, n_slots, S,
+                                                                                               out_dev);
+  PCB_LAUNCH_CHECK();
+  return PCB_OK;
+}
+
+// ---- host-buffer entry points ---------------------------------------------------
+int pcb_np_conv_dims_host(const double* c1, const double* c2, double* out, int64_t B, int32_t S, int32_t G) {
+  if (!c1 || !c2 || !out || B < 0) return fail(PCB_ERR_ARG, "np_conv_dims: null pointer");
+  if (B == 0) return PCB_OK;
+  // inputs interleaved into one dense block: tile 2b = c1[b], tile 2b+1 = c2[b]
+  std::vector<double> in((size_t)2 * B * S * G);
+  const size_t t = (size_t)S * G;
+  for (int64_t b = 0; b < B; ++b) {
+    memcpy(&in[(2 * b) * t], c1 + b * t, t * 8);
+    memcpy(&in[(2 * b + 1) * t], c2 + b * t, t * 8);
+  }
+  std::vector<int32_t> kids(2 * B);
+  std::vector<int64_t> koff(B + 1);
+  for (int64_t b = 0; b < B; ++b) {
+    kids[2 * b] = (int32_t)(2 * b);
+    kids[2 * b + 1] = (int32_t)(2 * b + 1);
+    koff[b] = 2 * b;
+  }
+  koff[B] = 2 * B;
+  return run_dense(in.data(), 2 * B, kids, koff, {}, 0, 0.0, B, S, G, out, nullptr, nullptr);
+}
+
+int pcb_sub_compute_S_host(const double* log_D, double* log_S, int64_t B, int32_t S, int32_t G) {
+  if (!log_D || !log_S || B < 0) return fail(PCB_ERR_ARG, "sub_compute_S: null pointer");
+  if (B == 0) return PCB_OK;
+  std::vector<int32_t> kids(B);
+  std::vector<int64_t> koff(B + 1);
+  for (int64_t b = 0; b < B; ++b) kids[b] = (int32_t)b, koff[b] = b;
+  koff[B] = B;
+  return run_dense(log_D, B, kids, koff, {}, PCB_JOB_SCAN, 0.0, B, S, G, log_S, nullptr, nullptr);
+}
+
+int pcb_compute_log_S_host(const double* children, const int64_t* child_off, double* log_S, int64_t B, int32_t S,
+                           int32_t G) {
+  if (!children || !child_off || !log_S || B < 0) return fail(PCB_ERR_ARG, "compute_log_S: null pointer");
+  if (B == 0) return PCB_OK;
+  const int64_t n = child_off[B];
+  std::vector<int32_t> kids(n);
+  for (int64_t i = 0; i < n; ++i) kids[i] = (int32_t)i;
+  std::vector<int64_t> koff(child_off, child_off + B + 1);
+  for (int64_t b = 0; b < B; ++b)
+    if (koff[b + 1] - koff[b] < 1) return fail(PCB_ERR_ARG, "compute_log_S: every job needs >= 1 child");
+  return run_dense(children, n, kids, koff, {}, PCB_JOB_SCAN, 0.0, B, S, G, log_S, nullptr, nullptr);
+}
+
+int pcb_node_update_host(const double* log_p, const double* children, const int64_t* child_off, double* log_r,
+                         int64_t B, int32_t S, int32_t G) {
+  if (!log_p || !child_off || !log_r || B < 0) return fail(PCB_ERR_ARG, "node_update: null pointer");
+  if (B == 0) return PCB_OK;
+  const int64_t n = child_off[B];
+  if (n > 0 && !children) return fail(PCB_ERR_ARG, "node_update: null children");
+  const size_t t = (size_t)S * G;
+  std::vector<double> in((size_t)(n + B) * t);
+  if (n) memcpy(in.data(), children, (size_t)n * t * 8);
+  memcpy(in.data() + (size_t)n * t, log_p, (size_t)B * t * 8);
+  std::vector<int32_t> kids(n), base(B);
+  for (int64_t i = 0; i < n; ++i) kids[i] = (int32_t)i;
+  for (int64_t b = 0; b < B; ++b) base[b] = (int32_t)(n + b);
+  std::vector<int64_t> koff(child_off, child_off + B + 1);
+  return run_dense(in.data(), n + B, kids, koff, base, PCB_JOB_SCAN, 0.0, B, S, G, log_r, nullptr, nullptr);
+}
+
+int pcb_root_terms_host(const double* root_tiles, double* lse_sum, double* last_sum, int64_t B, int32_t S,
+                        int32_t G) {
+  if (!root_tiles || !lse_sum || !last_sum || B < 0) return fail(PCB_ERR_ARG, "root_terms: null pointer");
+  if (B == 0) return PCB_OK;
+  HostScratch& hs = g_hs;
+  int rc;
+  const size_t bytes = (size_t)B * S * G * 8;
+  if ((rc = hs.in.ensure(bytes))) return rc;
+  if ((rc = hs.rows_a.ensure((size_t)B * S * 8))) return rc;
+  if ((rc = hs.rows_b.ensure((size_t)B * S * 8))) return rc;
+  if ((rc = hs.misc.ensure((size_t)B * 16))) return rc;
+  PCB_CUDA(cudaMemcpyAsync(hs.in.p, root_tiles, bytes, cudaMemcpyHostToDevice, 0));
+  const long long warps = B * S;
+  pcb::root_terms_rows_kernel<<<(unsigned)((warps + 3) / 4), 128>>>(hs.in.as<double>(), B, S, G, hs.rows_a.as<double>(),
+                                                                     hs.rows_b.as<double>());
+  PCB_LAUNCH_CHECK();
+  double* red = hs.misc.as<double>();
+  if ((rc = pcb_reduce_rows_dev(hs.rows_a.as<double>(), B, S, red, nullptr))) return rc;
+  if ((rc = pcb_reduce_rows_dev(hs.rows_b.as<double>(), B, S, red + B, nullptr))) return rc;
+  PCB_CUDA(cudaMemcpyAsync(lse_sum, red, (size_t)B * 8, cudaMemcpyDeviceToHost, 0));
+  PCB_CUDA(cudaMemcpyAsync(last_sum, red + B, (size_t)B * 8, cudaMemcpyDeviceToHost, 0));
+  PCB_CUDA(cudaStreamSynchronize(0));
+  return PCB_OK;
+}
+
+int pcb_likelihood_grid_dev(const int64_t* refc, const int64_t* altc, const double* tc, const int64_t* cn,
+                            const double* mu, const double* log_pi, const int32_t* n_geno, int64_t M, int32_t S,
+                            int32_t Cmax, int32_t G, int32_t density, double precision, double* out, void* stream) {
+  if (M <= 0) return PCB_OK;
+  if (G < 2 || Cmax < 1 || (density != 0 && density != 1)) return fail(PCB_ERR_ARG, "likelihood_grid: bad arguments");
+  const long long cells = (long long)M * S * G;
+  pcb::likelihood_grid_kernel<<<(unsigned)((cells + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      (const long long*)refc, (const long long*)altc, tc, (const long long*)cn, mu, log_pi, n_geno, (long long)M * S,
+      Cmax, G, density, precision, out);
+  PCB_LAUNCH_CHECK();
+  return PCB_OK;
+}
+
+int pcb_likelihood_grid_host(const int64_t* refc, const int64_t* altc, const double* tc, const int64_t* cn,
+                             const double* mu, const double* log_pi, const int32_t* n_geno, int64_t M, int32_t S,
+                             int32_t Cmax, int32_t G, int32_t density, double precision, double* out) {
+  if (!refc || !altc || !tc || !cn || !mu || !log_pi || !n_geno || !out) return fail(PCB_ERR_ARG, "likelihood_grid: null");
+  if (M <= 0) return PCB_OK;
+  HostScratch& hs = g_hs;
+  const size_t ms = (size_t)M * S;
+  const size_t b_counts = ms * 8, b_cn = ms * Cmax * 3 * 8, b_lp = ms * Cmax * 8, b_ng = ms * 4;
+  // one packed staging buffer: refc | altc | tc | cn | mu | log_pi | n_geno
+  const size_t total = 3 * b_counts + 2 * b_cn + b_lp + b_ng;
+  int rc;
+  if ((rc = hs.in.ensure(total))) return rc;
+  if ((rc = hs.out.ensure(ms * G * 8))) return rc;
+  char* d = hs.in.as<char>();
+  size_t o = 0;
+  auto put = [&](const void* src, size_t n) -> void* {
+    void* dst = d + o;
+    cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, 0);
+    o += n;
+    return dst;
+  };
+  auto* d_ref = (const int64_t*)put(refc, b_counts);
+  auto* d_alt = (const int64_t*)put(altc, b_counts);
+  auto* d_tc = (const double*)put(tc, b_counts);
+  auto* d_cn = (const int64_t*)put(cn, b_cn);
+  auto* d_mu = (const double*)put(mu, b_cn);
+  auto* d_lp = (const double*)put(log_pi, b_lp);
+  auto* d_ng = (const int32_t*)put(n_geno, b_ng);
+  PCB_CUDA(cudaGetLastError());
+  if ((rc = pcb_likelihood_grid_dev(d_ref, d_alt, d_tc, d_cn, d_mu, d_lp, d_ng, M, S, Cmax, G, density, precision,
+                                    hs.out.as<double>(), nullptr)))
+    return rc;
+  PCB_CUDA(cudaMemcpyAsync(out, hs.out.p, ms * G * 8, cudaMemcpyDeviceToHost, 0));
+  PCB_CUDA(cudaStreamSynchronize(0));
+  return PCB_OK;
+}
+
+int pcb_cluster_sum_host(const double* grids, const int64_t* cluster_off, int64_t K, int32_t S, int32_t G,
+                         double* out) {
+  if (!grids || !cluster_off || !out || K < 0) return fail(PCB_ERR_ARG, "cluster_sum: null pointer");
+  if (K == 0) return PCB_OK;
+  HostScratch& hs = g_hs;
+  const long long tile = (long long)S * G;
+  const int64_t M = cluster_off[K];
+  int rc;
+  if ((rc = hs.in.ensure((size_t)std::max<int64_t>(M, 1) * tile * 8))) return rc;
+  if ((rc = hs.out.ensure((size_t)K * tile * 8))) return rc;
+  if ((rc = hs.misc.ensure((size_t)(K + 1) * 8))) return rc;
+  PCB_CUDA(cudaMemcpyAsync(hs.in.p, grids, (size_t)M * tile * 8, cudaMemcpyHostToDevice, 0));
+  PCB_CUDA(cudaMemcpyAsync(hs.misc.p, cluster_off, (size_t)(K + 1) * 8, cudaMemcpyHostToDevice, 0));
+  const long long n = K * tile;
+  pcb::cluster_sum_kernel<<<(unsigned)((n + 255) / 256), 256>>>(hs.in.as<double>(), hs.misc.as<long long>(), K, tile,
+                                                                hs.out.as<double>());
+  PCB_LAUNCH_CHECK();
+  PCB_CUDA(cudaMemcpyAsync(out, hs.out.p, (size_t)n * 8, cudaMemcpyDeviceToHost, 0));
+  PCB_CUDA(cudaStreamSynchronize(0));
+  return PCB_OK;
+}
+
+int pcb_outlier_marginal_host(const double* values, int64_t K, int32_t S, int32_t G, double* out) {
+  if (!values || !out || K < 0) return fail(PCB_ERR_ARG, "outlier_marginal: null pointer");
+  if (K == 0) return PCB_OK;
+  HostScratch& hs = g_hs;
+  int rc;
+  if ((rc = hs.in.ensure((size_t)K * S * G * 8))) return rc;
+  if ((rc = hs.rows_a.ensure((size_t)K * S * 8))) return rc;
+  if ((rc = hs.misc.ensure((size_t)K * 8))) return rc;
+  PCB_CUDA(cudaMemcpyAsync(hs.in.p, values, (size_t)K * S * G * 8, cudaMemcpyHostToDevice, 0));
+  const long long warps = K * S;
+  const int wpb = 4;
+  pcb::outlier_marginal_rows_kernel<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, (size_t)wpb * G * 8>>>(
+      hs.in.as<double>(), K, S, G, hs.rows_a.as<double>());
+  PCB_LAUNCH_CHECK();
+  if ((rc = pcb_reduce_rows_dev(hs.rows_a.as<double>(), K, S, hs.misc.as<double>(), nullptr))) return rc;
+  PCB_CUDA(cudaMemcpyAsync(out, hs.misc.p, (size_t)K * 8, cudaMemcpyDeviceToHost, 0));
+  PCB_CUDA(cudaStreamSynchronize(0));
+  return PCB_OK;
+}
+
+int pcb_normalize_segments_dev(const double* log_p, const int64_t* seg_off_dev, int64_t U, double* log_q, double* q,
+                                double* log_norm, double* ess, void* stream) {
+  if (U <= 0) return PCB_OK;
+  if (!log_p || !seg_off_dev || !log_q || !q) return fail(PCB_ERR_ARG, "normalize_segments_dev: null pointer");
+  pcb::normalize_segments_kernel<<<(unsigned)U, 128, 0, (cudaStream_t)stream>>>(log_p, (const long long*)seg_off_dev,
+                                                                               log_q, q, log_norm, ess);
+  PCB_LAUNCH_CHECK();
+  return PCB_OK;
+}
+
+static int normalize_segments_impl(const double* log_p_host, const int64_t* seg_off, int64_t U, double* log_q,
+                                   double* q, double* log_norm, double* ess) {
+  HostScratch& hs = g_hs;
+  const int64_t n = seg_off[U];
+  int rc;
+  if ((rc = hs.in.ensure((size_t)std::max<int64_t>(n, 1) * 8))) return rc;
+  if ((rc = hs.out.ensure((size_t)std::max<int64_t>(n, 1) * 16))) return rc;
+  if ((rc = hs.misc.ensure((size_t)(U + 1) * 8 + (size_t)U * 16))) return rc;
+  PCB_CUDA(cudaMemcpyAsync(hs.in.p, log_p_host, (size_t)n * 8, cudaMemcpyHostToDevice, 0));
+  PCB_CUDA(cudaMemcpyAsync(hs.misc.p, seg_off, (size_t)(U + 1) * 8, cudaMemcpyHostToDevice, 0));
+  double* d_lq = hs.out.as<double>();
+  double* d_q = d_lq + n;
+  double* d_ln = (double*)(hs.misc.as<char>() + (size_t)(U + 1) * 8);
+  double* d_ess = d_ln + U;
+  pcb::normalize_segments_kernel<<<(unsigned)U, 128>>>(hs.in.as<double>(), hs.misc.as<long long>(), d_lq, d_q, d_ln,
+                                                       d_ess);
+  PCB_LAUNCH_CHECK();
+  if (log_q) PCB_CUDA(cudaMemcpyAsync(log_q, d_lq, (size_t)n * 8, cudaMemcpyDeviceToHost, 0));
+  if (q) PCB_CUDA(cudaMemcpyAsync(q, d_q, (size_t)n * 8, cudaMemcpyDeviceToHost, 0));
+  if (log_norm) PCB_CUDA(cudaMemcpyAsync(log_norm, d_ln, (size_t)U * 8, cudaMemcpyDeviceToHost, 0));
+  if (ess) PCB_CUDA(cudaMemcpyAsync(ess, d_ess, (size_t)U * 8, cudaMemcpyDeviceToHost, 0));
+  PCB_CUDA(cudaStreamSynchronize(0));
+  return PCB_OK;
+}
+
+int pcb_swarm_weights_host(const double* log_w, int64_t N, double* log_Z, double* log_W, double* W, double* ess) {
+  if (!log_w || N < 1) return fail(PCB_ERR_ARG, "swarm_weights: need N >= 1");
+  const int64_t off[2] = {0, N};
+  return normalize_segments_impl(log_w, off, 1, log_W, W, log_Z, ess);
+}
+
+int pcb_normalize_segments_host(const double* log_p, const int64_t* seg_off, int64_t U, double* log_q, double* q,
+                                double* log_norm) {
+  if (!log_p || !seg_off || U < 0) return fail(PCB_ERR_ARG, "normalize_segments: null pointer");
+  if (U == 0) return PCB_OK;
+  return normalize_segments_impl(log_p, seg_off, U, log_q, q, log_norm, nullptr);
+}
+
+int pcb_resample_host(const double* W, int64_t N, const double* uniforms, int64_t n_draws, int64_t* ancestors) {
+  if (!W || !uniforms || !ancestors || N < 1 || n_draws < 0) return fail(PCB_ERR_ARG, "resample: bad arguments");
+  if (n_draws == 0) return PCB_OK;
+  HostScratch& hs = g_hs;
+  int rc;
+  if ((rc = hs.in.ensure((size_t)(2 * N + n_draws) * 8))) return rc;
+  if ((rc = hs.out.ensure((size_t)n_draws * 8))) return rc;
+  double* dW = hs.in.as<double>();
+  double* dcdf = dW + N;
+  double* du = dcdf + N;
+  PCB_CUDA(cudaMemcpyAsync(dW, W, (size_t)N * 8, cudaMemcpyHostToDevice, 0));
+  PCB_CUDA(cudaMemcpyAsync(du, uniforms, (size_t)n_draws * 8, cudaMemcpyHostToDevice, 0));
+  pcb::resample_kernel<<<1, 1024>>>(dW, N, du, n_draws, hs.out.as<long long>(), dcdf);
+  PCB_LAUNCH_CHECK();
+  PCB_CUDA(cudaMemcpyAsync(ancestors, hs.out.p, (size_t)n_draws * 8, cudaMemcpyDeviceToHost, 0));
+  PCB_CUDA(cudaStreamSynchronize(0));
+  return PCB_OK;
+}
+
+int pcb_fp64_peak(int32_t iters, double* flops_per_s, double* elapsed_ms) {
+  if (!flops_per_s) return fail(PCB_ERR_ARG, "fp64_peak: null");
+  int dev = 0, sms = 0;
+  PCB_CUDA(cudaGetDevice(&dev));
+  PCB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  double* d = nullptr;
+  PCB_CUDA(cudaMalloc(&d, 8));
+  cudaEvent_t e0, e1;
+  PCB_CUDA(cudaEventCreate(&e0));
+  PCB_CUDA(cudaEventCreate(&e1));
+  const int blocks = sms * 8, threads = 256;
+  pcb::fp64_peak_kernel<<<blocks, threads>>>(d, 16, 1.0);  // warm-up
+  PCB_LAUNCH_CHECK();
+  PCB_CUDA(cudaEventRecord(e0));
+  pcb::fp64_peak_kernel<<<blocks, threads>>>(d, iters, 1.0);
+  PCB_LAUNCH_CHECK();
+  PCB_CUDA(cudaEventRecord(e1));
+  PCB_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  PCB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  const double fmas = (double)blocks * threads * (double)iters * 16.0 * 8.0;
+  *flops_per_s = 2.0 * fmas / (ms * 1e-3);
+  if (elapsed_ms) *elapsed_ms = ms;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  return PCB_OK;
+}
+
+}  // extern "C"

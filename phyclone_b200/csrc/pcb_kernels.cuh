@@ -1,0 +1,640 @@
+// sm_100a kernels for the PhyClone tree-node likelihood path.
+//
+// Data layout in HBM (see include/phyclone_b200.h): every tile is
+// kept twice, log domain (`lg`) and max-shifted linear domain (`lin` = exp(lg - rowmax)),
+// in a padded row layout [S][pitch] with `lead` zeros in front of each row and zeros
+// behind it.  A block of rows of one tile is therefore one contiguous 16-byte aligned
+// span that a single TMA bulk copy (cp.async.bulk, UBLKCP) drops into shared memory,
+// and the sliding-window convolution below needs no bounds checks.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "pcb_device.cuh"
+
+namespace pcb {
+
+constexpr double kFloor = 1e-100;  // tree/utils.py:77
+
+struct JobKernelParams {
+  const int32_t* jobs;      // [n_jobs][8]
+  const int32_t* children;  // flat child tile ids, fold order
+  double* lg;
+  double* lin;
+  double* rmax;
+  double* sc_lse;   // [slots][S]
+  double* sc_last;  // [slots][S]
+  long long tile_elems;
+  double prior;
+  int S, G, Q, U, P, pitch, lead, RB, row_blocks;
+};
+
+// ---------------------------------------------------------------------------------
+// One strip of L consecutive outputs k0..k0+L-1 of   y[k] = sum_{j<=k} b[j] * a[k-j].
+// The L values a[k0+i-j] live in a register window that slides by one element per j;
+// unrolling the j loop by L makes every register index static.  Per j: one broadcast
+// load of b[j], one load of the element entering the window, L DFMAs.
+// `a` has >= L zeros in front (index -L..-1) and zeros from G up to the strip end.
+// ---------------------------------------------------------------------------------
+template <int L>
+__device__ __forceinline__ void conv_strip(const double* __restrict__ a, const double* __restrict__ b, int k0, int G,
+                                           double (&acc)[L]) {
+  double w[L];
+#pragma unroll
+  for (int i = 0; i < L; ++i) {
+    w[i] = a[k0 + i];
+    acc[i] = 0.0;
+  }
+  const int steps = min(k0 + L, G);  // j = 0 .. steps-1
+  const int full = steps / L;
+  const double* an = a + k0 - 1;  // element entering the window at step j is an[-j]
+  int j = 0;
+  for (int it = 0; it < full; ++it, j += L) {
+#pragma unroll
+    for (int p = 0; p < L; ++p) {
+      const double bj = b[j + p];
+#pragma unroll
+      for (int i = 0; i < L; ++i) acc[i] = fma(bj, w[(i - p + L) % L], acc[i]);
+      w[L - 1 - p] = an[-(j + p)];
+    }
+  }
+  const int rem = steps - j;  // < L, only for the last (partial) strip
+#pragma unroll
+  for (int p = 0; p < L; ++p) {
+    if (p < rem) {
+      const double bj = b[j + p];
+#pragma unroll
+      for (int i = 0; i < L; ++i) acc[i] = fma(bj, w[(i - p + L) % L], acc[i]);
+      w[L - 1 - p] = an[-(j + p)];
+    }
+  }
+}
+
+// Robust prefix log-sum-exp of one row held in shared memory (`x`, length G), done by the
+// P lanes of the row group; writes prefix[k] into `out` (may alias x).  Equivalent to
+// np.logaddexp.accumulate (tree/utils.py:29) up to O(G*eps).
+__device__ __forceinline__ void row_prefix_lse(const double* x, double* out, int G, int P, int lir, bool row_ok) {
+  const int chunk = (G + P - 1) / P;
+  const int kbeg = min(G, lir * chunk), kend = min(G, kbeg + chunk);
+  LsePair loc{-INFINITY, 0.0};
+  if (row_ok)
+    for (int k = kbeg; k < kend; ++k) loc = lse_combine(loc, LsePair{x[k], 1.0});
+  // inclusive scan of pairs over the group, then shift to exclusive
+  LsePair inc = loc;
+  for (int off = 1; off < P; off <<= 1) {
+    LsePair o;
+    o.m = __shfl_up_sync(0xffffffffu, inc.m, off);
+    o.s = __shfl_up_sync(0xffffffffu, inc.s, off);
+    if (lir >= off) inc = lse_combine(o, inc);
+  }
+  LsePair run;
+  run.m = __shfl_up_sync(0xffffffffu, inc.m, 1);
+  run.s = __shfl_up_sync(0xffffffffu, inc.s, 1);
+  if (lir == 0) run = LsePair{-INFINITY, 0.0};
+  if (row_ok)
+    for (int k = kbeg; k < kend; ++k) {
+      run = lse_combine(run, LsePair{x[k], 1.0});
+      out[k] = (run.m == -INFINITY) ? -INFINITY : run.m + log(run.s);
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// node_jobs_kernel: one CTA per (job, row block).  See phyclone_b200.h for the job
+// record.  Shared memory: 4 mbarriers + two accumulator buffers + two operand buffers,
+// each RB*pitch doubles.
+// ---------------------------------------------------------------------------------
+template <int L>
+__global__ void node_jobs_kernel(const JobKernelParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  const int rows_elems = p.RB * p.pitch;
+  double* bufA0 = reinterpret_cast<double*>(smem_raw + 64);
+  double* bufA1 = bufA0 + rows_elems;
+  double* bufB0 = bufA1 + rows_elems;
+  double* bufB1 = bufB0 + rows_elems;
+
+  const int job = blockIdx.x / p.row_blocks;
+  const int rb = blockIdx.x - job * p.row_blocks;
+  const int32_t* jr = p.jobs + (size_t)job * 8;
+  const int coff = jr[0], C = jr[1], base = jr[2], outt = jr[3], flags = jr[4], slot = jr[5];
+  const int r0 = rb * p.RB;
+  const int nrows = min(p.RB, p.S - r0);
+  const int P = p.P, G = p.G, pitch = p.pitch, lead = p.lead;
+  const int tid = threadIdx.x;
+  const int lrow = tid / P;
+  const int lir = tid & (P - 1);
+  const bool row_ok = lrow < nrows;
+  const int row = r0 + lrow;
+  const uint32_t bytes = (uint32_t)nrows * pitch * 8u;
+  const bool scan = flags & 1;
+  const double addc = (flags & 2) ? p.prior : 0.0;
+  const bool shortcut = scan && base < 0 && outt < 0;
+
+  for (int i = tid; i < rows_elems; i += blockDim.x) bufA1[i] = 0.0;
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const int c0 = p.children[coff];
+  if (tid == 0) {
+    mbar_expect_tx(&bars[0], bytes);
+    tma_load_1d(bufA0, p.lin + (size_t)c0 * p.tile_elems + (size_t)r0 * pitch, bytes, &bars[0]);
+    if (C >= 2) {
+      const int c1 = p.children[coff + 1];
+      mbar_expect_tx(&bars[1], bytes);
+      tma_load_1d(bufB0, p.lin + (size_t)c1 * p.tile_elems + (size_t)r0 * pitch, bytes, &bars[1]);
+    } else if (!shortcut) {
+      mbar_expect_tx(&bars[1], bytes);
+      tma_load_1d(bufB0, p.lg + (size_t)c0 * p.tile_elems + (size_t)r0 * pitch, bytes, &bars[1]);
+    }
+  }
+
+  double M = row_ok ? p.rmax[(size_t)c0 * p.S + row] : 0.0;
+  mbar_wait(&bars[0], 0);
+
+  // ---- left fold over the children (tree/utils.py:33-47) --------------------------
+  for (int j = 1; j < C; ++j) {
+    double* Ain = (j & 1) ? bufA0 : bufA1;
+    double* Aout = (j & 1) ? bufA1 : bufA0;
+    double* Bcur = (j & 1) ? bufB0 : bufB1;
+    uint64_t* bbar = (j & 1) ? &bars[1] : &bars[2];
+    mbar_wait(bbar, ((j - 1) >> 1) & 1);
+    if (j + 1 < C && tid == 0) {  // prefetch the next operand; its buffer was released by the
+      double* Bnext = (j & 1) ? bufB1 : bufB0;  // __syncthreads that closed step j-1
+      uint64_t* nbar = (j & 1) ? &bars[2] : &bars[1];
+      const int cn = p.children[coff + j + 1];
+      mbar_expect_tx(nbar, bytes);
+      tma_load_1d(Bnext, p.lin + (size_t)cn * p.tile_elems + (size_t)r0 * pitch, bytes, nbar);
+    }
+    const double* a_row = Ain + lrow * pitch + lead;
+    const double* b_row = Bcur + lrow * pitch + lead;
+    double* o_row = Aout + lrow * pitch + lead;
+    double lmax = 0.0;
+    if (row_ok) {
+      for (int u = lir; u < p.U; u += P) {
+        const int q1 = u, q2 = p.Q - 1 - u;
+        double acc[L];
+        conv_strip<L>(a_row, b_row, q1 * L, G, acc);
+#pragma unroll
+        for (int i = 0; i < L; ++i) {
+          const int k = q1 * L + i;
+          if (k < G) {
+            double y = acc[i];
+            if (y <= 0.0) y = kFloor;
+            o_row[k] = y;
+            lmax = fmax(lmax, y);
+          }
+        }
+        if (q2 != q1) {
+          conv_strip<L>(a_row, b_row, q2 * L, G, acc);
+#pragma unroll
+          for (int i = 0; i < L; ++i) {
+            const int k = q2 * L + i;
+            if (k < G) {
+              double y = acc[i];
+              if (y <= 0.0) y = kFloor;
+              o_row[k] = y;
+              lmax = fmax(lmax, y);
+            }
+          }
+        }
+      }
+    }
+    const double ymax = group_max(lmax, P);
+    const double mB = row_ok ? p.rmax[(size_t)p.children[coff + j] * p.S + row] : 0.0;
+    if (j < C - 1) {
+      // re-normalise the running product exactly where the reference re-max-shifts it
+      M += mB + log(ymax);
+      if (row_ok) {
+        const bool tiny = !(ymax >= 1e-290);
+        const double inv = 1.0 / ymax;
+        for (int u = lir; u < p.U; u += P) {
+          const int q1 = u, q2 = p.Q - 1 - u;
+#pragma unroll
+          for (int i = 0; i < L; ++i) {
+            const int k = q1 * L + i;
+            if (k < G) o_row[k] = tiny ? o_row[k] / ymax : o_row[k] * inv;
+          }
+          if (q2 != q1) {
+#pragma unroll
+            for (int i = 0; i < L; ++i) {
+              const int k = q2 * L + i;
+              if (k < G) o_row[k] = tiny ? o_row[k] / ymax : o_row[k] * inv;
+            }
+          }
+        }
+      }
+    } else {
+      M += mB;
+    }
+    __syncthreads();
+  }
+
+  double* yrow = ((C >= 2 && ((C - 1) & 1)) ? bufA1 : bufA0) + lrow * pitch + lead;
+
+  // ---- epilogue 1: dummy-root scoring without materialising the tile --------------
+  if (shortcut) {
+    double t1 = 0.0, t2 = 0.0;
+    if (row_ok)
+      for (int k = lir; k < G; k += P) {
+        const double y = yrow[k];
+        t1 += y;
+        t2 = fma((double)(G - k), y, t2);
+      }
+    t1 = group_sum(t1, P);
+    t2 = group_sum(t2, P);
+    if (row_ok && lir == 0 && slot >= 0) {
+      p.sc_lse[(size_t)slot * p.S + row] = (M + addc) + log(t2);
+      p.sc_last[(size_t)slot * p.S + row] = (M + addc) + log(t1);
+    }
+    return;
+  }
+
+  // ---- epilogue 2: elementwise log_D / log_S, + log_p, store tile, optional scores --
+  if (C >= 2) {
+    if (scan) {
+      const int chunk = (G + P - 1) / P;
+      const int kbeg = min(G, lir * chunk), kend = min(G, kbeg + chunk);
+      double loc = 0.0;
+      if (row_ok)
+        for (int k = kbeg; k < kend; ++k) loc += yrow[k];
+      double run = group_excl_scan(loc, P, lir);
+      if (row_ok)
+        for (int k = kbeg; k < kend; ++k) {
+          run += yrow[k];
+          yrow[k] = log(run) + M;
+        }
+    } else if (row_ok) {
+      for (int k = lir; k < G; k += P) yrow[k] = log(yrow[k]) + M;
+    }
+  } else {
+    mbar_wait(&bars[1], 0);
+    const double* lrow_ptr = bufB0 + lrow * pitch + lead;
+    if (scan) {
+      row_prefix_lse(lrow_ptr, yrow, G, P, lir, row_ok);
+    } else if (row_ok) {
+      for (int k = lir; k < G; k += P) yrow[k] = lrow_ptr[k];
+    }
+  }
+  __syncwarp();
+
+  double vmax = -INFINITY;
+  if (row_ok) {
+    const double* bptr = (base >= 0) ? p.lg + (size_t)base * p.tile_elems + (size_t)row * pitch + lead : nullptr;
+    for (int k = lir; k < G; k += P) {
+      double v = yrow[k];
+      if (bptr) v = bptr[k] + v;
+      v += addc;
+      yrow[k] = v;
+      vmax = fmax(vmax, v);
+    }
+  }
+  vmax = group_max(vmax, P);
+  double esum = 0.0;
+  if (row_ok) {
+    double* olg = (outt >= 0) ? p.lg + (size_t)outt * p.tile_elems + (size_t)row * pitch + lead : nullptr;
+    double* olin = (outt >= 0) ? p.lin + (size_t)outt * p.tile_elems + (size_t)row * pitch + lead : nullptr;
+    for (int k = lir; k < G; k += P) {
+      const double v = yrow[k];
+      const double e = (v == -INFINITY) ? 0.0 : exp(v - vmax);
+      esum += e;
+      if (olg) {
+        olg[k] = v;
+        olin[k] = e;
+      }
+    }
+  }
+  esum = group_sum(esum, P);
+  __syncwarp();
+  if (row_ok && lir == 0) {
+    if (outt >= 0) p.rmax[(size_t)outt * p.S + row] = vmax;
+    if (slot >= 0) {
+      p.sc_lse[(size_t)slot * p.S + row] = (vmax == -INFINITY) ? -INFINITY : vmax + log(esum);
+      p.sc_last[(size_t)slot * p.S + row] = yrow[G - 1];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// Elementwise tile kernels.  One P-lane... one warp per (tile, row).
+// ---------------------------------------------------------------------------------
+// dense [n][S][G] -> arena (lg, lin, rmax) at ids[n]
+__global__ void import_tiles_kernel(const double* __restrict__ dense, const int32_t* __restrict__ ids, long long n,
+                                    double* lg, double* lin, double* rmax, int S, int G, int pitch, int lead,
+                                    long long tile_elems) {
+  const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (wid >= n * S) return;
+  const long long t = wid / S;
+  const int s = (int)(wid - t * S);
+  const double* src = dense + (t * S + s) * (long long)G;
+  const long long dst = (long long)ids[t] * tile_elems + (long long)s * pitch + lead;
+  double m = -INFINITY;
+  for (int k = lane; k < G; k += 32) m = fmax(m, src[k]);
+  m = group_max(m, 32);
+  for (int k = lane; k < G; k += 32) {
+    const double v = src[k];
+    lg[dst + k] = v;
+    lin[dst + k] = (v == -INFINITY) ? 0.0 : exp(v - m);
+  }
+  if (lane == 0) rmax[(long long)ids[t] * S + s] = m;
+}
+
+__global__ void export_tiles_kernel(const double* __restrict__ lg, const int32_t* __restrict__ ids, long long n,
+                                    double* __restrict__ dense, int S, int G, int pitch, int lead,
+                                    long long tile_elems) {
+  const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (wid >= n * S) return;
+  const long long t = wid / S;
+  const int s = (int)(wid - t * S);
+  const double* src = lg + (long long)ids[t] * tile_elems + (long long)s * pitch + lead;
+  double* dst = dense + (t * S + s) * (long long)G;
+  for (int k = lane; k < G; k += 32) dst[k] = src[k];
+}
+
+// out = a (+ b) + addend, refresh lin / rmax      (tree/tree_node.py:42-52)
+__global__ void tile_add_kernel(const int32_t* __restrict__ a_ids, const int32_t* __restrict__ b_ids,
+                                const int32_t* __restrict__ out_ids, long long n, double addend, double* lg,
+                                double* lin, double* rmax, int S, int G, int pitch, int lead, long long tile_elems) {
+  const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (wid >= n * S) return;
+  const long long t = wid / S;
+  const int s = (int)(wid - t * S);
+  const long long off = (long long)s * pitch + lead;
+  const double* pa = lg + (long long)a_ids[t] * tile_elems + off;
+  const int bid = b_ids ? b_ids[t] : -1;
+  const double* pb = bid >= 0 ? lg + (long long)bid * tile_elems + off : nullptr;
+  const long long o = (long long)out_ids[t] * tile_elems + off;
+  double m = -INFINITY;
+  // first pass keeps the sums in registers for up to 8 elements per lane (G <= 256); otherwise recompute
+  for (int k = lane; k < G; k += 32) {
+    double v = pa[k];
+    if (pb) v += pb[k];
+    v += addend;
+    m = fmax(m, v);
+  }
+  m = group_max(m, 32);
+  for (int k = lane; k < G; k += 32) {
+    double v = pa[k];
+    if (pb) v += pb[k];
+    v += addend;
+    lg[o + k] = v;
+    lin[o + k] = (v == -INFINITY) ? 0.0 : exp(v - m);
+  }
+  if (lane == 0) rmax[(long long)out_ids[t] * S + s] = m;
+}
+
+// out[slot] = sum_{s=0}^{S-1} rows[slot][s], sequentially (tree/distributions.py:197-200 loop order)
+__global__ void reduce_rows_kernel(const double* __restrict__ rows, long long n, int S, double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double acc = 0.0;
+  for (int s = 0; s < S; ++s) acc += rows[i * S + s];
+  out[i] = acc;
+}
+
+// root data terms straight from dense tiles: one warp per (tile,row)   (tree/distributions.py:197-200)
+__global__ void root_terms_rows_kernel(const double* __restrict__ dense, long long n, int S, int G,
+                                       double* __restrict__ lse_rows, double* __restrict__ last_rows) {
+  const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (wid >= n * S) return;
+  const double* src = dense + wid * (long long)G;
+  double m = -INFINITY;
+  for (int k = lane; k < G; k += 32) m = fmax(m, src[k]);
+  m = group_max(m, 32);
+  double e = 0.0;
+  if (m != -INFINITY && m != INFINITY)
+    for (int k = lane; k < G; k += 32) e += exp(src[k] - m);
+  e = group_sum(e, 32);
+  if (lane == 0) {
+    lse_rows[wid] = (m == -INFINITY || m == INFINITY) ? m : log(e) + m;
+    last_rows[wid] = src[G - 1];
+  }
+}
+
+// DataPoint.outlier_marginal_prob rows: LSE_g( prefixLSE_g(value + lp) + lp )   (data/base.py:31-37)
+__global__ void outlier_marginal_rows_kernel(const double* __restrict__ dense, long long n, int S, int G,
+                                             double* __restrict__ out_rows) {
+  extern __shared__ double sh[];
+  const int wpb = blockDim.x >> 5;
+  const int wl = threadIdx.x >> 5;
+  const long long wid = (long long)blockIdx.x * wpb + wl;
+  const int lane = threadIdx.x & 31;
+  const bool ok = wid < n * S;
+  double* x = sh + (size_t)wl * G;
+  const double lp = -log((double)G);
+  if (ok)
+    for (int k = lane; k < G; k += 32) x[k] = dense[wid * (long long)G + k] + lp;
+  __syncwarp();
+  row_prefix_lse(x, x, G, 32, lane, ok);
+  __syncwarp();
+  double m = -INFINITY;
+  if (ok)
+    for (int k = lane; k < G; k += 32) {
+      x[k] += lp;
+      m = fmax(m, x[k]);
+    }
+  m = group_max(m, 32);
+  double e = 0.0;
+  if (ok && m != -INFINITY)
+    for (int k = lane; k < G; k += 32) e += exp(x[k] - m);
+  e = group_sum(e, 32);
+  if (ok && lane == 0) out_rows[wid] = (m == -INFINITY) ? m : log(e) + m;
+}
+
+// value[k] = sum over member grids in order   (data/pyclone.py:94, np.sum(axis=0))
+__global__ void cluster_sum_kernel(const double* __restrict__ grids, const long long* __restrict__ off, long long K,
+                                   long long tile, double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K * tile) return;
+  const long long k = i / tile, e = i - k * tile;
+  double acc = 0.0;
+  for (long long m = off[k]; m < off[k + 1]; ++m) acc += grids[m * tile + e];
+  out[i] = acc;
+}
+
+// ---------------------------------------------------------------------------------
+// likelihood grid: one thread per (mutation, sample, grid point)   (data/pyclone.py:339-436)
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ double dev_log_beta(double a, double b) {  // utils/math.py:131-136
+  if (a <= 0.0 || b <= 0.0) return -INFINITY;
+  return lgamma(a) + lgamma(b) - lgamma(a + b);
+}
+
+__global__ void likelihood_grid_kernel(const long long* __restrict__ refc, const long long* __restrict__ altc,
+                                       const double* __restrict__ tc, const long long* __restrict__ cn,
+                                       const double* __restrict__ mu, const double* __restrict__ log_pi,
+                                       const int* __restrict__ n_geno, long long MS, int Cmax, int G, int density,
+                                       double precision, double* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= MS * G) return;
+  const long long ms = idx / G;
+  const int g = (int)(idx - ms * G);
+  // np.linspace(0, 1, G): i * step with the end point pinned to 1.0
+  const double f = (g == G - 1) ? 1.0 : (double)g * (1.0 / (double)(G - 1));
+  const double t = tc[ms];
+  const double w0 = 1.0 - t, w1 = t * (1.0 - f), w2 = t * f;
+  const double a = (double)refc[ms], b = (double)altc[ms];
+  const double n = a + b, x = b;
+  const double log_coeff = lgamma(n + 1.0) - lgamma(x + 1.0) - lgamma(n - x + 1.0);
+  const int C = n_geno[ms];
+  double m = -INFINITY, ssum = 0.0;
+  for (int c = 0; c < C; ++c) {
+    const long long o = (ms * Cmax + c) * 3;
+    double e_vaf = 0.0, norm = 0.0, e_cn;
+    e_cn = w0 * (double)cn[o + 0];
+    e_vaf += e_cn * mu[o + 0];
+    norm += e_cn;
+    e_cn = w1 * (double)cn[o + 1];
+    e_vaf += e_cn * mu[o + 1];
+    norm += e_cn;
+    e_cn = w2 * (double)cn[o + 2];
+    e_vaf += e_cn * mu[o + 2];
+    norm += e_cn;
+    e_vaf /= norm;
+    double ll;
+    if (density == 1) {
+      const double aa = e_vaf * precision;
+      const double bb = precision - aa;
+      ll = log_coeff + (dev_log_beta(aa + x, bb + n - x) - dev_log_beta(aa, bb));
+    } else {
+      double body;
+      if (e_vaf == 0.0)
+        body = (x == 0.0) ? 0.0 : -INFINITY;
+      else if (e_vaf == 1.0)
+        body = (x == n) ? 0.0 : -INFINITY;
+      else
+        body = x * log(e_vaf) + (n - x) * log(1.0 - e_vaf);
+      ll = log_coeff + body;
+    }
+    ll += log_pi[ms * Cmax + c];
+    // online log-sum-exp over genotypes (utils/math.py:102-118)
+    if (ll > m) {
+      ssum = (m == -INFINITY) ? 1.0 : ssum * exp(m - ll) + 1.0;
+      m = ll;
+    } else if (ll != -INFINITY) {
+      ssum += exp(ll - m);
+    }
+  }
+  out[idx] = (m == -INFINITY || m == INFINITY) ? m : log(ssum) + m;
+}
+
+// ---------------------------------------------------------------------------------
+// particle weights / candidate normalisation: one CTA per vector segment
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ double block_reduce(double v, bool is_max, double* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = is_max ? group_max(v, 32) : group_sum(v, 32);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  double r = is_max ? -INFINITY : 0.0;
+  for (int i = 0; i < nw; ++i) r = is_max ? fmax(r, sh[i]) : r + sh[i];
+  return r;
+}
+
+// segment u: x = log_p[off[u]..off[u+1]);  log_q = x - LSE(x); q = exp(log_q)/sum; optionally ESS
+__global__ void normalize_segments_kernel(const double* __restrict__ x, const long long* __restrict__ off,
+                                          double* __restrict__ log_q, double* __restrict__ q,
+                                          double* __restrict__ log_norm, double* __restrict__ ess) {
+  __shared__ double sh[32];
+  const long long beg = off[blockIdx.x], end = off[blockIdx.x + 1];
+  double m = -INFINITY;
+  for (long long i = beg + threadIdx.x; i < end; i += blockDim.x) m = fmax(m, x[i]);
+  m = block_reduce(m, true, sh);
+  double e = 0.0;
+  if (m != -INFINITY && m != INFINITY)
+    for (long long i = beg + threadIdx.x; i < end; i += blockDim.x) e += exp(x[i] - m);
+  e = block_reduce(e, false, sh);
+  const double ln = (m == -INFINITY || m == INFINITY) ? m : log(e) + m;
+  double qs = 0.0;
+  for (long long i = beg + threadIdx.x; i < end; i += blockDim.x) {
+    const double lq = x[i] - ln;
+    log_q[i] = lq;
+    qs += exp(lq);
+  }
+  qs = block_reduce(qs, false, sh);
+  double sq = 0.0;
+  for (long long i = beg + threadIdx.x; i < end; i += blockDim.x) {
+    const double w = exp(log_q[i]) / qs;
+    q[i] = w;
+    sq = fma(w, w, sq);
+  }
+  sq = block_reduce(sq, false, sh);
+  if (threadIdx.x == 0) {
+    if (log_norm) log_norm[blockIdx.x] = ln;
+    if (ess) ess[blockIdx.x] = 1.0 / sq;
+  }
+}
+
+// inverse-CDF ancestors from supplied uniforms (optional device resampling mode)
+__global__ void resample_kernel(const double* __restrict__ W, long long N, const double* __restrict__ u,
+                                long long n_draws, long long* __restrict__ anc, double* __restrict__ cdf) {
+  // single CTA: sequential-chunk inclusive scan into cdf (global scratch), then binary search
+  __shared__ double sh[1024];
+  const int T = blockDim.x;
+  const long long chunk = (N + T - 1) / T;
+  const long long beg = min(N, (long long)threadIdx.x * chunk), end = min(N, beg + chunk);
+  double loc = 0.0;
+  for (long long i = beg; i < end; ++i) loc += W[i];
+  sh[threadIdx.x] = loc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double run = 0.0;
+    for (int i = 0; i < T; ++i) {
+      const double v = sh[i];
+      sh[i] = run;
+      run += v;
+    }
+  }
+  __syncthreads();
+  double run = sh[threadIdx.x];
+  for (long long i = beg; i < end; ++i) {
+    run += W[i];
+    cdf[i] = run;
+  }
+  __syncthreads();
+  for (long long d = threadIdx.x; d < n_draws; d += T) {
+    const double v = u[d];
+    long long lo = 0, hi = N - 1;  // last bucket catches everything (cdf[N-1] treated as +inf)
+    while (lo < hi) {
+      const long long mid = (lo + hi) >> 1;
+      if (cdf[mid] > v)
+        hi = mid;
+      else
+        lo = mid + 1;
+    }
+    anc[d] = lo;
+  }
+}
+
+// dependent DFMA chains: the measured FP64 roofline denominator
+__global__ void fp64_peak_kernel(double* out, int iters, double seed) {
+  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+         a7 = a0 + 7;
+  const double b = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      a0 = fma(a0, b, c);
+      a1 = fma(a1, b, c);
+      a2 = fma(a2, b, c);
+      a3 = fma(a3, b, c);
+      a4 = fma(a4, b, c);
+      a5 = fma(a5, b, c);
+      a6 = fma(a6, b, c);
+      a7 = fma(a7, b, c);
+    }
+  }
+  const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (s == 123.456) out[0] = s;
+}
+
+}  // namespace pcb

@@ -1,0 +1,156 @@
+"""Device-resident tile arena + batched node-refresh jobs (host side of the hot path).
+
+PyTorch is used only as plumbing here: it owns the HBM allocations and the CUDA stream; all
+arithmetic is done by the kernels behind the C ABI (`pcb_*_dev` entry points).
+
+Tiles live in HBM in the padded layout described in include/phyclone_b200.h.  Tile ids are
+plain integers managed by the caller (see `TileAllocator`).
+"""
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+JOB_SCAN = 1
+JOB_ADD_PRIOR = 2
+JOB_INTS = 8
+
+
+class TileAllocator:
+    """Bump allocator over arena slots with a permanent prefix and a resettable region."""
+
+    def __init__(self, capacity):
+        self.capacity = capacity
+        self.permanent = 0
+        self.top = 0
+
+    def alloc(self, n=1):
+        first = self.top
+        self.top += n
+        if self.top > self.capacity:
+            raise _lib.PcbError("tile arena exhausted (%d slots)" % self.capacity)
+        return first
+
+    def freeze(self):
+        """Everything allocated so far survives `reset()`."""
+        self.permanent = self.top
+
+    def reset(self):
+        self.top = self.permanent
+
+
+class DeviceArena:
+    def __init__(self, S, G, capacity, device=None, variant=-1):
+        self.lib = _lib.require_device()
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        self.layout = _lib.Layout()
+        _lib.check(self.lib.pcb_make_layout(S, G, variant, C.byref(self.layout)))
+        self.S, self.G = S, G
+        self.capacity = int(capacity)
+        pitch = self.layout.pitch
+        with torch.cuda.device(self.device):
+            # pads must be (and stay) zero: kernels only ever write the G payload columns
+            self.lg = torch.zeros((self.capacity, S, pitch), dtype=torch.float64, device=self.device)
+            self.lin = torch.zeros((self.capacity, S, pitch), dtype=torch.float64, device=self.device)
+            self.rmax = torch.zeros((self.capacity, S), dtype=torch.float64, device=self.device)
+        self.c = _lib.Arena(self.layout, self.lg.data_ptr(), self.lin.data_ptr(), self.rmax.data_ptr(), self.capacity)
+        self.alloc = TileAllocator(self.capacity)
+        self.prior = -float(np.log(G))
+        self._staging = {}
+
+    # ---------------------------------------------------------------- plumbing
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _to_dev_i32(self, arr, key):
+        """Host int32 array -> device tensor through a reusable pinned staging buffer."""
+        arr = np.ascontiguousarray(arr, dtype=np.int32).reshape(-1)
+        n = arr.shape[0]
+        st = self._staging.get(key)
+        if st is None or st[0].shape[0] < n:
+            cap = max(1024, int(n * 1.5))
+            st = (
+                torch.empty(cap, dtype=torch.int32, pin_memory=True),
+                torch.empty(cap, dtype=torch.int32, device=self.device),
+                torch.cuda.Event(),
+            )
+            self._staging[key] = st
+        else:
+            st[2].synchronize()  # the previous async copy out of this pinned buffer must have drained
+        host, dev, ev = st
+        host.numpy()[:n] = arr
+        dev[:n].copy_(host[:n], non_blocking=True)
+        ev.record(torch.cuda.current_stream(self.device))
+        return dev
+
+    # ------------------------------------------------------------------- tiles
+    def import_tiles(self, dense, ids):
+        """dense: [n,S,G] numpy (host) or CUDA tensor of log tiles -> arena slots `ids`."""
+        if isinstance(dense, np.ndarray):
+            dense = torch.from_numpy(np.ascontiguousarray(dense, dtype=np.float64)).to(self.device)
+        dense = dense.contiguous()
+        n = dense.shape[0]
+        assert dense.shape[1:] == (self.S, self.G) and len(ids) == n
+        ids_dev = self._to_dev_i32(ids, "ids")
+        _lib.check(
+            self.lib.pcb_arena_import_dev(C.byref(self.c), dense.data_ptr(), ids_dev.data_ptr(), n, self._stream())
+        )
+        self._keep = dense  # keep alive until the stream has consumed it
+
+    def export_tiles(self, ids):
+        n = len(ids)
+        out = torch.empty((n, self.S, self.G), dtype=torch.float64, device=self.device)
+        ids_dev = self._to_dev_i32(ids, "ids")
+        _lib.check(self.lib.pcb_arena_export_dev(C.byref(self.c), ids_dev.data_ptr(), n, out.data_ptr(), self._stream()))
+        return out
+
+    def tile_add(self, a_ids, b_ids, out_ids, addend=0.0):
+        """out = a (+ b) + addend in the log domain; refreshes lin / rmax of `out`."""
+        n = len(out_ids)
+        if n == 0:
+            return
+        a = self._to_dev_i32(a_ids, "add_a")
+        o = self._to_dev_i32(out_ids, "add_o")
+        b_ptr = None
+        if b_ids is not None:
+            b_ptr = self._to_dev_i32(b_ids, "add_b").data_ptr()
+        _lib.check(
+            self.lib.pcb_tile_add_dev(C.byref(self.c), a.data_ptr(), b_ptr, o.data_ptr(), n, float(addend), self._stream())
+        )
+
+    # -------------------------------------------------------------------- jobs
+    def run_jobs(self, jobs, children, n_slots=0):
+        """Enqueue node-refresh jobs.  jobs: int32 [n,8]; children: int32 flat tile ids.
+
+        Returns (lse_sum, last_sum) CUDA tensors of length n_slots (or None)."""
+        jobs = np.ascontiguousarray(jobs, dtype=np.int32).reshape(-1, JOB_INTS)
+        n = jobs.shape[0]
+        if n == 0:
+            return None
+        jd = self._to_dev_i32(jobs, "jobs")
+        cd = self._to_dev_i32(children if len(children) else np.zeros(1, np.int32), "kids")
+        rows_l = rows_t = None
+        pl = pt = None
+        if n_slots:
+            rows_l = torch.empty((n_slots, self.S), dtype=torch.float64, device=self.device)
+            rows_t = torch.empty((n_slots, self.S), dtype=torch.float64, device=self.device)
+            pl, pt = rows_l.data_ptr(), rows_t.data_ptr()
+        _lib.check(
+            self.lib.pcb_node_jobs_dev(C.byref(self.c), jd.data_ptr(), cd.data_ptr(), n, self.prior, pl, pt, self._stream())
+        )
+        if not n_slots:
+            return None
+        out = torch.empty((2, n_slots), dtype=torch.float64, device=self.device)
+        st = self._stream()
+        _lib.check(self.lib.pcb_reduce_rows_dev(rows_l.data_ptr(), n_slots, self.S, out[0].data_ptr(), st))
+        _lib.check(self.lib.pcb_reduce_rows_dev(rows_t.data_ptr(), n_slots, self.S, out[1].data_ptr(), st))
+        return out
+
+
+def make_job(child_off, n_children, base=-1, out=-1, flags=JOB_SCAN, slot=-1):
+    return (child_off, n_children, base, out, flags, slot, 0, 0)
