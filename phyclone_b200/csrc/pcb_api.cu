@@ -45,9 +45,11 @@ int fill_layout(int S, int G, int L, int P, pcb_layout* out) {
   if (!okL || (P != 4 && P != 8 && P != 16 && P != 32)) return fail(PCB_ERR_ARG, "layout: unsupported strip/lanes");
   const int Q = (G + L - 1) / L;
   int pitch = L + Q * L;
-  const int want = (P == 4) ? 4 : 8;  // bank rule: rows sharing a half-warp must not collide
+  int want = (P == 4) ? 4 : 8;  // bank rule: rows sharing a half-warp must not collide
+  if (const char* e = getenv("PCB_PITCH_MOD")) want = atoi(e);  // tuning knob
   while (pitch % 16 != want) ++pitch;
   int RB = std::min(S, std::max(1, 64 / P));
+  if (const char* e = getenv("PCB_CTA_THREADS")) RB = std::min(S, std::max(1, atoi(e) / P));  // tuning knob
   // keep at least one full warp per CTA but stay under 48 KB of shared memory when possible
   while (RB * P > 32 && 64 + 4ll * RB * pitch * 8 > 48 * 1024) RB = (RB + 1) / 2;
   while (RB > 1 && 64 + 4ll * RB * pitch * 8 > 200 * 1024) RB = (RB + 1) / 2;

@@ -62,7 +62,9 @@ __device__ __forceinline__ double group_excl_scan(double v, int P, int lane_in_g
     double o = __shfl_up_sync(0xffffffffu, incl, off);
     if (lane_in_group >= off) incl += o;
   }
-  return incl - v;
+  // shift rather than subtract: `incl - v` cancels catastrophically when v dwarfs the prefix
+  const double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+  return lane_in_group == 0 ? 0.0 : excl;
 }
 
 // (m, s) pairs representing log(sum) = m + log(s); combine is associative

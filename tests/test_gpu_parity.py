@@ -25,7 +25,7 @@ def _conv_cases(golden):
     return sorted(k[len("conv_out_"):] for k in golden.files if k.startswith("conv_out_"))
 
 
-VARIANTS = ["", "507", "708", "716", "908", "1304", "1308", "1316", "732"]
+VARIANTS = ["", "508", "708", "716", "908", "1304", "1308", "1316", "732"]
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
