@@ -36,24 +36,24 @@ int fail(int code, const std::string& msg) {
   } while (0)
 
 // ---- layout -------------------------------------------------------------------
-const int kStrips[] = {5, 7, 9, 13};
+const int kStrips[] = {5, 7, 9, 13, 17};
+
+size_t jobs_smem_bytes(int RB, int pitch) { return pcb::kSmemHead + 3ull * RB * pitch * 8 + pcb::kSmemTail; }
 
 int fill_layout(int S, int G, int L, int P, pcb_layout* out) {
-  if (S < 1 || G < 1 || G > 4096) return fail(PCB_ERR_ARG, "layout: need S >= 1 and 1 <= G <= 4096");
+  if (S < 1 || G < 1 || G > 1088) return fail(PCB_ERR_ARG, "layout: need S >= 1 and 1 <= G <= 1088");
   bool okL = false;
   for (int l : kStrips) okL |= (l == L);
   if (!okL || (P != 4 && P != 8 && P != 16 && P != 32)) return fail(PCB_ERR_ARG, "layout: unsupported strip/lanes");
   const int Q = (G + L - 1) / L;
-  int pitch = L + Q * L;
-  int want = (P == 4) ? 4 : 8;  // bank rule: rows sharing a half-warp must not collide (DESIGN.md 4.2)
+  if ((Q + 1) / 2 > P) return fail(PCB_ERR_ARG, "layout: lanes_per_row must cover ceil(Q/2) strip pairs");
+  // lead zeros | Q strips | one spare strip (the operand refill of a body that never runs stays in the row)
+  int pitch = L + (Q + 1) * L;
+  int want = (P == 4) ? 4 : 8;  // bank rule: rows sharing a half-warp must not collide (DESIGN.md)
   if (const char* e = getenv("PCB_PITCH_MOD")) want = atoi(e);  // tuning knob
   while (pitch % 16 != want) ++pitch;
-  int RB = std::min(S, std::max(1, 64 / P));
-  if (const char* e = getenv("PCB_CTA_THREADS")) RB = std::min(S, std::max(1, atoi(e) / P));  // tuning knob
-  // keep at least one full warp per CTA but stay under 48 KB of shared memory when possible
-  while (RB * P > 32 && 64 + 4ll * RB * pitch * 8 > 48 * 1024) RB = (RB + 1) / 2;
-  while (RB > 1 && 64 + 4ll * RB * pitch * 8 > 200 * 1024) RB = (RB + 1) / 2;
-  if (64 + 4ll * RB * pitch * 8 > 200 * 1024) return fail(PCB_ERR_ARG, "layout: grid too large for shared memory");
+  const int RB = 32 / P;  // one warp per CTA
+  if (jobs_smem_bytes(RB, pitch) > 200 * 1024) return fail(PCB_ERR_ARG, "layout: grid too large for shared memory");
   out->S = S;
   out->G = G;
   out->strip = L;
@@ -245,12 +245,15 @@ int pcb_make_layout(int32_t S, int32_t G, int32_t variant, pcb_layout* out) {
   // default: fewest executed lane-FMAs among the conflict-free (odd strip) configurations with
   // at least 7 FMAs per shared-memory operand pair
   long long best = -1;
-  int bl = 7, bp = 8;
-  for (int L : {7, 13})
+  int bl = 13, bp = 32;
+  for (int L : {7, 13, 17})
     for (int P : {4, 8, 16, 32}) {
-      if (L == 7 && P == 4) continue;
-      const long long c = lane_slots(G, L, P);
-      if (best < 0 || c <= best) best = c, bl = L, bp = P;  // ties: more lanes per row = less smem per warp
+      const int Q = (G + L - 1) / L;
+      if ((Q + 1) / 2 > P) continue;
+      if (L == 17 && G <= 13 * 64) continue;  // the widest strip only where 13 cannot cover the grid
+      // executed lane-FMAs per row; prefer the long strip on ties (13 DFMAs per operand pair)
+      const long long c = lane_slots(G, L, P) * (L == 13 ? 9 : 10);
+      if (best < 0 || c < best) best = c, bl = L, bp = P;
     }
   return fill_layout(S, G, bl, bp, out);
 }
@@ -321,8 +324,8 @@ int pcb_node_jobs_dev(const pcb_arena* a, const int32_t* jobs_dev, const int32_t
   kp.lead = l.lead;
   kp.RB = l.rows_per_cta;
   kp.row_blocks = (l.S + l.rows_per_cta - 1) / l.rows_per_cta;
-  const int threads = ((l.rows_per_cta * l.lanes_per_row + 31) / 32) * 32;
-  const size_t smem = 64 + 4ull * l.rows_per_cta * l.pitch * 8;
+  const int threads = 32;
+  const size_t smem = jobs_smem_bytes(l.rows_per_cta, l.pitch);
   cudaStream_t st = (cudaStream_t)stream;
   switch (l.strip) {
     case 5:
@@ -333,6 +336,8 @@ int pcb_node_jobs_dev(const pcb_arena* a, const int32_t* jobs_dev, const int32_t
       return launch_jobs_L<9>(kp, n_jobs, threads, smem, st);
     case 13:
       return launch_jobs_L<13>(kp, n_jobs, threads, smem, st);
+    case 17:
+      return launch_jobs_L<17>(kp, n_jobs, threads, smem, st);
   }
   return fail(PCB_ERR_ARG, "node_jobs: unsupported strip");
 }

@@ -38,61 +38,94 @@ struct JobKernelParams {
 // warp-uniform trip count -- a lane switches strips at a body boundary -- because two
 // separate loops would each run for the slowest lane of the warp (measured: 1.7x the DFMAs).
 // Inside a body the L window values a[k0+i-j] live in registers and slide by one element
-// per j; unrolling by L makes every register index static.  Per j: one broadcast load of
-// b[j], one load of the element entering the window, L DFMAs.
+// per j; unrolling by L makes every register index static.  The operands of a body
+// (bv[p] = b[j+p], av[p] = element entering the window after step p) are also registers:
+// each is refilled for the NEXT body right after its last use, so every shared-memory load
+// has a whole body (L*L DFMAs) to land -- the first version loaded one step ahead and was
+// short-scoreboard bound (profiles/r1_kernel_notes.md).
 // `a` has >= L zeros in front and zeros from G to the padded end, `b` has zeros from G on,
-// so neither the partial last strip nor negative indices need a bounds check.
-// Raw sums are written to out[k]; flooring / max / rescale happen in a convergent pass.
+// so neither the partial last strip nor negative indices need a bounds check; the refill
+// of a body that is never executed reads at most L doubles outside the row (inside the
+// shared-memory allocation, never used).
+// Raw sums come back in registers: y1 = strip u, y2 = strip Q-1-u.
 // ---------------------------------------------------------------------------------
+// One body (L steps of j) plus the strip bookkeeping.  X is the window at body entry
+// (X[r] = a[k0 - j + r]); Y[L-1-p] is the element that enters after step p (loaded during the
+// previous body).  Element (i - p) of the window at step p is X[i-p] while it is still in the
+// old window and Y[i-p+L] once it has entered, so no register is ever copied; X[L-1-p] dies
+// after step p and is refilled at once with the NEXT body's entering element, which makes X
+// the "Y" of the next body: the caller alternates step(X,Y) / step(Y,X).
 template <int L>
-__device__ __forceinline__ void conv_body(const double* __restrict__ an, const double* __restrict__ bj_ptr,
-                                          double (&acc)[L], double (&w)[L]) {
+struct ConvLane {
+  const double* a;
+  const double* b;
+  const double* an;  // next body's entering elements: an[-p]
+  const double* bn;  // next body's multipliers:       bn[p]
+  int k2, left;
+  bool active, second;
+};
+
+template <int L>
+__device__ __forceinline__ void conv_step(ConvLane<L>& st, double (&X)[L], double (&Y)[L], double (&bv)[L],
+                                          double (&y1)[L], double (&y2)[L]) {
+  if (!st.active) return;
 #pragma unroll
   for (int p = 0; p < L; ++p) {
-    const double bj = bj_ptr[p];
+    const double bj = bv[p];
 #pragma unroll
-    for (int i = 0; i < L; ++i) acc[i] = fma(bj, w[(i - p + L) % L], acc[i]);
-    w[L - 1 - p] = an[-p];
+    for (int i = 0; i < L; ++i) y2[i] = fma(bj, (i >= p) ? X[i - p] : Y[i - p + L], y2[i]);
+    X[L - 1 - p] = st.an[-p];
+    bv[p] = st.bn[p];
+  }
+  st.bn += L;
+  st.an -= L;
+  if (--st.left == 0) {
+    if (st.second) {  // switch to the lane's second strip; Y is the window of the next step
+      st.second = false;
+      st.left = st.k2 / L + 1;
+#pragma unroll
+      for (int i = 0; i < L; ++i) {
+        y1[i] = y2[i];
+        y2[i] = 0.0;
+        Y[i] = st.a[st.k2 + i];
+        X[L - 1 - i] = st.a[st.k2 - 1 - i];
+        bv[i] = st.b[i];
+      }
+      st.an = st.a + st.k2 - 1 - L;
+      st.bn = st.b + L;
+    } else {
+      st.active = false;
+    }
   }
 }
 
+// Raw sums come back in registers: y1 = strip u, y2 = strip Q-1-u (y2 only, for the middle
+// unit of an odd Q).
 template <int L>
-__device__ __forceinline__ void conv_row_unit(const double* __restrict__ a, const double* __restrict__ b,
-                                              double* __restrict__ out, int u, int Q, int G, bool active) {
-  // strips q1 = u (u+1 bodies) then q2 = Q-1-u (Q-u bodies); the middle unit of an odd Q has one strip
-  int k0 = u * L;
-  int left = u + 1;
-  bool second = (Q - 1 - u) != u;
-  double acc[L], w[L];
+__device__ __forceinline__ void conv_unit(const double* __restrict__ a, const double* __restrict__ b, int u, int Q,
+                                          bool active, double (&y1)[L], double (&y2)[L]) {
+  const int k0 = u * L;
+  ConvLane<L> st;
+  st.a = a;
+  st.b = b;
+  st.k2 = (Q - 1 - u) * L;
+  st.left = u + 1;
+  st.active = active;
+  st.second = st.k2 != k0;
+  st.an = a + k0 - 1 - L;
+  st.bn = b + L;
+  double X[L], Y[L], bv[L];
 #pragma unroll
   for (int i = 0; i < L; ++i) {
-    w[i] = active ? a[k0 + i] : 0.0;
-    acc[i] = 0.0;
+    y1[i] = 0.0;
+    y2[i] = 0.0;
+    X[i] = active ? a[k0 + i] : 0.0;
+    Y[L - 1 - i] = active ? a[k0 - 1 - i] : 0.0;
+    bv[i] = active ? b[i] : 0.0;
   }
-  int j = 0;
-  for (int it = 0; it <= Q; ++it) {  // warp-uniform
-    if (active) {
-      conv_body<L>(a + k0 - 1 - j, b + j, acc, w);
-      j += L;
-      if (--left == 0) {
-#pragma unroll
-        for (int i = 0; i < L; ++i)
-          if (k0 + i < G) out[k0 + i] = acc[i];
-        if (second) {
-          second = false;
-          k0 = (Q - 1 - u) * L;
-          left = Q - u;
-          j = 0;
-#pragma unroll
-          for (int i = 0; i < L; ++i) {
-            w[i] = a[k0 + i];
-            acc[i] = 0.0;
-          }
-        } else {
-          active = false;
-        }
-      }
-    }
+  for (int it = 0; it <= Q; it += 2) {  // warp-uniform; Q+1 bodies per lane (one spare when Q is even)
+    conv_step<L>(st, X, Y, bv, y1, y2);
+    conv_step<L>(st, Y, X, bv, y1, y2);
   }
 }
 
@@ -125,18 +158,25 @@ __device__ __forceinline__ void row_prefix_lse(const double* x, double* out, int
 }
 
 // ---------------------------------------------------------------------------------
-// node_jobs_kernel: one CTA per (job, row block).  See phyclone_b200.h for the job
-// record.  Shared memory: 4 mbarriers + two accumulator buffers + two operand buffers,
-// each RB*pitch doubles.
+// node_jobs_kernel: one single-warp CTA per (job, row block of RB = 32/P rows).  Rows of a
+// tile are independent through the whole fold, so nothing ever needs a CTA-wide barrier:
+// the P lanes of a row group live in one warp and synchronise with __syncwarp / shuffles.
+// Shared memory: [256 B: mbarriers + underrun slack][A: RB*pitch][B0][B1][256 B slack].
+//   A   running product of the fold (max-normalised, linear domain), updated in place
+//   B0/1 operand tiles, double-buffered: the TMA bulk copy of child j+1 is in flight while
+//        child j is being folded in.
+// See phyclone_b200.h for the job record.
 // ---------------------------------------------------------------------------------
+constexpr int kSmemHead = 256;
+constexpr int kSmemTail = 256;
+
 template <int L>
-__global__ void node_jobs_kernel(const JobKernelParams p) {
+__global__ void __launch_bounds__(32) node_jobs_kernel(const JobKernelParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
   const int rows_elems = p.RB * p.pitch;
-  double* bufA0 = reinterpret_cast<double*>(smem_raw + 64);
-  double* bufA1 = bufA0 + rows_elems;
-  double* bufB0 = bufA1 + rows_elems;
+  double* bufA = reinterpret_cast<double*>(smem_raw + kSmemHead);
+  double* bufB0 = bufA + rows_elems;
   double* bufB1 = bufB0 + rows_elems;
 
   const int job = blockIdx.x / p.row_blocks;
@@ -145,7 +185,7 @@ __global__ void node_jobs_kernel(const JobKernelParams p) {
   const int coff = jr[0], C = jr[1], base = jr[2], outt = jr[3], flags = jr[4], slot = jr[5];
   const int r0 = rb * p.RB;
   const int nrows = min(p.RB, p.S - r0);
-  const int P = p.P, G = p.G, pitch = p.pitch, lead = p.lead;
+  const int P = p.P, G = p.G, pitch = p.pitch, lead = p.lead, Q = p.Q;
   const int tid = threadIdx.x;
   const int lrow = tid / P;
   const int lir = tid & (P - 1);
@@ -156,19 +196,18 @@ __global__ void node_jobs_kernel(const JobKernelParams p) {
   const double addc = (flags & 2) ? p.prior : 0.0;
   const bool shortcut = scan && base < 0 && outt < 0;
 
-  for (int i = tid; i < rows_elems; i += blockDim.x) bufA1[i] = 0.0;
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
     mbar_init(&bars[2], 1);
     mbar_fence_init();
   }
-  __syncthreads();
+  __syncwarp();
 
   const int c0 = p.children[coff];
   if (tid == 0) {
     mbar_expect_tx(&bars[0], bytes);
-    tma_load_1d(bufA0, p.lin + (size_t)c0 * p.tile_elems + (size_t)r0 * pitch, bytes, &bars[0]);
+    tma_load_1d(bufA, p.lin + (size_t)c0 * p.tile_elems + (size_t)r0 * pitch, bytes, &bars[0]);
     if (C >= 2) {
       const int c1 = p.children[coff + 1];
       mbar_expect_tx(&bars[1], bytes);
@@ -182,53 +221,78 @@ __global__ void node_jobs_kernel(const JobKernelParams p) {
   double M = row_ok ? p.rmax[(size_t)c0 * p.S + row] : 0.0;
   mbar_wait(&bars[0], 0);
 
+  double* a_row = bufA + lrow * pitch + lead;
+  const int u = lir;  // the layout guarantees ceil(Q/2) <= P: one unit (strip pair) per lane
+  const bool lane_ok = row_ok && u < p.U;
+  const int k1 = u * L, k2 = (Q - 1 - u) * L;
+  const bool two = k2 != k1;
+
   // ---- left fold over the children (tree/utils.py:33-47) --------------------------
   for (int j = 1; j < C; ++j) {
-    double* Ain = (j & 1) ? bufA0 : bufA1;
-    double* Aout = (j & 1) ? bufA1 : bufA0;
     double* Bcur = (j & 1) ? bufB0 : bufB1;
     uint64_t* bbar = (j & 1) ? &bars[1] : &bars[2];
     mbar_wait(bbar, ((j - 1) >> 1) & 1);
-    if (j + 1 < C && tid == 0) {  // prefetch the next operand; its buffer was released by the
-      double* Bnext = (j & 1) ? bufB1 : bufB0;  // __syncthreads that closed step j-1
+    if (j + 1 < C && tid == 0) {  // prefetch the next operand into the buffer step j-1 released
+      double* Bnext = (j & 1) ? bufB1 : bufB0;
       uint64_t* nbar = (j & 1) ? &bars[2] : &bars[1];
       const int cn = p.children[coff + j + 1];
       mbar_expect_tx(nbar, bytes);
       tma_load_1d(Bnext, p.lin + (size_t)cn * p.tile_elems + (size_t)r0 * pitch, bytes, nbar);
     }
-    const double* a_row = Ain + lrow * pitch + lead;
     const double* b_row = Bcur + lrow * pitch + lead;
-    double* o_row = Aout + lrow * pitch + lead;
-    for (int ub = 0; ub < p.U; ub += P) conv_row_unit<L>(a_row, b_row, o_row, ub + lir, p.Q, G, row_ok && (ub + lir) < p.U);
-    __syncwarp();
-    // floor (tree/utils.py:77) and row maximum, lanes strided over the row
-    double lmax = 0.0;
-    if (row_ok)
-      for (int k = lir; k < G; k += P) {
-        double y = o_row[k];
-        if (y <= 0.0) {
-          y = kFloor;
-          o_row[k] = y;
-        }
-        lmax = fmax(lmax, y);
-      }
-    const double ymax = group_max(lmax, P);
+    double y1[L], y2[L];
+    conv_unit<L>(a_row, b_row, u, Q, lane_ok, y1, y2);
+    // floor (tree/utils.py:77) and row maximum, all in registers.  Outputs past G (only the last
+    // strip is partial) are forced to 0 so that they can be stored unconditionally: they land
+    // on pad columns, which must stay zero anyway.
+    const int nv2 = lane_ok ? min(L, G - k2) : 0;
+    const bool v1 = lane_ok && two;
+#pragma unroll
+    for (int i = 0; i < L; ++i) {
+      y2[i] = (i < nv2) ? ((y2[i] > 0.0) ? y2[i] : kFloor) : 0.0;
+      y1[i] = v1 ? ((y1[i] > 0.0) ? y1[i] : kFloor) : 0.0;
+    }
+    double mx[L];
+#pragma unroll
+    for (int i = 0; i < L; ++i) mx[i] = (y1[i] > y2[i]) ? y1[i] : y2[i];
+#pragma unroll
+    for (int w = 1; w < L; w <<= 1)
+#pragma unroll
+      for (int i = 0; i + w < L; i += 2 * w) mx[i] = (mx[i] > mx[i + w]) ? mx[i] : mx[i + w];
+    const double ymax = group_max(mx[0], P);
     const double mB = row_ok ? p.rmax[(size_t)p.children[coff + j] * p.S + row] : 0.0;
+    double scale = 1.0;
+    bool tiny = false;
     if (j < C - 1) {
       // re-normalise the running product exactly where the reference re-max-shifts it
       M += mB + log(ymax);
-      if (row_ok) {
-        const bool tiny = !(ymax >= 1e-290);
-        const double inv = 1.0 / ymax;
-        for (int k = lir; k < G; k += P) o_row[k] = tiny ? o_row[k] / ymax : o_row[k] * inv;
-      }
+      tiny = !(ymax >= 1e-290);
+      scale = 1.0 / ymax;
     } else {
       M += mB;
     }
-    __syncthreads();
+    __syncwarp();  // every lane is done reading A: update it in place
+    if (lane_ok) {
+      if (!tiny) {
+#pragma unroll
+        for (int i = 0; i < L; ++i) a_row[k2 + i] = y2[i] * scale;
+        if (two) {
+#pragma unroll
+          for (int i = 0; i < L; ++i) a_row[k1 + i] = y1[i] * scale;
+        }
+      } else {  // 1/ymax would overflow: divide
+#pragma unroll
+        for (int i = 0; i < L; ++i) a_row[k2 + i] = y2[i] / ymax;
+        if (two) {
+#pragma unroll
+          for (int i = 0; i < L; ++i) a_row[k1 + i] = y1[i] / ymax;
+        }
+      }
+    }
+    __syncwarp();
   }
 
-  double* yrow = ((C >= 2 && ((C - 1) & 1)) ? bufA1 : bufA0) + lrow * pitch + lead;
+  double* yrow = a_row;
 
   // ---- epilogue 1: dummy-root scoring without materialising the tile --------------
   if (shortcut) {
