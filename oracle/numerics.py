@@ -94,15 +94,18 @@ def node_log_r(log_p, children):
 #                                                 tree/distributions.py:197-200
 # --------------------------------------------------------------------------
 def lse_1d(x):
-    """utils/math.py:102-118 (log_sum_exp)."""
+    """utils/math.py:102-118 (log_sum_exp).  The reference body is Numba-compiled, i.e. scalar
+    libm exp/log, which is what math.exp/math.log call; NumPy's SIMD exp can differ in the last
+    bit, and one ulp in a particle weight is enough to change how many uniforms
+    Generator.multinomial consumes ("RNG-stream identity")."""
     x = np.asarray(x, dtype=np.float64)
-    m = np.max(x)
-    if np.isinf(m):
+    m = float(np.max(x))
+    if math.isinf(m):
         return m
     total = 0.0
-    for v in x:
-        total += np.exp(v - m)
-    return np.log(total) + m
+    for v in x.tolist():
+        total += math.exp(v - m)
+    return math.log(total) + m
 
 
 def root_terms(root_tile):
@@ -124,10 +127,14 @@ def log_normalize(log_p):
 
 
 def exp_normalize(log_p):
+    """utils/math.py:37-59; Numba body: elementwise libm exp and a sequential sum."""
     log_p = np.asarray(log_p, dtype=np.float64)
     log_norm = lse_1d(log_p)
-    p = np.exp(log_p - log_norm)
-    p = p / p.sum()
+    p = np.array([math.exp(v) for v in (log_p - log_norm).tolist()])
+    total = 0.0
+    for v in p.tolist():
+        total += v
+    p = p / total
     return p, log_norm
 
 
