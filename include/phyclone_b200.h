@@ -85,11 +85,11 @@ int pcb_arena_import_dev(const pcb_arena* arena, const double* dense, const int3
 /* arena slots ids[n] -> dense [n][S][G] log tiles (device) */
 int pcb_arena_export_dev(const pcb_arena* arena, const int32_t* ids_dev, int64_t n, double* dense, void* stream);
 
-/* out[i] = a[i] (+ b[i] if b_ids[i] >= 0) + addend, with lin/rmax refreshed.
- * Replaces TreeNode.add_data_point / log_p initialisation
- * (tree/tree_node.py:12, 42-44, 47-52): log_p += value; log_r += value. */
+/* out[i] = a[i] + b_sign * b[i] (if b_ids && b_ids[i] >= 0) + addend, with lin/rmax refreshed;
+ * b_sign is +1.0 or -1.0.  Replaces TreeNode.add_data_point / remove_data_point / the log_p
+ * initialisation (tree/tree_node.py:12, 42-59): log_p += value; log_r += value; log_p -= value. */
 int pcb_tile_add_dev(const pcb_arena* arena, const int32_t* a_ids, const int32_t* b_ids, const int32_t* out_ids,
-                     int64_t n, double addend, void* stream);
+                     int64_t n, double b_sign, double addend, void* stream);
 
 /* ---- the node-refresh job kernel -------------------------------------- */
 /* One job = one TreeNode.update_node_from_child_r_vals (tree/tree_node.py:61-71)

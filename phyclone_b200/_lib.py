@@ -48,7 +48,7 @@ SIGNATURES = {
     "pcb_make_layout": (C.c_int, [_i32, _i32, _i32, C.POINTER(Layout)]),
     "pcb_arena_import_dev": (C.c_int, [C.POINTER(Arena), _P, _P, _i64, _P]),
     "pcb_arena_export_dev": (C.c_int, [C.POINTER(Arena), _P, _i64, _P, _P]),
-    "pcb_tile_add_dev": (C.c_int, [C.POINTER(Arena), _P, _P, _P, _i64, _f64, _P]),
+    "pcb_tile_add_dev": (C.c_int, [C.POINTER(Arena), _P, _P, _P, _i64, _f64, _f64, _P]),
     "pcb_node_jobs_dev": (C.c_int, [C.POINTER(Arena), _P, _P, _i64, _f64, _P, _P, _P]),
     "pcb_reduce_rows_dev": (C.c_int, [_P, _i64, _i32, _P, _P]),
     "pcb_np_conv_dims_host": (C.c_int, [_P, _P, _P, _i64, _i32, _i32]),

@@ -285,7 +285,7 @@ int pcb_arena_export_dev(const pcb_arena* a, const int32_t* ids_dev, int64_t n, 
 }
 
 int pcb_tile_add_dev(const pcb_arena* a, const int32_t* a_ids, const int32_t* b_ids, const int32_t* out_ids,
-                     int64_t n, double addend, void* stream) {
+                     int64_t n, double b_sign, double addend, void* stream) {
   int rc = check_arena(a);
   if (rc) return rc;
   if (n <= 0) return PCB_OK;
@@ -293,7 +293,7 @@ int pcb_tile_add_dev(const pcb_arena* a, const int32_t* a_ids, const int32_t* b_
   const long long warps = n * l.S;
   const int wpb = 4;
   pcb::tile_add_kernel<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
-      a_ids, b_ids, out_ids, n, addend, a->lg, a->lin, a->rmax, l.S, l.G, l.pitch, l.lead, l.tile_elems);
+      a_ids, b_ids, out_ids, n, b_sign, addend, a->lg, a->lin, a->rmax, l.S, l.G, l.pitch, l.lead, l.tile_elems);
   PCB_LAUNCH_CHECK();
   return PCB_OK;
 }

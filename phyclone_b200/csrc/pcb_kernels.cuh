@@ -415,9 +415,10 @@ __global__ void export_tiles_kernel(const double* __restrict__ lg, const int32_t
   for (int k = lane; k < G; k += 32) dst[k] = src[k];
 }
 
-// out = a (+ b) + addend, refresh lin / rmax      (tree/tree_node.py:42-52)
+// out = a (+/- b) + addend, refresh lin / rmax      (tree/tree_node.py:42-59); b_sign is +1 or -1
 __global__ void tile_add_kernel(const int32_t* __restrict__ a_ids, const int32_t* __restrict__ b_ids,
-                                const int32_t* __restrict__ out_ids, long long n, double addend, double* lg,
+                                const int32_t* __restrict__ out_ids, long long n, double b_sign, double addend,
+                                double* lg,
                                 double* lin, double* rmax, int S, int G, int pitch, int lead, long long tile_elems) {
   const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -433,14 +434,14 @@ __global__ void tile_add_kernel(const int32_t* __restrict__ a_ids, const int32_t
   // first pass keeps the sums in registers for up to 8 elements per lane (G <= 256); otherwise recompute
   for (int k = lane; k < G; k += 32) {
     double v = pa[k];
-    if (pb) v += pb[k];
+    if (pb) v += b_sign * pb[k];
     v += addend;
     m = fmax(m, v);
   }
   m = group_max(m, 32);
   for (int k = lane; k < G; k += 32) {
     double v = pa[k];
-    if (pb) v += pb[k];
+    if (pb) v += b_sign * pb[k];
     v += addend;
     lg[o + k] = v;
     lin[o + k] = (v == -INFINITY) ? 0.0 : exp(v - m);

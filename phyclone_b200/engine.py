@@ -109,19 +109,49 @@ class DeviceArena:
         _lib.check(self.lib.pcb_arena_export_dev(C.byref(self.c), ids_dev.data_ptr(), n, out.data_ptr(), self._stream()))
         return out
 
-    def tile_add(self, a_ids, b_ids, out_ids, addend=0.0):
-        """out = a (+ b) + addend in the log domain; refreshes lin / rmax of `out`."""
+    def tile_add(self, a_ids, b_ids, out_ids, addend=0.0, b_sign=1.0):
+        """out = a (+/- b) + addend in the log domain; refreshes lin / rmax of `out`."""
         n = len(out_ids)
         if n == 0:
             return
-        a = self._to_dev_i32(a_ids, "add_a")
-        o = self._to_dev_i32(out_ids, "add_o")
-        b_ptr = None
-        if b_ids is not None:
-            b_ptr = self._to_dev_i32(b_ids, "add_b").data_ptr()
+        # one packed staging copy: [a | b | out]
+        packed = np.empty(3 * n, dtype=np.int32)
+        packed[:n] = a_ids
+        packed[n : 2 * n] = b_ids if b_ids is not None else -1
+        packed[2 * n :] = out_ids
+        d = self._to_dev_i32(packed, "add")
+        base = d.data_ptr()
         _lib.check(
-            self.lib.pcb_tile_add_dev(C.byref(self.c), a.data_ptr(), b_ptr, o.data_ptr(), n, float(addend), self._stream())
+            self.lib.pcb_tile_add_dev(C.byref(self.c), base, base + 4 * n, base + 8 * n, n, float(b_sign), float(addend),
+                                      self._stream())
         )
+
+    def tile_sub(self, a_ids, b_ids, out_ids):
+        self.tile_add(a_ids, b_ids, out_ids, 0.0, -1.0)
+
+    def launch_jobs(self, tab, kids, rows):
+        """tab: int32 [n,8] job records; kids: flat child ids; rows: CUDA [2,n_slots,S] tensor or None."""
+        n = tab.shape[0]
+        nk = kids.shape[0]
+        packed = np.empty(n * JOB_INTS + max(nk, 1), dtype=np.int32)
+        packed[: n * JOB_INTS] = tab.reshape(-1)
+        packed[n * JOB_INTS : n * JOB_INTS + nk] = kids
+        d = self._to_dev_i32(packed, "jobs")
+        base = d.data_ptr()
+        pl = pt = None
+        if rows is not None:
+            pl, pt = rows[0].data_ptr(), rows[1].data_ptr()
+        _lib.check(
+            self.lib.pcb_node_jobs_dev(C.byref(self.c), base, base + 4 * n * JOB_INTS, n, self.prior, pl, pt, self._stream())
+        )
+
+    def reduce_rows(self, rows):
+        n_slots = rows.shape[1]
+        out = torch.empty((2, n_slots), dtype=torch.float64, device=self.device)
+        st = self._stream()
+        _lib.check(self.lib.pcb_reduce_rows_dev(rows[0].data_ptr(), n_slots, self.S, out[0].data_ptr(), st))
+        _lib.check(self.lib.pcb_reduce_rows_dev(rows[1].data_ptr(), n_slots, self.S, out[1].data_ptr(), st))
+        return out
 
     # -------------------------------------------------------------------- jobs
     def run_jobs(self, jobs, children, n_slots=0):

@@ -1,0 +1,136 @@
+"""TreeHolder / Particle / ParticleSwarm (reference smc/swarm/*.py).
+
+A holder keeps the as-built tree and a lazy score: reading `log_p` is what finally triggers the
+batched device evaluation, so building all candidate holders of an SMC step first and reading
+their scores afterwards costs one flush.
+"""
+
+import itertools
+
+import numpy as np
+
+from ..utils.math import log_sum_exp
+
+_uid = itertools.count()
+
+
+class TreeHolder(object):
+    __slots__ = ("_tree_dist", "_pending", "_built", "_thawed", "tree_roots", "tree_nodes", "labels",
+                 "node_last_added_to", "num_children_on_node_that_matters", "outlier_node_name", "log_pdf", "uid")
+
+    def __init__(self, tree, tree_dist, perm_dist=None):
+        self.uid = next(_uid)  # cache key (object ids can be recycled within an iteration)
+        self._tree_dist = tree_dist
+        self.outlier_node_name = tree.outlier_node_name
+        self.log_pdf = 0.0  # perm_dist is None in production (run.py:416)
+        self._pending = tree_dist.prepare(tree)
+        self.tree_roots = np.asarray(tree.roots)
+        self.tree_nodes = tree.nodes
+        self._built = tree  # callers hand the tree over: it is never mutated afterwards
+        self._thawed = None
+        self.labels = tree.labels
+        self.node_last_added_to = tree.node_last_added_to
+        if self.node_last_added_to != tree.outlier_node_name:
+            self.num_children_on_node_that_matters = tree.get_number_of_children(self.node_last_added_to)
+        else:
+            self.num_children_on_node_that_matters = 0
+
+    @property
+    def log_p(self):
+        return self._pending.resolve()[0]
+
+    @property
+    def log_p_one(self):
+        return self._pending.resolve()[1]
+
+    @property
+    def tree(self):
+        """What `Tree.from_dict(holder._tree)` gives in the reference (tree_holder.py:80-82): a fresh
+        tree whose adjacency follows slot order and whose tiles were all refreshed."""
+        if self._thawed is None:
+            self._thawed = self._built.thawed_copy()
+        return self._thawed.copy()
+
+
+class Particle(object):
+    """smc/swarm/particle.py; the incremental weight (kernels/base.py:38-57) is evaluated on first read so
+    that every new tree of an SMC step is scored by one batched flush."""
+
+    __slots__ = ("_log_w", "_log_q", "parent_particle", "_holder")
+
+    def __init__(self, log_q, parent_particle, tree_holder):
+        self._log_w = None
+        self._log_q = log_q
+        self.parent_particle = parent_particle
+        self._holder = tree_holder
+
+    @property
+    def log_w(self):
+        if self._log_w is None:
+            if self.parent_particle is None:
+                self._log_w = self._holder.log_p - self._log_q
+            else:
+                self._log_w = self._holder.log_p - self.parent_particle.log_p - self._log_q
+        return self._log_w
+
+    log_p = property(lambda self: self._holder.log_p)
+    log_p_one = property(lambda self: self._holder.log_p_one)
+    log_pdf = property(lambda self: 0.0)
+    tree_roots = property(lambda self: self._holder.tree_roots)
+    tree_nodes = property(lambda self: self._holder.tree_nodes)
+    holder = property(lambda self: self._holder)
+
+    @property
+    def tree(self):
+        return self._holder.tree
+
+
+class ParticleSwarm(object):
+    """smc/swarm/swarm.py:6-81"""
+
+    __slots__ = ("particles", "_log_norm_const", "_unnormalized_log_weights")
+
+    def __init__(self):
+        self.particles = []
+        self._log_norm_const = None
+        self._unnormalized_log_weights = []
+
+    @property
+    def ess(self):
+        return 1 / np.square(self.weights).sum()
+
+    @property
+    def log_norm_const(self):
+        if self._log_norm_const is None:
+            self._log_norm_const = log_sum_exp(self.unnormalized_log_weights)
+        return self._log_norm_const
+
+    @property
+    def log_weights(self):
+        return self.unnormalized_log_weights - self.log_norm_const
+
+    @property
+    def num_particles(self):
+        return len(self.particles)
+
+    @property
+    def relative_ess(self):
+        return self.ess / self.num_particles
+
+    @property
+    def unnormalized_log_weights(self):
+        return np.fromiter(self._unnormalized_log_weights, dtype=np.float64, count=len(self._unnormalized_log_weights))
+
+    @property
+    def weights(self):
+        weights = np.exp(self.log_weights)
+        weights /= weights.sum()
+        return weights
+
+    def add_particle(self, log_weight, particle):
+        self.particles.append(particle)
+        self._unnormalized_log_weights.append(log_weight)
+        self._log_norm_const = None
+
+    def to_list(self):
+        return zip(self.particles, self.weights)

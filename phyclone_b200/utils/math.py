@@ -1,0 +1,74 @@
+"""Scalar / tiny-vector host helpers with the names of the reference's `phyclone/utils/math.py`.
+
+These are O(particles) host-side scalars between kernel launches (prior terms, proposal
+probabilities, RNG draws); the tile arithmetic is on the device.  log-gamma goes through the
+C library exactly like the reference's Numba `math.lgamma` (utils/math.py:126-151).
+"""
+
+import ctypes
+import ctypes.util
+import math
+from functools import lru_cache
+
+import numpy as np
+
+_libm = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+_libm.lgamma.restype = ctypes.c_double
+_libm.lgamma.argtypes = [ctypes.c_double]
+
+
+def log_gamma(x):
+    return _libm.lgamma(float(x))
+
+
+def log_factorial(x):
+    return _libm.lgamma(float(x) + 1.0)
+
+
+@lru_cache(maxsize=None)
+def cached_log_factorial(x):
+    return log_factorial(x)
+
+
+def log_binomial_coefficient(n, x):
+    return log_factorial(n) - log_factorial(x) - log_factorial(n - x)
+
+
+@lru_cache(maxsize=2048)
+def cached_log_binomial_coefficient(n, x):
+    return log_binomial_coefficient(n, x)
+
+
+def log_sum_exp(log_X):
+    """utils/math.py:102-118"""
+    log_X = np.asarray(log_X, dtype=np.float64)
+    max_exp = float(np.max(log_X))
+    if math.isinf(max_exp):
+        return max_exp
+    total = 0.0
+    for x in log_X.tolist():
+        total += math.exp(x - max_exp)
+    return math.log(total) + max_exp
+
+
+def log_normalize(log_p):
+    """utils/math.py:121-123"""
+    log_p = np.asarray(log_p, dtype=np.float64)
+    return log_p - log_sum_exp(log_p)
+
+
+def exp_normalize(log_p):
+    """utils/math.py:37-59"""
+    log_p = np.asarray(log_p, dtype=np.float64)
+    log_norm = log_sum_exp(log_p)
+    p = np.array([math.exp(v) for v in (log_p - log_norm).tolist()])
+    total = 0.0
+    for v in p.tolist():
+        total += v
+    return p / total, log_norm
+
+
+def discrete_rvs(p, rng):
+    """utils/math.py:19-21"""
+    p = p / np.sum(p)
+    return rng.multinomial(1, p).argmax()
