@@ -1059,15 +1059,16 @@ def alpha_move(joint, tree, rng, a=0.01, b=0.01):  # concentration.py:29-60, run
 
     sizes = [len(v) for k, v in tree.node_data.items() if k != OUT]
     k, n = len(sizes), sum(sizes)
+    rs = getattr(rng, "generator", rng)  # scipy wants the real Generator (tests may pass a recording proxy)
     if k == 0:
-        joint.alpha = gamma.rvs(a, scale=(1 / b), random_state=rng)
+        joint.alpha = gamma.rvs(a, scale=(1 / b), random_state=rs)
         return
-    eta = beta.rvs(a=joint.alpha + 1, b=n, random_state=rng)
+    eta = beta.rvs(a=joint.alpha + 1, b=n, random_state=rs)
     shape = a + k - 1
     rate = b - np.log(eta)
     x = shape / (n * rate)
-    shape += bernoulli.rvs(x / (1 + x), random_state=rng)
-    joint.alpha = max(gamma.rvs(shape, scale=(1 / rate), random_state=rng), 1e-10)
+    shape += bernoulli.rvs(x / (1 + x), random_state=rs)
+    joint.alpha = max(gamma.rvs(shape, scale=(1 / rate), random_state=rs), 1e-10)
 
 
 # ------------------------------------------------------------------------------------

@@ -66,9 +66,9 @@ class Kernel(object):
         raise NotImplementedError
 
     def get_proposal_distribution(self, data_point, parent_particle, parent_tree=None):
-        # the reference keys its LRU on particle VALUE equality; identity catches the resampled copies and the
-        # shared candidate holders, which is where the hits come from (a miss only costs memoised tile ops)
-        key = (data_point.idx, parent_particle._holder.uid if parent_particle is not None else None,
+        # keyed on particle VALUE like the reference's lru_cache (semi_adapted.py:219-237): the first proposal
+        # built for a given frozen tree is the one every equal particle gets, child order and all
+        key = (data_point.idx, parent_particle._holder.vkey if parent_particle is not None else None,
                self.tree_dist.prior.alpha)
         return self._dist_cache.get(key, lambda: self._make_proposal(data_point, parent_particle, parent_tree))
 
@@ -213,7 +213,7 @@ class SemiAdaptedProposalDistribution(ProposalDistribution):
         else:
             children = self._rng.choice(self.parent_particle.tree_roots, num_children, replace=False)
         children = frozenset(children)
-        key = (self.parent_particle._holder.uid, self.data_point.idx, children)
+        key = (self.parent_particle._holder.vkey, self.data_point.idx, children)
 
         def make():
             tree = self.parent_particle.tree

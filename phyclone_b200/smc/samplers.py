@@ -43,7 +43,7 @@ class AbstractSMCSampler(object):
         data_point = self.data_points[self.iteration]
         seen = set()
         for p in parents:
-            key = None if p is None else p.holder.uid
+            key = None if p is None else p.holder.vkey
             if key not in seen:
                 seen.add(key)
                 self.kernel.get_proposal_distribution(data_point, p)

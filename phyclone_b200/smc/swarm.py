@@ -16,7 +16,8 @@ _uid = itertools.count()
 
 class TreeHolder(object):
     __slots__ = ("_tree_dist", "_pending", "_built", "_thawed", "tree_roots", "tree_nodes", "labels",
-                 "node_last_added_to", "num_children_on_node_that_matters", "outlier_node_name", "log_pdf", "uid")
+                 "node_last_added_to", "num_children_on_node_that_matters", "outlier_node_name", "log_pdf", "uid",
+                 "vkey")
 
     def __init__(self, tree, tree_dist, perm_dist=None):
         self.uid = next(_uid)  # cache key (object ids can be recycled within an iteration)
@@ -27,6 +28,7 @@ class TreeHolder(object):
         self.tree_roots = np.asarray(tree.roots)
         self.tree_nodes = tree.nodes
         self._built = tree  # callers hand the tree over: it is never mutated afterwards
+        self.vkey = tree.structure_key()  # "equal particle" in the reference's sense (dict equality of frozen trees)
         self._thawed = None
         self.labels = tree.labels
         self.node_last_added_to = tree.node_last_added_to

@@ -21,7 +21,7 @@ class Tree(object):
     _ROOT_NODE_NAME = "root"
     _OUTLIER_NODE_NAME = -1
     __slots__ = ("grid_size", "store", "_data", "_graph", "_node_indices", "_node_indices_rev", "_last_node_added_to",
-                 "_lp", "_lr", "_dirty")
+                 "_lp", "_lr", "_dirty", "_skey")
 
     def __init__(self, grid_size, store):
         self.grid_size = grid_size
@@ -38,6 +38,7 @@ class Tree(object):
         # graph indices whose adjacency order / log_r a from_dict(to_dict()) round trip would change
         # (see thawed_copy); None = unknown, take the generic round trip
         self._dirty = set()
+        self._skey = 0  # running structure hash (see structure_key); None = recompute
         self._add_node(self._ROOT_NODE_NAME)
 
     # ------------------------------------------------------------------ identity
@@ -74,6 +75,26 @@ class Tree(object):
             return "({}){}".format(",".join(kids), name) if kids else "{}".format(name)
 
         return rec(self._node_indices[self._ROOT_NODE_NAME]) + ";"
+
+    def structure_key(self):
+        """Value identity of the frozen tree, i.e. of what `to_dict()` would hold: edges by slot, data lists
+        in order, last node added to.  The reference keys its proposal caches on dict equality of frozen
+        trees (smc/swarm/particle.py:44-49, tree_holder.py:44-49) -- and because the first-built proposal
+        wins and was folded in ITS parent's child order, those cache hits are part of the result once floors
+        occur -- so the host needs the same notion of "equal particle".  Kept as an XOR of 64-bit hashes that
+        is updated in O(1) by the two SMC edits; anything else recomputes it."""
+        if self._skey is None:
+            g = self._graph
+            k = 0
+            s, d = g.esrc, g.edst
+            for e in range(len(s)):
+                if s[e] >= 0:
+                    k ^= hash((e, s[e], d[e]))
+            for node, lst in self._data.items():
+                for pos, dp in enumerate(lst):
+                    k ^= hash((node, pos, dp.idx, "d"))
+            self._skey = k
+        return (self._skey, self._last_node_added_to, self._graph.n_nodes)
 
     # ------------------------------------------------------------------ queries
     @staticmethod
@@ -209,7 +230,11 @@ class Tree(object):
     def _add_list_of_data_points_to_node(self, data, node):
         i = self._node_indices[node]
         if len(data) > 0:
-            self._data[node] = self._data[node] + tuple(data)
+            old = self._data[node]
+            self._data[node] = old + tuple(data)
+            if self._skey is not None:
+                for pos, dp in enumerate(data, len(old)):
+                    self._skey ^= hash((node, pos, dp.idx, "d"))
             self._absorb(i, data)
         return i
 
@@ -222,11 +247,17 @@ class Tree(object):
         self._add_node(node)
         r = self._node_indices[self._ROOT_NODE_NAME]
         i = self._add_list_of_data_points_to_node(data, node)
-        g.add_edge(r, i)
+        k = self._skey
+        e = g.add_edge(r, i)
+        if k is not None:
+            k ^= hash((e, r, i))
         for child in children:
             ci = self._node_indices[child]
             g.remove_edge(r, ci)
-            g.add_edge(i, ci)
+            e = g.add_edge(i, ci)
+            if k is not None:
+                k ^= hash((e, r, ci)) ^ hash((e, i, ci))  # the freed slot is the one re-used
+        self._skey = k
         self._last_node_added_to = node
         if self._dirty is not None:
             self._dirty.add(i)
@@ -235,7 +266,10 @@ class Tree(object):
 
     def add_data_point_to_node(self, data_point, node):
         """tree/tree.py:231-246"""
-        self._data[node] = self._data[node] + (data_point,)
+        old = self._data[node]
+        self._data[node] = old + (data_point,)
+        if self._skey is not None:
+            self._skey ^= hash((node, len(old), data_point.idx, "d"))
         self._last_node_added_to = node
         if node != self._OUTLIER_NODE_NAME:
             i = self._node_indices[node]
@@ -255,6 +289,7 @@ class Tree(object):
         lst = list(self._data[node])
         lst.remove(data_point)
         self._data[node] = tuple(lst)
+        self._skey = None
         if node != self._OUTLIER_NODE_NAME:
             i = self._node_indices[node]
             self._lp[i] = self.store.sub(self._lp[i], self.store.value_id[data_point.idx])
@@ -265,6 +300,7 @@ class Tree(object):
         lst = list(self._data[self._OUTLIER_NODE_NAME])
         lst.remove(data_point)
         self._data[self._OUTLIER_NODE_NAME] = tuple(lst)
+        self._skey = None
 
     def copy(self):
         new = Tree.__new__(Tree)
@@ -278,6 +314,7 @@ class Tree(object):
         new._lp = self._lp.copy()
         new._lr = self._lr.copy()
         new._dirty = None if self._dirty is None else self._dirty.copy()
+        new._skey = self._skey
         return new
 
     def thawed_copy(self):
@@ -373,6 +410,7 @@ class Tree(object):
         g = new._graph = SlotDiGraph()
         new._lp, new._lr = {}, {}
         new._dirty = set()
+        new._skey = None
         r = g.add_node(cls._ROOT_NODE_NAME)
         new._lp[r], new._lr[r] = store.prior_id, NO_TILE
         if len(tree_dict["graph"]) > 0:
@@ -413,6 +451,7 @@ class Tree(object):
             new._node_indices[node] = ni
             new._node_indices_rev[ni] = node
         new._dirty = None
+        new._skey = None
         new.update()
         return new
 
@@ -441,6 +480,7 @@ class Tree(object):
             self._node_indices_rev[new_idx] = node_name
         self._last_node_added_to = subtree._last_node_added_to
         self._dirty = None
+        self._skey = None
         self._update_path_to_root(parent)
 
     def remove_subtree(self, subtree):
@@ -464,6 +504,7 @@ class Tree(object):
             self._lp.pop(i, None)
             self._lr.pop(i, None)
         self._dirty = None
+        self._skey = None
         self._update_path_to_root(parent)
 
     def relabel_nodes(self):
@@ -490,3 +531,4 @@ class Tree(object):
 
         rec(self._node_indices[root])
         self._data, self._node_indices, self._node_indices_rev = data, idx, rev
+        self._skey = None

@@ -1,0 +1,48 @@
+"""CPU: the decision tape itself -- record an oracle run, replay it into the product host sampler
+(NumPy tile store): every call must line up and the traces must agree."""
+
+import numpy as np
+import pytest
+
+from oracle import sampler as osm
+from tests.chain_utils import compare_trace, load_chain
+from tests.tape import RecordingRNG, ReplayRNG
+from tests.test_host_sampler_cpu import FakeTileStore
+from tests.test_oracle_chain import run_oracle
+
+
+def record_oracle(g):
+    vals = g["values"]
+    data = [osm.Datum(i, vals[i], outlier_prob=float(g["outlier_prob"][i]) if g["outlier_prob"][i] != 0 else 0,
+                      outlier_prob_not=float(g["outlier_prob_not"][i])) for i in range(len(vals))]
+    seed, iters, particles, burnin = [int(x) for x in g["meta"]]
+    rec = RecordingRNG(np.random.default_rng(seed))
+    res = osm.run_chain(data, rec, iters, burnin=burnin, num_particles=particles, proposal=str(g["proposal"]),
+                        outlier_prob=float(g["outlier_prob_run"]))
+    return res, rec.tape
+
+
+def replay_product(g, tape, store):
+    from phyclone_b200.data.base import DataPoint
+    from phyclone_b200.run import run_phyclone_chain
+    from oracle import numerics as onum
+
+    vals = g["values"]
+    data = [DataPoint(i, vals[i], outlier_prob=float(g["outlier_prob"][i]) if g["outlier_prob"][i] != 0 else 0,
+                      outlier_prob_not=float(g["outlier_prob_not"][i]),
+                      outlier_marginal_prob=onum.outlier_marginal(vals[i])) for i in range(len(vals))]
+    seed, iters, particles, burnin = [int(x) for x in g["meta"]]
+    rep = ReplayRNG(tape)
+    res = run_phyclone_chain(burnin, True, 1.0, data, float("inf"), iters, particles, 1, 1, float(g["outlier_prob_run"]),
+                             10**9, str(g["proposal"]), 0.5, rep, ["s"], 1, 0, 0.0, store=store)
+    assert rep.done(), "product consumed %d of %d recorded draws" % (rep.pos, len(tape))
+    return res, rep
+
+
+@pytest.mark.parametrize("name", ["mixing", "syn12", "syn8_outliers", "syn6_fully", "syn6_boot"])
+def test_tape_replay_cpu(name):
+    g = load_chain(name)
+    res, tape = record_oracle(g)
+    compare_trace(res["trace"], g, 1e-12, name)  # recording does not disturb the oracle
+    res2, rep = replay_product(g, tape, FakeTileStore(g["values"]))
+    compare_trace(res2["trace"], g, 1e-9, name + " (replayed)")
