@@ -180,8 +180,7 @@ class SemiAdaptedProposalDistribution(ProposalDistribution):
             self._finish()
         if self.parent_is_empty_tree:
             return self._log_q[self.candidate_index(tree_holder)]
-        node = tree_holder.labels[self.data_point.idx]
-        assert node == tree_holder.node_last_added_to
+        node = tree_holder.node_last_added_to  # == tree_holder.labels[data_point.idx] (semi_adapted.py:44-45)
         if node in self.parent_particle.tree_nodes or node == tree_holder.outlier_node_name:
             return self.log_half + self._log_q[self.candidate_index(tree_holder)]
         old_num_roots = len(self.parent_particle.tree_roots)

@@ -15,7 +15,7 @@ _uid = itertools.count()
 
 
 class TreeHolder(object):
-    __slots__ = ("_tree_dist", "_pending", "_built", "_thawed", "tree_roots", "tree_nodes", "labels",
+    __slots__ = ("_tree_dist", "_pending", "_built", "_thawed", "tree_roots", "_tree_nodes", "_labels",
                  "node_last_added_to", "num_children_on_node_that_matters", "outlier_node_name", "log_pdf", "uid",
                  "vkey")
 
@@ -26,16 +26,28 @@ class TreeHolder(object):
         self.log_pdf = 0.0  # perm_dist is None in production (run.py:416)
         self._pending = tree_dist.prepare(tree)
         self.tree_roots = np.asarray(tree.roots)
-        self.tree_nodes = tree.nodes
+        self._tree_nodes = None
         self._built = tree  # callers hand the tree over: it is never mutated afterwards
         self.vkey = tree.structure_key()  # "equal particle" in the reference's sense (dict equality of frozen trees)
         self._thawed = None
-        self.labels = tree.labels
+        self._labels = None
         self.node_last_added_to = tree.node_last_added_to
         if self.node_last_added_to != tree.outlier_node_name:
             self.num_children_on_node_that_matters = tree.get_number_of_children(self.node_last_added_to)
         else:
             self.num_children_on_node_that_matters = 0
+
+    @property
+    def tree_nodes(self):
+        if self._tree_nodes is None:
+            self._tree_nodes = set(self._built.nodes)
+        return self._tree_nodes
+
+    @property
+    def labels(self):
+        if self._labels is None:
+            self._labels = self._built.labels
+        return self._labels
 
     @property
     def log_p(self):

@@ -52,23 +52,20 @@ class FSCRPDistribution(object):
         return -(z_term + (log_const * (num_roots - 1)))
 
     def compute_both_log_p_and_log_p_one_priors(self, tree, tree_node_data=None):
-        """distributions.py:39-101"""
-        if tree_node_data is None:
-            tree_node_data = tree.node_data
-        outlier = tree.outlier_node_name
+        """distributions.py:39-101, from the tree's running statistics (`Tree.prior_terms`)."""
+        crp_sum, multiplicity, size, _, _ = tree.prior_terms()
         num_nodes = tree.get_number_of_nodes()
         crp = 0
         crp += num_nodes * self.log_alpha
-        crp += sum(cached_log_factorial(len(v) - 1) for k, v in tree_node_data.items() if k != outlier)
-        multiplicity = tree.multiplicity
+        crp += crp_sum
         log_p = crp - (num_nodes - 1) * np.log(num_nodes + 1)
         log_p -= multiplicity
-        tree_roots = tree.roots
+        root_idx = tree._graph.successor_indices(tree._node_indices[tree.root_node_name])
         num_ways = 0
-        for root in tree_roots:
-            n = tree.get_number_of_descendants(root) + 1
+        for i in root_idx:
+            n = size[i]
             num_ways += (n - 1) * np.log(n)
-        log_p_one = crp + (-num_ways + self._compute_r_term(len(tree_roots)))
+        log_p_one = crp + (-num_ways + self._compute_r_term(len(root_idx)))
         log_p_one -= multiplicity
         return log_p, log_p_one
 
@@ -130,13 +127,12 @@ class TreeJointDistribution(object):
 
     def prepare(self, tree):
         """Record everything `compute_both_log_p_and_log_p_one` (distributions.py:186-206) needs; no launch."""
-        tree_node_data = tree.node_data
-        log_p, log_p_one = self.prior.compute_both_log_p_and_log_p_one_priors(tree, tree_node_data)
-        op = self.outlier_prior(tree_node_data, tree.outlier_node_name)
-        log_p += op
-        log_p_one += op
-        marg = [dp.outlier_marginal_prob for dp in tree.outliers]
-        return PendingScore(log_p, log_p_one, tree.score_handle(), tree.store, marg)
+        log_p, log_p_one = self.prior.compute_both_log_p_and_log_p_one_priors(tree)
+        pt = tree.prior_terms()
+        log_p += pt[3]
+        log_p_one += pt[3]
+        tree.outliers  # noqa: B018 -- the reference touches _data[-1] here, which fixes that key's position
+        return PendingScore(log_p, log_p_one, tree.score_handle(), tree.store, (pt[4],) if pt[4] != 0.0 else ())
 
     def compute_both_log_p_and_log_p_one(self, tree):
         return self.prepare(tree).resolve()

@@ -21,7 +21,7 @@ class Tree(object):
     _ROOT_NODE_NAME = "root"
     _OUTLIER_NODE_NAME = -1
     __slots__ = ("grid_size", "store", "_data", "_graph", "_node_indices", "_node_indices_rev", "_last_node_added_to",
-                 "_lp", "_lr", "_dirty", "_skey")
+                 "_lp", "_lr", "_dirty", "_skey", "_pt")
 
     def __init__(self, grid_size, store):
         self.grid_size = grid_size
@@ -39,6 +39,8 @@ class Tree(object):
         # (see thawed_copy); None = unknown, take the generic round trip
         self._dirty = set()
         self._skey = 0  # running structure hash (see structure_key); None = recompute
+        # running integer/scalar statistics behind the FS-CRP prior (see prior_terms); None = recompute
+        self._pt = [0.0, 0.0, {}, 0.0, 0.0]  # crp_sum, multiplicity, subtree node counts, outlier prior, outlier marginals
         self._add_node(self._ROOT_NODE_NAME)
 
     # ------------------------------------------------------------------ identity
@@ -95,6 +97,58 @@ class Tree(object):
                     k ^= hash((node, pos, dp.idx, "d"))
             self._skey = k
         return (self._skey, self._last_node_added_to, self._graph.n_nodes)
+
+    def prior_terms(self):
+        """(crp_sum, multiplicity, {graph idx: nodes in its subtree}, outlier_prior, outlier_marginals): the tree
+        statistics FSCRPDistribution / TreeJointDistribution need (tree/distributions.py:54-133, 186-219), kept
+        up to date in O(1) by the SMC edits instead of being re-derived from the whole tree per candidate."""
+        pt = self._pt
+        if pt is None:
+            g = self._graph
+            out = self._OUTLIER_NODE_NAME
+            root = self._ROOT_NODE_NAME
+            crp = sum(cached_log_factorial(len(v) - 1) for k, v in self._data.items() if k != out and k != root)
+            mult = sum(map(cached_log_factorial, map(g.out_degree, g.node_indices())))
+            size = {}
+
+            def rec(i):
+                n = 1
+                for c in g.successor_indices(i):
+                    n += rec(c)
+                size[i] = n
+                return n
+
+            rec(self._node_indices[root])
+            oprior = 0
+            for node, lst in self._data.items():
+                if node == root:
+                    continue
+                for dp in lst:
+                    if dp.outlier_prob != 0:
+                        oprior += dp.outlier_prob if node == out else dp.outlier_prob_not
+            omarg = 0.0
+            for dp in self._data[out]:
+                omarg += dp.outlier_marginal_prob
+            pt = self._pt = [crp, mult, size, oprior, omarg]
+        return pt
+
+    def _pt_attach(self, node, data_points, old_len):
+        pt = self._pt
+        if pt is None:
+            return
+        out = self._OUTLIER_NODE_NAME
+        if node != out:
+            n = old_len
+            for _ in data_points:
+                # sum of log((len-1)!) over nodes: a node going from n to n+1 points gains log(n) (n >= 1)
+                if n >= 1:
+                    pt[0] += cached_log_factorial(n) - cached_log_factorial(n - 1)
+                n += 1
+        for dp in data_points:
+            if dp.outlier_prob != 0:
+                pt[3] += dp.outlier_prob if node == out else dp.outlier_prob_not
+            if node == out:
+                pt[4] += dp.outlier_marginal_prob
 
     # ------------------------------------------------------------------ queries
     @staticmethod
@@ -235,6 +289,7 @@ class Tree(object):
             if self._skey is not None:
                 for pos, dp in enumerate(data, len(old)):
                     self._skey ^= hash((node, pos, dp.idx, "d"))
+            self._pt_attach(node, data, len(old))
             self._absorb(i, data)
         return i
 
@@ -258,6 +313,15 @@ class Tree(object):
             if k is not None:
                 k ^= hash((e, r, ci)) ^ hash((e, i, ci))  # the freed slot is the one re-used
         self._skey = k
+        pt = self._pt
+        if pt is not None:
+            nk = len(children)
+            size = pt[2] = pt[2].copy()
+            size[i] = 1 + sum(size[self._node_indices[c]] for c in children)
+            size[r] = size.get(r, 1) + 1
+            # out-degrees: the dummy root loses nk children and gains one, the new node has nk
+            d_root = g.out_degree(r)
+            pt[1] += cached_log_factorial(d_root) - cached_log_factorial(d_root + nk - 1) + cached_log_factorial(nk)
         self._last_node_added_to = node
         if self._dirty is not None:
             self._dirty.add(i)
@@ -270,6 +334,7 @@ class Tree(object):
         self._data[node] = old + (data_point,)
         if self._skey is not None:
             self._skey ^= hash((node, len(old), data_point.idx, "d"))
+        self._pt_attach(node, (data_point,), len(old))
         self._last_node_added_to = node
         if node != self._OUTLIER_NODE_NAME:
             i = self._node_indices[node]
@@ -290,6 +355,7 @@ class Tree(object):
         lst.remove(data_point)
         self._data[node] = tuple(lst)
         self._skey = None
+        self._pt = None
         if node != self._OUTLIER_NODE_NAME:
             i = self._node_indices[node]
             self._lp[i] = self.store.sub(self._lp[i], self.store.value_id[data_point.idx])
@@ -301,6 +367,7 @@ class Tree(object):
         lst.remove(data_point)
         self._data[self._OUTLIER_NODE_NAME] = tuple(lst)
         self._skey = None
+        self._pt = None
 
     def copy(self):
         new = Tree.__new__(Tree)
@@ -315,6 +382,8 @@ class Tree(object):
         new._lr = self._lr.copy()
         new._dirty = None if self._dirty is None else self._dirty.copy()
         new._skey = self._skey
+        pt = self._pt
+        new._pt = None if pt is None else pt.copy()  # the size dict is replaced, never mutated, on edit
         return new
 
     def thawed_copy(self):
@@ -411,6 +480,7 @@ class Tree(object):
         new._lp, new._lr = {}, {}
         new._dirty = set()
         new._skey = None
+        new._pt = None
         r = g.add_node(cls._ROOT_NODE_NAME)
         new._lp[r], new._lr[r] = store.prior_id, NO_TILE
         if len(tree_dict["graph"]) > 0:
@@ -452,6 +522,7 @@ class Tree(object):
             new._node_indices_rev[ni] = node
         new._dirty = None
         new._skey = None
+        new._pt = None
         new.update()
         return new
 
@@ -481,6 +552,7 @@ class Tree(object):
         self._last_node_added_to = subtree._last_node_added_to
         self._dirty = None
         self._skey = None
+        self._pt = None
         self._update_path_to_root(parent)
 
     def remove_subtree(self, subtree):
@@ -505,6 +577,7 @@ class Tree(object):
             self._lr.pop(i, None)
         self._dirty = None
         self._skey = None
+        self._pt = None
         self._update_path_to_root(parent)
 
     def relabel_nodes(self):
@@ -532,3 +605,4 @@ class Tree(object):
         rec(self._node_indices[root])
         self._data, self._node_indices, self._node_indices_rev = data, idx, rev
         self._skey = None
+        self._pt = None
