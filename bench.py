@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""Benchmark of the PhyClone hot path on B200 (contract: see the task statement / DESIGN.md section 6).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (sm_100a kernels + host sampler)
+    python bench.py --impl reference --steps K --warmup W     # CPU arm: the oracle port of the reference
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   # one chain per GPU
+
+A "step" is one particle-Gibbs iteration = one trip of the reference's main loop (run.py:261-288):
+conditional-SMC sweep over all data points with N particles, data-point Gibbs, prune-regraph, relabel and
+concentration update, on the synthetic BASELINE.json configs[1] shape (50 clusters x 8 samples, grid 101,
+100 particles, one chain per GPU).  `value` = PG iterations/s summed over all chains (chains are
+independent, so N GPUs run N chains: weak scaling, no data-path collective).
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = {"clusters": 50, "samples": 8, "grid": 101, "particles": 100, "muts_per_cluster": 10, "depth": 200,
+       "proposal": "semi-adapted", "resample_threshold": 0.5, "precision": 400, "density": "beta-binomial"}
+WORKLOAD = ("synthetic 50 clusters x 8 samples, grid 101, 100 particles, semi-adapted proposal, 1 chain per GPU "
+            "(BASELINE.json configs[1]); data seed 0, chain seed 1")
+METRIC = "pg_iterations_per_sec"
+UNIT = "PG iterations/s"
+
+
+# ----------------------------------------------------------------------------- inputs
+def synthetic_counts():
+    from phyclone_b200.simulate import simulate_counts
+
+    return simulate_counts(CFG["clusters"], CFG["samples"], CFG["muts_per_cluster"], CFG["depth"], seed=0)
+
+
+def chain_rng(rank, world):
+    """run.py:87-139: a single chain uses the main Generator itself, several chains use its spawned children."""
+    main = np.random.default_rng(1)
+    return main if world == 1 else main.spawn(world)[rank]
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._thr = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._thr.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        reasons = []
+        for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
+            if any(r[col].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows), "power_w_max": max(float(r[2]) for r in self.rows)}
+
+
+# ----------------------------------------------------------------------------- CPU arms
+def oracle_chain_rate(iters, warmup, quiet=True):
+    """PG iterations/s of the CPU port of the reference (oracle/sampler.py, with the reference's tile
+    caches on: its real configuration) on the same workload; 1 core (a chain is single-threaded)."""
+    from oracle import sampler as osm
+    from oracle.synthetic import make_synthetic
+
+    syn = make_synthetic(CFG["clusters"], CFG["samples"], CFG["grid"], CFG["muts_per_cluster"], CFG["depth"], seed=0,
+                         density=CFG["density"], precision=CFG["precision"])
+    data = [osm.Datum(i, v) for i, v in enumerate(syn["values"])]
+    marks = []
+    res = osm.run_chain(data, np.random.default_rng(1), warmup + iters, burnin=1, num_particles=CFG["particles"],
+                        proposal=CFG["proposal"], resample_threshold=CFG["resample_threshold"], use_tile_caches=True,
+                        on_iteration=lambda i, e: marks.append(time.perf_counter()))
+    t0 = marks[warmup - 1] if warmup > 0 else None
+    if t0 is None:
+        raise ValueError("need at least one warm-up iteration for the CPU arm")
+    elapsed = marks[-1] - t0
+    return iters / elapsed, elapsed, res["extensions"]
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # bounded sample: at ~10 s per iteration, cap the timed iterations so the run ends within a few minutes
+    iters = min(args.steps, 12)
+    warm = min(max(args.warmup, 1), 2)
+    rate, elapsed, ext = oracle_chain_rate(iters, warm)
+    sample = ("%d timed PG iterations of the config after 1 burn-in + %d warm-up iterations (%.1f s); a chain is "
+              "single-threaded in the reference" % (iters, warm, elapsed))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 / rate, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": dict(CFG, workload=WORKLOAD),
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "CPU port of the reference sampler (oracle/sampler.py, tile caches on); /root/reference is a Python "
+                "package with an uninstallable Rust dependency and does not exist on the GPU box",
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from phyclone_b200 import ops
+    from phyclone_b200.data.base import make_data_points
+    from phyclone_b200.run import Chain
+    from phyclone_b200.tiles import TileStore
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- inputs (one-off, a2/a3/a4 of the path on the device; not timed)
+    c = synthetic_counts()
+    grids = ops.likelihood_grid(c["ref"], c["alt"], c["tumour_content"], c["cn"], c["mu"], c["log_pi"], c["n_geno"],
+                                CFG["grid"], CFG["density"], CFG["precision"])
+    values = ops.cluster_sum(grids, c["cluster_off"])
+    data = make_data_points(values)
+    fp64_peak, _ = ops.fp64_peak(8192)
+    fp64_peak = max(fp64_peak, ops.fp64_peak(8192)[0])
+
+    store = TileStore(values, device=dev)
+    chain = Chain(data, chain_rng(rank, world), num_particles=CFG["particles"], proposal=CFG["proposal"],
+                  resample_threshold=CFG["resample_threshold"], store=store)
+    chain.burnin_step()
+    for _ in range(args.warmup):
+        chain.step()
+
+    stream = torch.cuda.current_stream(dev)
+
+    def timed(n_steps, before_step=None, after_step=None):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(n_steps):
+            if before_step:
+                before_step()
+            chain.step()
+            if after_step:
+                after_step()
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- timed region 1: inputs resident in HBM
+    store.arena.job_timing = []
+    s0 = dict(chain.stats)
+    launches0 = ops.launch_count()
+    staged0 = store.arena.staged_bytes
+    with ClockSampler(local) as clocks:
+        ms = timed(args.steps)
+    launches = ops.launch_count() - launches0
+    s1 = dict(chain.stats)
+    job_timing, store.arena.job_timing = store.arena.job_timing, None
+    kernel_ms = sum(a.elapsed_time(b) for a, b, _, _ in job_timing)
+    conv_pairs = sum(t[3] for t in job_timing)
+    flop = conv_pairs * CFG["samples"] * CFG["grid"] * (CFG["grid"] + 1)  # 2 flop x S*G*(G+1)/2 FMA per pair conv
+    n_launch = max(len(job_timing), 1)
+    achieved = flop / max(kernel_ms * 1e-3, 1e-12)
+    value = world * args.steps / (ms * 1e-3)
+
+    # ---- timed region 2: end to end through the host-facing API, inputs re-sent from pinned host memory
+    d2h0, st0 = chain.stats["d2h_bytes"], store.arena.staged_bytes
+    sink = []
+    ms_e2e = timed(args.steps, before_step=lambda: store.upload_values(values),
+                   after_step=lambda: sink.append(chain.log_p_one()))
+    e2e_value = world * args.steps / (ms_e2e * 1e-3)
+    h2d = values.nbytes + (store.arena.staged_bytes - st0) / args.steps
+    d2h = (chain.stats["d2h_bytes"] - d2h0) / args.steps
+
+    # ---- saturated-batch figure for the same kernel (how far the kernel itself goes when a launch is big)
+    sat = None
+    if rank == 0:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "scripts"))
+            from kernel_bench import bench_variant
+
+            r = bench_variant(CFG["samples"], CFG["grid"], -1, 32768, 8, 4096, 5)
+            sat = {"achieved": r["tflops"], "unit": "TFLOP/s", "frac": r["tflops"] * 1e12 / fp64_peak,
+                   "launch": "32768 jobs x 8 children"}
+        except Exception as e:  # noqa: BLE001
+            sat = {"error": str(e)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, elapsed, _ = oracle_chain_rate(2, 1)
+        cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "2 PG iterations of the same config after 1 burn-in + 1 warm-up iteration (%.1f s), "
+                         "oracle/sampler.py with the reference's tile caches on" % elapsed}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:  # noqa: BLE001
+            pass
+        ext = (s1["extensions"] - s0["extensions"]) * world
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": dict(CFG, workload=WORKLOAD, chains=world,
+                           l2="no explicit flush: one iteration allocates %d fresh tiles (~%d MB) in the arena, larger than "
+                              "the 126 MB L2" % ((s1["adds"] + s1["node_jobs"] - s0["adds"] - s0["node_jobs"]) // args.steps,
+                                                 (s1["adds"] + s1["node_jobs"] - s0["adds"] - s0["node_jobs"]) // args.steps
+                                                 * store.arena.layout.tile_elems * 16 // (1 << 20))),
+            "particle_extensions_per_sec": ext / (ms * 1e-3),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "fp64", "kernel": "node_jobs_kernel", "achieved": achieved / 1e12,
+                         "peak": fp64_peak / 1e12, "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": None,
+                         "launches": len(job_timing), "avg_launch_us": 1e3 * kernel_ms / n_launch,
+                         "flop_per_launch": flop / n_launch, "kernel_share_of_step": kernel_ms / ms,
+                         "peak_source": "pcb_fp64_peak (dependent-DFMA-chain microbenchmark) measured in this run; "
+                                        "MEASURED_PEAKS.json has no FP64 figure (hbm_gbs=%s)" % peaks.get("hbm_gbs"),
+                         "saturated_batch": sat},
+            "cpu_baseline": cpu,
+            "clocks": clocks.summary(),
+            "per_step": {k: (s1[k] - s0[k]) / args.steps for k in ("flushes", "launches", "node_jobs", "adds", "scores",
+                                                                    "conv_pairs", "memo_hits", "extensions")},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -62,6 +62,8 @@ class DeviceArena:
         self.alloc = TileAllocator(self.capacity)
         self.prior = -float(np.log(G))
         self._staging = {}
+        self.staged_bytes = 0  # host->device bytes of job tables / id lists so far
+        self.job_timing = None  # set to a list to record (start_event, end_event, n_jobs, conv_pairs) per launch
 
     # ---------------------------------------------------------------- plumbing
     def _stream(self):
@@ -83,6 +85,7 @@ class DeviceArena:
         else:
             st[2].synchronize()  # the previous async copy out of this pinned buffer must have drained
         host, dev, ev = st
+        self.staged_bytes += 4 * n
         host.numpy()[:n] = arr
         dev[:n].copy_(host[:n], non_blocking=True)
         ev.record(torch.cuda.current_stream(self.device))
@@ -141,16 +144,22 @@ class DeviceArena:
         pl = pt = None
         if rows is not None:
             pl, pt = rows[0].data_ptr(), rows[1].data_ptr()
+        timing = self.job_timing
+        if timing is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(torch.cuda.current_stream(self.device))
         _lib.check(
             self.lib.pcb_node_jobs_dev(C.byref(self.c), base, base + 4 * n * JOB_INTS, n, self.prior, pl, pt, self._stream())
         )
+        if timing is not None:
+            e1.record(torch.cuda.current_stream(self.device))
+            timing.append((e0, e1, n, int(tab[:, 1].sum()) - n))
 
     def reduce_rows(self, rows):
+        """rows: contiguous [2, n_slots, S] -> [2, n_slots] (sum over samples in order), one launch."""
         n_slots = rows.shape[1]
         out = torch.empty((2, n_slots), dtype=torch.float64, device=self.device)
-        st = self._stream()
-        _lib.check(self.lib.pcb_reduce_rows_dev(rows[0].data_ptr(), n_slots, self.S, out[0].data_ptr(), st))
-        _lib.check(self.lib.pcb_reduce_rows_dev(rows[1].data_ptr(), n_slots, self.S, out[1].data_ptr(), st))
+        _lib.check(self.lib.pcb_reduce_rows_dev(rows.data_ptr(), 2 * n_slots, self.S, out.data_ptr(), self._stream()))
         return out
 
     # -------------------------------------------------------------------- jobs

@@ -42,6 +42,72 @@ def setup_kernel(outlier_prob, proposal, rng, tree_dist, store):
     return KERNELS[proposal](tree_dist, rng, store, outlier_proposal_prob=outlier_proposal_prob)
 
 
+class Chain(object):
+    """One MCMC chain = one Python thread driving one CUDA stream and one device arena (run.py:177-380).
+    `burnin_step()` / `step()` are one trip of the reference's burn-in / main loops."""
+
+    def __init__(self, data, rng, num_particles=100, proposal="semi-adapted", resample_threshold=0.5, outlier_prob=0.0,
+                 concentration_value=1.0, concentration_update=True, num_samples_data_point=1,
+                 num_samples_prune_regraph=1, device=None, store=None):
+        self.data = data
+        self.rng = rng
+        if store is None:
+            store = TileStore(np.array([dp.value for dp in data]), device=device)
+        self.store = store
+        self.tree_dist = TreeJointDistribution(FSCRPDistribution(concentration_value))
+        self.kernel = setup_kernel(outlier_prob, proposal, rng, self.tree_dist, store)
+        self.dp_sampler = DataPointSampler(self.tree_dist, rng, outliers=(outlier_prob > 0))
+        self.prg_sampler = PruneRegraphSampler(self.tree_dist, rng)
+        self.conc_sampler = GammaPriorConcentrationSampler(0.01, 0.01, rng=rng)
+        self.burnin_sampler = UnconditionalSMCSampler(self.kernel, num_particles=num_particles,
+                                                      resample_threshold=resample_threshold)
+        self.tree_sampler = ParticleGibbsTreeSampler(self.kernel, rng, num_particles=num_particles,
+                                                     resample_threshold=resample_threshold)
+        self.concentration_update = concentration_update
+        self.num_samples_data_point = num_samples_data_point
+        self.num_samples_prune_regraph = num_samples_prune_regraph
+        self.tree = Tree.get_single_node_tree(data, store)
+        self.iteration = 0
+
+    def _local_moves(self, tree):
+        for _ in range(self.num_samples_data_point):
+            tree = self.dp_sampler.sample_tree(tree)
+        for _ in range(self.num_samples_prune_regraph):
+            tree = self.prg_sampler.sample_tree(tree)
+        tree.relabel_nodes()
+        return tree
+
+    def burnin_step(self):
+        """run.py:323-361"""
+        self.kernel.clear_proposal_dist_caches()
+        self.store.reset()  # new arena generation: the carried tree is only read structurally from here on
+        self.tree = self._local_moves(self.burnin_sampler.sample_tree(self.tree))
+
+    def step(self):
+        """run.py:261-288: PG sweep, data-point Gibbs, prune-regraph, relabel, concentration update."""
+        self.kernel.clear_proposal_dist_caches()
+        self.store.reset()
+        self.rng.random()  # run.py:268: the subtree-move coin is drawn even when its probability is 0
+        tree = self.tree = self._local_moves(self.tree_sampler.sample_tree(self.tree))
+        if self.concentration_update:
+            node_sizes = [len(v) for k, v in tree.node_data.items() if k != tree.outlier_node_name]
+            self.tree_dist.prior.alpha = self.conc_sampler.sample(self.tree_dist.prior.alpha, len(node_sizes),
+                                                                  sum(node_sizes))
+        self.iteration += 1
+
+    def log_p_one(self):
+        return self.tree_dist.log_p_one(self.tree)
+
+    def trace_entry(self, i, elapsed):
+        """run.py:293-302"""
+        return {"iter": i, "time": elapsed, "alpha": self.tree_dist.prior.alpha, "log_p_one": self.log_p_one(),
+                "tree": self.tree.to_dict()}
+
+    @property
+    def stats(self):
+        return dict(self.store.stats, extensions=self.kernel.num_extensions)
+
+
 def run_phyclone_chain(burnin, concentration_update, concentration_value, data, max_time, num_iters, num_particles,
                        num_samples_data_point, num_samples_prune_regraph, outlier_prob, print_freq, proposal,
                        resample_threshold, rng, samples, thin, chain_num, subtree_update_prob, device=None,
@@ -49,54 +115,24 @@ def run_phyclone_chain(burnin, concentration_update, concentration_value, data, 
     """run.py:177-232 (+ :235-380).  Returns {"data", "samples", "trace", "chain_num", "stats"}."""
     if subtree_update_prob != 0.0:
         raise NotImplementedError("the subtree particle-Gibbs move is outside the B200 hot path (DESIGN.md section 7)")
-    if store is None:
-        store = TileStore(np.array([dp.value for dp in data]), device=device)
-    tree_dist = TreeJointDistribution(FSCRPDistribution(concentration_value))
-    kernel = setup_kernel(outlier_prob, proposal, rng, tree_dist, store)
-    dp_sampler = DataPointSampler(tree_dist, rng, outliers=(outlier_prob > 0))
-    prg_sampler = PruneRegraphSampler(tree_dist, rng)
-    conc_sampler = GammaPriorConcentrationSampler(0.01, 0.01, rng=rng)
-    burnin_sampler = UnconditionalSMCSampler(kernel, num_particles=num_particles, resample_threshold=resample_threshold)
-    tree_sampler = ParticleGibbsTreeSampler(kernel, rng, num_particles=num_particles,
-                                            resample_threshold=resample_threshold)
+    chain = Chain(data, rng, num_particles=num_particles, proposal=proposal, resample_threshold=resample_threshold,
+                  outlier_prob=outlier_prob, concentration_value=concentration_value,
+                  concentration_update=concentration_update, num_samples_data_point=num_samples_data_point,
+                  num_samples_prune_regraph=num_samples_prune_regraph, device=device, store=store)
     timer = Timer()
-    tree = Tree.get_single_node_tree(data, store)
-
-    def local_moves(tree):
-        for _ in range(num_samples_data_point):
-            tree = dp_sampler.sample_tree(tree)
-        for _ in range(num_samples_prune_regraph):
-            tree = prg_sampler.sample_tree(tree)
-        tree.relabel_nodes()
-        return tree
-
     for i in range(burnin):
         with timer:
-            kernel.clear_proposal_dist_caches()
-            store.reset()
-            tree = local_moves(burnin_sampler.sample_tree(tree))
+            chain.burnin_step()
             if timer.elapsed > max_time:
                 break
-
-    def entry(i, tree):
-        return {"iter": i, "time": timer.elapsed, "alpha": tree_dist.prior.alpha,
-                "log_p_one": tree_dist.log_p_one(tree), "tree": tree.to_dict()}
-
-    trace = [entry(0, tree)]
+    trace = [chain.trace_entry(0, timer.elapsed)]
     for i in range(num_iters):
         with timer:
-            kernel.clear_proposal_dist_caches()
-            store.reset()
-            rng.random()  # run.py:268: the subtree-move coin is drawn even when its probability is 0
-            tree = local_moves(tree_sampler.sample_tree(tree))
-            if concentration_update:
-                node_sizes = [len(v) for k, v in tree.node_data.items() if k != tree.outlier_node_name]
-                tree_dist.prior.alpha = conc_sampler.sample(tree_dist.prior.alpha, len(node_sizes), sum(node_sizes))
+            chain.step()
             if i % thin == 0:
-                trace.append(entry(i, tree))
+                trace.append(chain.trace_entry(i, timer.elapsed))
             if on_iteration is not None:
                 on_iteration(i, trace[-1])
             if timer.elapsed >= max_time:
                 break
-    return {"data": data, "samples": samples, "trace": trace, "chain_num": chain_num,
-            "stats": dict(store.stats, extensions=kernel.num_extensions)}
+    return {"data": data, "samples": samples, "trace": trace, "chain_num": chain_num, "stats": chain.stats}

@@ -41,14 +41,24 @@ class TileStore:
         self.value_id = list(range(al.alloc(T), al.top))
         self.single_id = list(range(al.alloc(T), al.top))
         self.prior_id = al.alloc(1)
-        self.arena.import_tiles(values, self.value_id)
         self.arena.import_tiles(np.full((1, S, G), self.prior), [self.prior_id])
-        self.arena.tile_add([self.prior_id] * T, self.value_id, self.single_id, 0.0)
+        self._pinned = torch.empty((T, S, G), dtype=torch.float64, pin_memory=True)
+        self._staged = torch.empty((T, S, G), dtype=torch.float64, device=self.device)
         al.freeze()
-        self.h2d_bytes = values.nbytes
+        self.upload_values(values)
         self.stats = {"flushes": 0, "adds": 0, "node_jobs": 0, "scores": 0, "launches": 0, "memo_hits": 0,
                       "d2h_bytes": 0, "conv_pairs": 0}
         self.reset()
+
+    def upload_values(self, values):
+        """(Re)load the data points' grids: pinned host buffer -> HBM -> arena tiles V_d and P_d = prior + V_d.
+        Returns the bytes copied host->device."""
+        self._pinned.numpy()[...] = values
+        self._staged.copy_(self._pinned, non_blocking=True)
+        self.arena.import_tiles(self._staged, self.value_id)
+        self.arena.tile_add([self.prior_id] * self.T, self.value_id, self.single_id, 0.0)
+        self.h2d_bytes = self._pinned.numel() * 8
+        return self.h2d_bytes
 
     # ------------------------------------------------------------------ state
     def reset(self):
@@ -190,7 +200,7 @@ class TileStore:
                 st["node_jobs"] += n
         if n_slots:
             sums = ar.reduce_rows(rows)  # [2, n_slots] on device
-            st["launches"] += 2
+            st["launches"] += 1
             host = sums.cpu().numpy()  # the one synchronising D2H copy of the step
             st["d2h_bytes"] += host.nbytes
             st["scores"] += n_slots
