@@ -136,3 +136,67 @@ def run_phyclone_chain(burnin, concentration_update, concentration_value, data, 
             if timer.elapsed >= max_time:
                 break
     return {"data": data, "samples": samples, "trace": trace, "chain_num": chain_num, "stats": chain.stats}
+
+
+# ------------------------------------------------------------------------------------------------
+# several chains: one process per GPU, chains sharded over ranks, traces gathered at the end
+# ------------------------------------------------------------------------------------------------
+def chain_generators(seed, num_chains):
+    """run.py:57,87-113: one chain uses the main Generator itself, several use its spawned children."""
+    rng_main = np.random.default_rng(seed)
+    return [rng_main] if num_chains == 1 else rng_main.spawn(num_chains)
+
+
+def chains_of_rank(num_chains, rank, world_size):
+    """Chains are independent (run.py:111-149), so they shard with no data-path collective: chain c runs on
+    rank c % world_size."""
+    return [c for c in range(num_chains) if c % world_size == rank]
+
+
+def gather_results(results, rank, world_size, device=None):
+    """The one collective of the run: every rank's {chain_num: result} dict, pickled, gathered on rank 0
+    (NCCL over NVLink when the process group is NCCL; traces are MBs, so this is latency-irrelevant)."""
+    import pickle
+
+    import torch
+    import torch.distributed as dist
+
+    if world_size == 1:
+        return results
+    payload = np.frombuffer(pickle.dumps(results, protocol=pickle.HIGHEST_PROTOCOL), dtype=np.uint8).copy()
+    on_gpu = dist.get_backend() == "nccl"
+    dev = device if on_gpu else torch.device("cpu")
+    n = torch.tensor([payload.size], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros_like(n) for _ in range(world_size)]
+    dist.all_gather(sizes, n)
+    cap = int(max(s.item() for s in sizes))
+    buf = torch.zeros(cap, dtype=torch.uint8, device=dev)
+    buf[: payload.size] = torch.from_numpy(payload).to(dev)
+    bufs = [torch.zeros_like(buf) for _ in range(world_size)]
+    dist.all_gather(bufs, buf)
+    if rank != 0:
+        return None
+    merged = {}
+    for r in range(world_size):
+        part = pickle.loads(bufs[r][: int(sizes[r].item())].cpu().numpy().tobytes())
+        merged.update(part)
+    return dict(sorted(merged.items()))
+
+
+def run_chains(data, samples, num_chains=1, seed=None, burnin=100, num_iters=5000, num_particles=80,
+               concentration_value=1.0, concentration_update=True, max_time=float("inf"), num_samples_data_point=1,
+               num_samples_prune_regraph=1, outlier_prob=0, print_freq=100, proposal="semi-adapted",
+               resample_threshold=0.5, thin=1, subtree_update_prob=0.0, rank=0, world_size=1, device=None,
+               store_factory=None):
+    """The chain part of the reference's `run()` (run.py:28-149) with its ProcessPoolExecutor replaced by
+    rank sharding: call it from every rank of a torch.distributed job (or alone).  Returns {chain_num: result}
+    on rank 0 and None elsewhere."""
+    rngs = chain_generators(seed, num_chains)
+    results = {}
+    for c in chains_of_rank(num_chains, rank, world_size):
+        store = None if store_factory is None else store_factory(np.array([dp.value for dp in data]))
+        results[c] = run_phyclone_chain(burnin, concentration_update, concentration_value, data, max_time, num_iters,
+                                        num_particles, num_samples_data_point, num_samples_prune_regraph, outlier_prob,
+                                        print_freq, proposal, resample_threshold, rngs[c], samples, thin, c,
+                                        subtree_update_prob, device=device, store=store)
+    return gather_results(results, rank, world_size, device=device)

@@ -61,7 +61,7 @@ def main():
 
         pr = cProfile.Profile()
         res = pr.runcall(go)
-        pstats.Stats(pr).sort_stats("cumulative").print_stats(45)
+        pstats.Stats(pr).sort_stats(os.environ.get("PROF_SORT", "cumulative")).print_stats(60)
     else:
         res = go()
     wall = time.time() - t0
