@@ -13,7 +13,8 @@ import numpy as np
 
 from ..tree.tree import Tree
 from ..utils.math import cached_log_binomial_coefficient, discrete_rvs, log_binomial_coefficient, log_normalize
-from .swarm import Particle, TreeHolder
+from .forest_state import ATTACH, NEW, OUTLIER, ForestState
+from .swarm import Particle, StateHolder, TreeHolder
 
 
 class _LRU(object):
@@ -181,7 +182,9 @@ class SemiAdaptedProposalDistribution(ProposalDistribution):
         if self.parent_is_empty_tree:
             return self._log_q[self.candidate_index(tree_holder)]
         node = tree_holder.node_last_added_to  # == tree_holder.labels[data_point.idx] (semi_adapted.py:44-45)
-        if node in self.parent_particle.tree_nodes or node == tree_holder.outlier_node_name:
+        # "node in parent.tree_nodes": SMC only ever adds to a ROOT of the parent, or to a brand-new node whose name
+        # (= number of nodes) no parent node has
+        if node == tree_holder.outlier_node_name or node in self.parent_particle.tree_roots:
             return self.log_half + self._log_q[self.candidate_index(tree_holder)]
         old_num_roots = len(self.parent_particle.tree_roots)
         num_children = tree_holder.num_children_on_node_that_matters
@@ -222,10 +225,72 @@ class SemiAdaptedProposalDistribution(ProposalDistribution):
         return self.kernel._new_tree_cache.get(key, make)
 
 
+class StateSemiAdaptedProposalDistribution(object):
+    """Semi-adapted proposal (smc/kernels/semi_adapted.py:11-183) evaluated on root-level forest states: same
+    candidates, order, probabilities and RNG calls as the tree-copying version above, O(#roots) work each."""
+
+    def __init__(self, data_point, kernel, parent_particle, parent_state, base_state):
+        self.data_point = data_point
+        self.kernel = kernel
+        self.tree_dist = kernel.tree_dist
+        self.parent_particle = parent_particle
+        self._rng = kernel.rng
+        self.log_half = kernel.log_half
+        self._pstate = parent_state
+        ph = parent_particle._holder if parent_particle is not None else None
+        self._pholder = ph
+        td = self.tree_dist
+        trees = []
+        if parent_particle is not None:
+            for node in parent_particle.tree_roots:
+                trees.append(StateHolder(ph, parent_state, base_state, ATTACH, data_point, node, td))
+        if kernel.outlier_proposal_prob > 0:
+            trees.append(StateHolder(ph, parent_state, base_state, OUTLIER, data_point, None, td))
+        self.parent_is_empty_tree = parent_particle is None or len(parent_particle.tree_roots) == 0
+        if self.parent_is_empty_tree:
+            trees.append(StateHolder(ph, parent_state, base_state, NEW, data_point, frozenset(), td))
+        else:
+            self._cached_log_old_num_roots = np.log(len(parent_particle.tree_roots) + 1)
+        self._curr_trees = trees
+        self._index = {h.uid: i for i, h in enumerate(trees)}
+        self._log_q = None
+        self._q_dist = None
+
+    _finish = SemiAdaptedProposalDistribution._finish
+    candidate_index = SemiAdaptedProposalDistribution.candidate_index
+    log_p = SemiAdaptedProposalDistribution.log_p
+    sample = SemiAdaptedProposalDistribution.sample
+    _propose_existing_node = SemiAdaptedProposalDistribution._propose_existing_node
+
+    def _propose_new_node(self):
+        num_roots = len(self.parent_particle.tree_roots)
+        num_children = self._rng.integers(0, num_roots + 1)
+        if num_children == 0:
+            children = []
+        else:
+            children = self._rng.choice(self.parent_particle.tree_roots, num_children, replace=False)
+        children = frozenset(children)
+        key = (self._pholder.vkey, self.data_point.idx, children)
+        # the new node always goes onto the parent re-read through from_dict (semi_adapted.py:186-194)
+        return self.kernel._new_tree_cache.get(
+            key, lambda: StateHolder(self._pholder, self._pstate, self._pstate, NEW, self.data_point, children,
+                                     self.tree_dist))
+
+
 class SemiAdaptedKernel(Kernel):
     log_half = np.log(0.5)
 
+    use_states = True  # evaluate candidates from root-level ForestStates instead of copied trees
+
     def _make_proposal(self, data_point, parent_particle, parent_tree):
+        if self.use_states:
+            if parent_particle is None:
+                empty = ForestState.empty(self.store, data_point.grid_size)
+                return StateSemiAdaptedProposalDistribution(data_point, self, None, empty, empty)
+            pstate = parent_particle._holder.thawed_state()
+            base = pstate if parent_tree is None else ForestState.from_tree(parent_tree)
+            if pstate is not None and base is not None:
+                return StateSemiAdaptedProposalDistribution(data_point, self, parent_particle, pstate, base)
         return SemiAdaptedProposalDistribution(data_point, self, parent_particle, parent_tree)
 
 

@@ -17,7 +17,7 @@ _uid = itertools.count()
 class TreeHolder(object):
     __slots__ = ("_tree_dist", "_pending", "_built", "_thawed", "tree_roots", "_tree_nodes", "_labels",
                  "node_last_added_to", "num_children_on_node_that_matters", "outlier_node_name", "log_pdf", "uid",
-                 "vkey")
+                 "vkey", "_tstate")
 
     def __init__(self, tree, tree_dist, perm_dist=None):
         self.uid = next(_uid)  # cache key (object ids can be recycled within an iteration)
@@ -30,6 +30,7 @@ class TreeHolder(object):
         self._built = tree  # callers hand the tree over: it is never mutated afterwards
         self.vkey = tree.structure_key()  # "equal particle" in the reference's sense (dict equality of frozen trees)
         self._thawed = None
+        self._tstate = False
         self._labels = None
         self.node_last_added_to = tree.node_last_added_to
         if self.node_last_added_to != tree.outlier_node_name:
@@ -63,6 +64,96 @@ class TreeHolder(object):
         tree whose adjacency follows slot order and whose tiles were all refreshed."""
         if self._thawed is None:
             self._thawed = self._built.thawed_copy()
+        return self._thawed.copy()
+
+    def thawed_state(self):
+        """Root-level `ForestState` of `self.tree` (None if the tree is not SMC-grown)."""
+        if self._tstate is False:
+            from .forest_state import ForestState
+
+            if self._thawed is None:
+                self._thawed = self._built.thawed_copy()
+            self._tstate = ForestState.from_tree(self._thawed)
+        return self._tstate
+
+
+class StateHolder(object):
+    """Holder of `thawed(parent) + one SMC edit`, evaluated from root-level `ForestState`s instead of a copied
+    `Tree` (see forest_state.py).  Same read interface as `TreeHolder`; the actual tree is only rebuilt, by
+    replaying the edits, when `.tree` is asked for."""
+
+    __slots__ = ("uid", "kind", "dp", "arg", "_parent_holder", "_parent_state", "_score", "tree_roots",
+                 "node_last_added_to", "num_children_on_node_that_matters", "outlier_node_name", "log_pdf", "_tstate",
+                 "_thawed", "_store", "_grid_size")
+
+    def __init__(self, parent_holder, parent_state, base_state, kind, dp, arg, tree_dist):
+        from .forest_state import NEW, OUTLIER, score_edit
+
+        self.uid = next(_uid)
+        self.kind, self.dp, self.arg = kind, dp, arg
+        self._parent_holder = parent_holder
+        self._parent_state = parent_state
+        self._store, self._grid_size = base_state.store, base_state.grid_size
+        self._score, roots, nkids = score_edit(base_state, kind, dp, arg, tree_dist)
+        self.tree_roots = np.asarray(roots)
+        self.outlier_node_name = -1
+        self.log_pdf = 0.0
+        if kind == OUTLIER:
+            self.node_last_added_to = -1
+        elif kind == NEW:
+            self.node_last_added_to = base_state.n_nodes
+        else:
+            self.node_last_added_to = arg
+        self.num_children_on_node_that_matters = nkids
+        self._tstate = None
+        self._thawed = None
+
+    @property
+    def log_p(self):
+        return self._score.resolve()[0]
+
+    @property
+    def log_p_one(self):
+        return self._score.resolve()[1]
+
+    def thawed_state(self):
+        if self._tstate is None:
+            self._tstate = self._parent_state.extend(self.kind, self.dp, self.arg)
+        return self._tstate
+
+    @property
+    def vkey(self):
+        st = self.thawed_state()
+        return (st.skey, st.last_added, st.n_nodes + 1)
+
+    @property
+    def labels(self):
+        return self.tree.labels
+
+    @property
+    def tree_nodes(self):
+        return set(self.tree.nodes)
+
+    @property
+    def tree(self):
+        """Replay: thaw(parent) + edit, then its own `from_dict` round trip -- the chain of to_dict/from_dict
+        round trips the reference performs along a particle's genealogy."""
+        if self._thawed is None:
+            from ..tree.tree import Tree
+            from .forest_state import ATTACH, NEW
+
+            if self._parent_holder is None:
+                t = Tree(self._grid_size, self._store)
+            else:
+                t = self._parent_holder.tree
+            if self.kind == ATTACH:
+                t.add_data_point_to_node(self.dp, self.arg)
+            elif self.kind == NEW:
+                t.create_root_node(children=self.arg, data=[self.dp])
+            else:
+                t.add_data_point_to_outliers(self.dp)
+            t.outliers  # noqa: B018 -- key-creation side effect of scoring a tree (see distributions.prepare)
+            self._thawed = t.thawed_copy()
         return self._thawed.copy()
 
 
