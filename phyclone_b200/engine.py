@@ -62,6 +62,7 @@ class DeviceArena:
         self.alloc = TileAllocator(self.capacity)
         self.prior = -float(np.log(G))
         self._staging = {}
+        self._rows = self._sums = self._sums_host = None
         self.staged_bytes = 0  # host->device bytes of job tables / id lists so far
         self.job_timing = None  # set to a list to record (start_event, end_event, n_jobs, conv_pairs) per launch
 
@@ -154,6 +155,49 @@ class DeviceArena:
         if timing is not None:
             e1.record(torch.cuda.current_stream(self.device))
             timing.append((e0, e1, n, int(tab[:, 1].sum()) - n))
+
+    def run_plan(self, packed, plan, n_slots):
+        """Execute one flush: `packed` (int32) holds every id list / job table of the batch and is sent to the
+        device in ONE pinned copy; `plan` is a list of launches over it:
+            ("add", offset, n, sign)          ids at offset: [a | b | out], n each
+            ("jobs", offset, n, n_kids, cp)   table at offset (n*8 ints) followed by n_kids child ids
+        Returns a host float64 array [2, n_slots] with the summed score rows (synchronises), or None."""
+        lib, arena_ref, prior = self.lib, C.byref(self.c), self.prior
+        stream_obj = torch.cuda.current_stream(self.device)
+        stream = C.c_void_p(stream_obj.cuda_stream)
+        base = self._to_dev_i32(packed, "plan").data_ptr()
+        pl = pt = None
+        if n_slots:
+            if self._rows is None or self._rows.shape[1] < n_slots:
+                cap = max(4096, int(n_slots * 1.5))
+                self._rows = torch.empty((2, cap, self.S), dtype=torch.float64, device=self.device)
+                self._sums = torch.empty((2, cap), dtype=torch.float64, device=self.device)
+                self._sums_host = torch.empty((2, cap), dtype=torch.float64, pin_memory=True)
+            pl, pt = self._rows[0].data_ptr(), self._rows[1].data_ptr()
+        timing = self.job_timing
+        for rec in plan:
+            if rec[0] == "add":
+                _, off, n, sign = rec
+                p0 = base + 4 * off
+                _lib.check(lib.pcb_tile_add_dev(arena_ref, p0, p0 + 4 * n, p0 + 8 * n, n, sign, 0.0, stream))
+            else:
+                _, off, n, n_kids, conv_pairs = rec
+                p0 = base + 4 * off
+                if timing is not None:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(stream_obj)
+                _lib.check(lib.pcb_node_jobs_dev(arena_ref, p0, p0 + 4 * n * JOB_INTS, n, prior, pl, pt, stream))
+                if timing is not None:
+                    e1.record(stream_obj)
+                    timing.append((e0, e1, n, conv_pairs))
+        if not n_slots:
+            return None
+        # rows of the two score kinds are [cap, S] blocks: reduce each over S, copy both to pinned memory
+        _lib.check(lib.pcb_reduce_rows_dev(pl, n_slots, self.S, self._sums[0].data_ptr(), stream))
+        _lib.check(lib.pcb_reduce_rows_dev(pt, n_slots, self.S, self._sums[1].data_ptr(), stream))
+        self._sums_host[:, :n_slots].copy_(self._sums[:, :n_slots], non_blocking=True)
+        stream_obj.synchronize()
+        return self._sums_host.numpy()[:, :n_slots]
 
     def reduce_rows(self, rows):
         """rows: contiguous [2, n_slots, S] -> [2, n_slots] (sum over samples in order), one launch."""

@@ -162,13 +162,24 @@ class StateScore(object):
         return v
 
 
+_LOG = {}
+
+
+def _log(n):
+    """np.log of a small integer, memoised (NumPy's scalar log costs ~1 us a call)."""
+    v = _LOG.get(n)
+    if v is None:
+        v = _LOG[n] = float(np.log(n))
+    return v
+
+
 def _priors(prior, n, crp, mult, sizes, oprior, omarg):
     """tree/distributions.py:39-133 from running statistics."""
     base = n * prior.log_alpha + crp
-    log_p = base - (n - 1) * np.log(n + 1) - mult
+    log_p = base - (n - 1) * _log(n + 1) - mult
     ways = 0
     for z in sizes:
-        ways += (z - 1) * np.log(z)
+        ways += (z - 1) * _log(z)
     log_p_one = base + (-ways + prior._compute_r_term(len(sizes))) - mult
     extra = oprior + omarg
     return log_p + extra, log_p_one + extra

@@ -184,7 +184,9 @@ class SemiAdaptedProposalDistribution(ProposalDistribution):
         node = tree_holder.node_last_added_to  # == tree_holder.labels[data_point.idx] (semi_adapted.py:44-45)
         # "node in parent.tree_nodes": SMC only ever adds to a ROOT of the parent, or to a brand-new node whose name
         # (= number of nodes) no parent node has
-        if node == tree_holder.outlier_node_name or node in self.parent_particle.tree_roots:
+        kind = getattr(tree_holder, "kind", None)
+        if (kind is not None and kind != NEW) or (kind is None and (
+                node == tree_holder.outlier_node_name or node in self.parent_particle.tree_roots)):
             return self.log_half + self._log_q[self.candidate_index(tree_holder)]
         old_num_roots = len(self.parent_particle.tree_roots)
         num_children = tree_holder.num_children_on_node_that_matters

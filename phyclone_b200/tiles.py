@@ -18,6 +18,8 @@ the key keeps the child ORDER, so the floored fold is always evaluated in the or
 (SURVEY.md App. A.9).
 """
 
+import time
+
 import numpy as np
 import torch
 
@@ -47,7 +49,7 @@ class TileStore:
         al.freeze()
         self.upload_values(values)
         self.stats = {"flushes": 0, "adds": 0, "node_jobs": 0, "scores": 0, "launches": 0, "memo_hits": 0,
-                      "d2h_bytes": 0, "conv_pairs": 0}
+                      "d2h_bytes": 0, "conv_pairs": 0, "flush_s": 0.0, "sync_s": 0.0}
         self.reset()
 
     def upload_values(self, values):
@@ -146,72 +148,59 @@ class TileStore:
     def flush(self):
         if not (self._pend_adds or self._pend_jobs):
             return
-        ar = self.arena
         st = self.stats
+        t_begin = time.perf_counter()
         st["flushes"] += 1
-        n_slots = len(self._pend_scores)
-        max_level = 0
+        scores = self._pend_scores
+        n_slots = len(scores)
+        # group by dependency level; within a level the tile adds go first (jobs of the level may not depend on
+        # them, ops of one level never depend on each other)
+        levels = {}
         for rec in self._pend_adds:
-            if rec[0] > max_level:
-                max_level = rec[0]
+            levels.setdefault(rec[0], ([], [], []))[0 if rec[4] > 0 else 1].append(rec)
         for rec in self._pend_jobs:
-            if rec[0] > max_level:
-                max_level = rec[0]
-        adds_by = [[] for _ in range(max_level + 1)]
-        jobs_by = [[] for _ in range(max_level + 1)]
-        for rec in self._pend_adds:
-            adds_by[rec[0]].append(rec)
-        for rec in self._pend_jobs:
-            jobs_by[rec[0]].append(rec)
-        rows = None
-        if n_slots:
-            rows = torch.empty((2, n_slots, self.S), dtype=torch.float64, device=self.device)
-        for lv in range(1, max_level + 1):
-            adds = adds_by[lv]
-            if adds:
-                pos = [r for r in adds if r[4] > 0]
-                neg = [r for r in adds if r[4] < 0]
-                if pos:
-                    ar.tile_add([r[1] for r in pos], [r[2] for r in pos], [r[3] for r in pos], 0.0)
-                    st["launches"] += 1
-                if neg:
-                    ar.tile_sub([r[1] for r in neg], [r[2] for r in neg], [r[3] for r in neg])
-                    st["launches"] += 1
-                st["adds"] += len(adds)
-            jobs = jobs_by[lv]
+            levels.setdefault(rec[0], ([], [], []))[2].append(rec)
+        packed = []
+        plan = []
+        ext = packed.extend
+        for lv in sorted(levels):
+            pos, neg, jobs = levels[lv]
+            for adds, sign in ((pos, 1.0), (neg, -1.0)):
+                if adds:
+                    plan.append(("add", len(packed), len(adds), sign))
+                    ext([r[1] for r in adds])
+                    ext([r[2] for r in adds])
+                    ext([r[3] for r in adds])
+                    st["adds"] += len(adds)
             if jobs:
-                n = len(jobs)
-                tab = np.zeros((n, 8), dtype=np.int32)
-                kids = []
-                off = 0
-                for i, (_, base, ks, out, slot) in enumerate(jobs):
+                off = len(packed)
+                koff = 0
+                kids_all = []
+                kext = kids_all.extend
+                for _, base, ks, out, slot in jobs:
                     c = len(ks)
-                    tab[i, 0] = off
-                    tab[i, 1] = c
-                    tab[i, 2] = base
-                    tab[i, 3] = out
-                    tab[i, 4] = JOB_SCAN | (JOB_ADD_PRIOR if slot >= 0 else 0)
-                    tab[i, 5] = slot
-                    kids.extend(ks)
-                    off += c
-                    st["conv_pairs"] += c - 1
-                ar.launch_jobs(tab, np.asarray(kids, dtype=np.int32), rows)
-                st["launches"] += 1
+                    ext((koff, c, base, out, (JOB_SCAN | JOB_ADD_PRIOR) if slot >= 0 else JOB_SCAN, slot, 0, 0))
+                    kext(ks)
+                    koff += c
+                ext(kids_all)
+                n = len(jobs)
+                plan.append(("jobs", off, n, koff, koff - n))
                 st["node_jobs"] += n
+                st["conv_pairs"] += koff - n
+        st["launches"] += len(plan) + (2 if n_slots else 0)
+        host = self.arena.run_plan(np.asarray(packed, dtype=np.int32), plan, n_slots)
         if n_slots:
-            sums = ar.reduce_rows(rows)  # [2, n_slots] on device
-            st["launches"] += 1
-            host = sums.cpu().numpy()  # the one synchronising D2H copy of the step
-            st["d2h_bytes"] += host.nbytes
+            st["d2h_bytes"] += 16 * n_slots
             st["scores"] += n_slots
             lse, last = host[0].tolist(), host[1].tolist()
             memo = self._score_memo
-            for slot, ks in enumerate(self._pend_scores):
+            for slot, ks in enumerate(scores):
                 memo[ks][1] = (lse[slot], last[slot])
         self._pend_adds = []
         self._pend_jobs = []
         self._pend_scores = []
         self._level = {}
+        st["flush_s"] += time.perf_counter() - t_begin
 
     def fetch(self, ids):
         """Dense [n,S,G] host copy of tiles (debug / tests / trace export)."""

@@ -10,6 +10,9 @@ import numpy as np
 from ..utils.math import cached_log_factorial
 
 
+_R_CACHE = {}
+
+
 class FSCRPDistribution(object):
     """FSCRP prior distribution on trees."""
 
@@ -43,7 +46,15 @@ class FSCRPDistribution(object):
         self._c_const = np.log(c_const)
 
     def _compute_r_term(self, num_roots):
-        """distributions.py:103-133"""
+        """distributions.py:103-133 (a function of the root count only: memoised)"""
+        cache = self.__dict__.setdefault("_r_cache", {}) if hasattr(self, "__dict__") else _R_CACHE
+        key = (num_roots, self._c_const)
+        val = cache.get(key)
+        if val is None:
+            val = cache[key] = self._r_term_uncached(num_roots)
+        return val
+
+    def _r_term_uncached(self, num_roots):
         log_const = self._c_const
         if num_roots == 0:
             z_term, num_roots = 0.0, 1
