@@ -171,8 +171,8 @@ class DeviceArena:
             if self._rows is None or self._rows.shape[1] < n_slots:
                 cap = max(4096, int(n_slots * 1.5))
                 self._rows = torch.empty((2, cap, self.S), dtype=torch.float64, device=self.device)
-                self._sums = torch.empty((2, cap), dtype=torch.float64, device=self.device)
-                self._sums_host = torch.empty((2, cap), dtype=torch.float64, pin_memory=True)
+                self._sums = torch.empty(2 * cap, dtype=torch.float64, device=self.device)
+                self._sums_host = torch.empty(2 * cap, dtype=torch.float64, pin_memory=True)
             pl, pt = self._rows[0].data_ptr(), self._rows[1].data_ptr()
         timing = self.job_timing
         for rec in plan:
@@ -193,11 +193,13 @@ class DeviceArena:
         if not n_slots:
             return None
         # rows of the two score kinds are [cap, S] blocks: reduce each over S, copy both to pinned memory
-        _lib.check(lib.pcb_reduce_rows_dev(pl, n_slots, self.S, self._sums[0].data_ptr(), stream))
-        _lib.check(lib.pcb_reduce_rows_dev(pt, n_slots, self.S, self._sums[1].data_ptr(), stream))
-        self._sums_host[:, :n_slots].copy_(self._sums[:, :n_slots], non_blocking=True)
+        # the two score kinds are reduced into one contiguous [2*n_slots] run: a single contiguous D2H copy
+        sp = self._sums.data_ptr()
+        _lib.check(lib.pcb_reduce_rows_dev(pl, n_slots, self.S, sp, stream))
+        _lib.check(lib.pcb_reduce_rows_dev(pt, n_slots, self.S, sp + 8 * n_slots, stream))
+        self._sums_host[: 2 * n_slots].copy_(self._sums[: 2 * n_slots], non_blocking=True)
         stream_obj.synchronize()
-        return self._sums_host.numpy()[:, :n_slots]
+        return self._sums_host.numpy()[: 2 * n_slots].reshape(2, n_slots)
 
     def reduce_rows(self, rows):
         """rows: contiguous [2, n_slots, S] -> [2, n_slots] (sum over samples in order), one launch."""
