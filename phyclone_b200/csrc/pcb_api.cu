@@ -38,7 +38,17 @@ int fail(int code, const std::string& msg) {
 // ---- layout -------------------------------------------------------------------
 const int kStrips[] = {5, 7, 9, 13, 17};
 
-size_t jobs_smem_bytes(int RB, int pitch) { return pcb::kSmemHead + 3ull * RB * pitch * 8 + pcb::kSmemTail; }
+int jobs_double_b() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PCB_NBUF");
+    v = (e && atoi(e) == 3) ? 1 : 0;  // default: one operand buffer (12 instead of 8 warps per SM: +12% measured)
+  }
+  return v;
+}
+size_t jobs_smem_bytes(int RB, int pitch) {
+  return pcb::kSmemHead + (jobs_double_b() ? 3ull : 2ull) * RB * pitch * 8 + pcb::kSmemTail;
+}
 
 int fill_layout(int S, int G, int L, int P, pcb_layout* out) {
   if (S < 1 || G < 1 || G > 1088) return fail(PCB_ERR_ARG, "layout: need S >= 1 and 1 <= G <= 1088");
@@ -324,6 +334,7 @@ int pcb_node_jobs_dev(const pcb_arena* a, const int32_t* jobs_dev, const int32_t
   kp.lead = l.lead;
   kp.RB = l.rows_per_cta;
   kp.row_blocks = (l.S + l.rows_per_cta - 1) / l.rows_per_cta;
+  kp.double_b = jobs_double_b();
   const int threads = 32;
   const size_t smem = jobs_smem_bytes(l.rows_per_cta, l.pitch);
   cudaStream_t st = (cudaStream_t)stream;

@@ -27,6 +27,7 @@ struct JobKernelParams {
   long long tile_elems;
   double prior;
   int S, G, Q, U, P, pitch, lead, RB, row_blocks;
+  int double_b;  // 1: two operand buffers (next child prefetched during the fold step), 0: one
 };
 
 // ---------------------------------------------------------------------------------
@@ -161,10 +162,11 @@ __device__ __forceinline__ void row_prefix_lse(const double* x, double* out, int
 // node_jobs_kernel: one single-warp CTA per (job, row block of RB = 32/P rows).  Rows of a
 // tile are independent through the whole fold, so nothing ever needs a CTA-wide barrier:
 // the P lanes of a row group live in one warp and synchronise with __syncwarp / shuffles.
-// Shared memory: [256 B: mbarriers + underrun slack][A: RB*pitch][B0][B1][256 B slack].
+// Shared memory: [256 B: mbarriers + underrun slack][A: RB*pitch][B0]([B1])[256 B slack].
 //   A   running product of the fold (max-normalised, linear domain), updated in place
-//   B0/1 operand tiles, double-buffered: the TMA bulk copy of child j+1 is in flight while
-//        child j is being folded in.
+//   B0  operand tile: the TMA bulk copy of child j+1 is issued as soon as the last lane has read
+//       child j (default), or double-buffered with B1 (PCB_NBUF=3; costs occupancy: 8 vs 12
+//       warps per SM at (8,101) and measured 12 % slower on saturated batches).
 // See phyclone_b200.h for the job record.
 // ---------------------------------------------------------------------------------
 constexpr int kSmemHead = 256;
@@ -228,11 +230,12 @@ __global__ void __launch_bounds__(32) node_jobs_kernel(const JobKernelParams p) 
   const bool two = k2 != k1;
 
   // ---- left fold over the children (tree/utils.py:33-47) --------------------------
+  const bool db = p.double_b;
   for (int j = 1; j < C; ++j) {
-    double* Bcur = (j & 1) ? bufB0 : bufB1;
-    uint64_t* bbar = (j & 1) ? &bars[1] : &bars[2];
-    mbar_wait(bbar, ((j - 1) >> 1) & 1);
-    if (j + 1 < C && tid == 0) {  // prefetch the next operand into the buffer step j-1 released
+    double* Bcur = (!db || (j & 1)) ? bufB0 : bufB1;
+    uint64_t* bbar = (!db || (j & 1)) ? &bars[1] : &bars[2];
+    mbar_wait(bbar, db ? (((j - 1) >> 1) & 1) : ((j - 1) & 1));
+    if (db && j + 1 < C && tid == 0) {  // prefetch the next operand into the buffer step j-1 released
       double* Bnext = (j & 1) ? bufB1 : bufB0;
       uint64_t* nbar = (j & 1) ? &bars[2] : &bars[1];
       const int cn = p.children[coff + j + 1];
@@ -242,6 +245,15 @@ __global__ void __launch_bounds__(32) node_jobs_kernel(const JobKernelParams p) 
     const double* b_row = Bcur + lrow * pitch + lead;
     double y1[L], y2[L];
     conv_unit<L>(a_row, b_row, u, Q, lane_ok, y1, y2);
+    if (!db && j + 1 < C) {  // single operand buffer: refill it as soon as every lane is done with it
+      __syncwarp();
+      if (tid == 0) {
+        fence_proxy_async();
+        const int cn = p.children[coff + j + 1];
+        mbar_expect_tx(&bars[1], bytes);
+        tma_load_1d(bufB0, p.lin + (size_t)cn * p.tile_elems + (size_t)r0 * pitch, bytes, &bars[1]);
+      }
+    }
     // floor (tree/utils.py:77) and row maximum, all in registers.  Outputs past G (only the last
     // strip is partial) are forced to 0 so that they can be stored unconditionally: they land
     // on pad columns, which must stay zero anyway.
