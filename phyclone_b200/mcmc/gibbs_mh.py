@@ -58,24 +58,32 @@ class DataPointSampler(object):
         v = st.value_id[data_point.idx]
         succ = g.successor_indices
         pred = g.predecessor_indices
-        # ---- removal: new log_p of old_node, refreshed log_r along old_node..root
-        oi = idx[old_node]
-        lp_old = st.sub(lp[oi], v)
-        over = {}
-        i, first = oi, True
-        while i != root:
-            kids = tuple(over.get(c, lr[c]) for c in succ(i))
-            base = lp_old if first else lp[i]
-            over[i] = st.node(base, kids) if kids else base
-            first = False
-            i = pred(i)[0]
         crp, mult, size, oprior, omarg = tree.prior_terms()
         n_nodes = tree.get_number_of_nodes()
         roots = succ(root)
         sizes = [size[i] for i in roots]
-        n_old = len(tree._data[old_node])
-        crp_removed = crp - (lf(n_old - 1) - lf(n_old - 2))
         prior = self.tree_dist.prior
+        over = {}
+        if old_node == tree._OUTLIER_NODE_NAME:
+            # the point is currently an outlier: removing it touches no tile (tree/tree.py:446-454)
+            oi, lp_old = -1, None
+            crp_removed = crp
+            if data_point.outlier_prob != 0:
+                oprior = oprior - data_point.outlier_prob + data_point.outlier_prob_not
+            omarg = omarg - data_point.outlier_marginal_prob
+        else:
+            # ---- removal: new log_p of old_node, refreshed log_r along old_node..root
+            oi = idx[old_node]
+            lp_old = st.sub(lp[oi], v)
+            i, first = oi, True
+            while i != root:
+                kids = tuple(over.get(c, lr[c]) for c in succ(i))
+                base = lp_old if first else lp[i]
+                over[i] = st.node(base, kids) if kids else base
+                first = False
+                i = pred(i)[0]
+            n_old = len(tree._data[old_node])
+            crp_removed = crp - (lf(n_old - 1) - lf(n_old - 2))
         out = []
         for new_node in tree.nodes:
             ni = idx[new_node]

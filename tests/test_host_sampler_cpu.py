@@ -36,3 +36,35 @@ def test_host_sampler_reproduces_reference_trace(name):
     compare_trace(res["trace"], g, 1e-9, name)
     # with the NumPy tile store the arithmetic is the oracle's, so even the Generator state must agree
     assert rng.random() == float(g["rng_after"])
+
+
+def test_host_sampler_matches_oracle_with_many_outliers():
+    """Outlier-heavy run (outlier_prob 0.3): exercises outlier proposals, outlier <-> node Gibbs moves and the
+    outlier bookkeeping of the root-level forest states against the pinned oracle sampler.  The oracle's
+    decisions are replayed (tests/tape.py): the product's prior terms are running sums, not bit-identical to the
+    oracle's, and with many tied particles one ulp is enough to flip a free-running multinomial draw."""
+    from oracle import sampler as osm
+    from tests.chain_utils import signature
+    from tests.tape import RecordingRNG, ReplayRNG
+
+    g = load_chain("syn12")
+    vals = g["values"][:9]
+    lo, lon = float(np.log(0.3) * 4), float(np.log1p(-0.3) * 4)
+    odata = [osm.Datum(i, vals[i], outlier_prob=lo, outlier_prob_not=lon) for i in range(len(vals))]
+    rec = RecordingRNG(np.random.default_rng(5))
+    ref = osm.run_chain(odata, rec, 10, burnin=2, num_particles=12, outlier_prob=0.3)
+    assert any(len(e["outliers"]) > 0 for e in ref["trace"]), "the case must actually produce outliers"
+    assert len({tuple(sorted(e["outliers"])) for e in ref["trace"]}) > 1, "and move points in and out of them"
+    data = [DataPoint(i, vals[i], outlier_prob=lo, outlier_prob_not=lon,
+                      outlier_marginal_prob=onum.outlier_marginal(vals[i])) for i in range(len(vals))]
+    rep = ReplayRNG(rec.tape)
+    res = run_phyclone_chain(2, True, 1.0, data, float("inf"), 10, 12, 1, 1, 0.3, 10**9, "semi-adapted", 0.5, rep,
+                             ["s"], 1, 0, 0.0, store=FakeTileStore(vals))
+    assert rep.done()
+    n = len(vals)
+    for i, (a, b) in enumerate(zip(res["trace"], ref["trace"])):
+        own_a, par_a = signature(a["tree"], n)
+        own_b, par_b = signature(b["tree"], n)
+        assert np.array_equal(own_a, own_b) and np.array_equal(par_a, par_b), "topology differs at entry %d" % i
+        assert abs(a["log_p_one"] - b["log_p_one"]) <= 1e-9 * abs(b["log_p_one"])
+        assert abs(a["alpha"] - b["alpha"]) <= 1e-9 * abs(b["alpha"])
