@@ -224,3 +224,31 @@ def score_edit(base, kind, dp, arg, tree_dist):
     handle = st.score((lr,) + tuple(base.lr[j] for j in keep))
     roots = (base.n_nodes,) + tuple(base.roots[j] for j in keep)
     return StateScore(lp, lp1, handle, st), roots, k
+
+
+def score_attach_all(base, dp, nodes, tree_dist):
+    """`score_edit(base, ATTACH, dp, node)` for every node of `nodes` with the shared prior terms computed once;
+    returns [(StateScore, number of children of the node)]."""
+    st = base.store
+    prior = tree_dist.prior
+    oprior = base.oprior
+    if dp.outlier_prob != 0:
+        oprior = oprior + dp.outlier_prob_not
+    n = base.n_nodes
+    head = n * prior.log_alpha
+    ways = 0
+    for z in base.size:
+        ways += (z - 1) * _log(z)
+    tail_p = -(n - 1) * _log(n + 1) - base.mult + (oprior + base.omarg)
+    tail_one = (-ways + prior._compute_r_term(len(base.size))) - base.mult + (oprior + base.omarg)
+    v = st.value_id[dp.idx]
+    lr_all = base.lr
+    out = []
+    for node in nodes:
+        j = base.index_of(node)
+        m = base.ndata[j]
+        crp = head + (base.crp + (lf(m) - lf(m - 1) if m >= 1 else 0.0))
+        lr = st.add(lr_all[j], v)
+        handle = st.score(lr_all[:j] + (lr,) + lr_all[j + 1:])
+        out.append((StateScore(crp + tail_p, crp + tail_one, handle, st), len(base.kids[j])))
+    return out

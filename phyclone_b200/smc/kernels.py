@@ -13,7 +13,7 @@ import numpy as np
 
 from ..tree.tree import Tree
 from ..utils.math import cached_log_binomial_coefficient, discrete_rvs, log_binomial_coefficient, log_normalize
-from .forest_state import ATTACH, NEW, OUTLIER, ForestState
+from .forest_state import ATTACH, NEW, OUTLIER, ForestState, score_attach_all
 from .swarm import Particle, StateHolder, TreeHolder
 
 
@@ -243,9 +243,12 @@ class StateSemiAdaptedProposalDistribution(object):
         self._pholder = ph
         td = self.tree_dist
         trees = []
-        if parent_particle is not None:
-            for node in parent_particle.tree_roots:
-                trees.append(StateHolder(ph, parent_state, base_state, ATTACH, data_point, node, td))
+        if parent_particle is not None and len(parent_particle.tree_roots):
+            nodes = parent_particle.tree_roots
+            shared_roots = np.asarray(base_state.roots)  # attaching does not change the as-built root order
+            for node, (score, nkids) in zip(nodes, score_attach_all(base_state, data_point, nodes.tolist(), td)):
+                trees.append(StateHolder(ph, parent_state, base_state, ATTACH, data_point, node, td,
+                                         prescored=(score, nkids, shared_roots)))
         if kernel.outlier_proposal_prob > 0:
             trees.append(StateHolder(ph, parent_state, base_state, OUTLIER, data_point, None, td))
         self.parent_is_empty_tree = parent_particle is None or len(parent_particle.tree_roots) == 0

@@ -84,9 +84,9 @@ class StateHolder(object):
 
     __slots__ = ("uid", "kind", "dp", "arg", "_parent_holder", "_parent_state", "_score", "tree_roots",
                  "node_last_added_to", "num_children_on_node_that_matters", "outlier_node_name", "log_pdf", "_tstate",
-                 "_thawed", "_store", "_grid_size")
+                 "_thawed", "_store", "_grid_size", "_vkey")
 
-    def __init__(self, parent_holder, parent_state, base_state, kind, dp, arg, tree_dist):
+    def __init__(self, parent_holder, parent_state, base_state, kind, dp, arg, tree_dist, prescored=None):
         from .forest_state import NEW, OUTLIER, score_edit
 
         self.uid = next(_uid)
@@ -94,8 +94,12 @@ class StateHolder(object):
         self._parent_holder = parent_holder
         self._parent_state = parent_state
         self._store, self._grid_size = base_state.store, base_state.grid_size
-        self._score, roots, nkids = score_edit(base_state, kind, dp, arg, tree_dist)
-        self.tree_roots = np.asarray(roots)
+        if prescored is None:
+            self._score, roots, nkids = score_edit(base_state, kind, dp, arg, tree_dist)
+            self.tree_roots = np.asarray(roots)
+        else:  # (StateScore, children of the node, shared as-built roots array) from score_attach_all
+            self._score, nkids, self.tree_roots = prescored
+        self._vkey = None
         self.outlier_node_name = -1
         self.log_pdf = 0.0
         if kind == OUTLIER:
@@ -123,8 +127,11 @@ class StateHolder(object):
 
     @property
     def vkey(self):
-        st = self.thawed_state()
-        return (st.skey, st.last_added, st.n_nodes + 1)
+        k = self._vkey
+        if k is None:
+            st = self.thawed_state()
+            k = self._vkey = (st.skey, st.last_added, st.n_nodes + 1)
+        return k
 
     @property
     def labels(self):
