@@ -19,6 +19,30 @@ NVCC_FLAGS = [
 ]
 
 
+HOST_SRC = os.path.join(HERE, "csrc", "pcb_host.cpp")
+HOST_OUT = os.path.join(OUT_DIR, "libpcb_host.so")
+
+
+def build_host(force=False):
+    """Host-side sampling draws (csrc/pcb_host.cpp): plain g++, linked against numpy's own libnpyrandom.a."""
+    if not force and os.path.exists(HOST_OUT) and os.path.getmtime(HOST_OUT) >= os.path.getmtime(HOST_SRC):
+        return HOST_OUT
+    import sysconfig
+
+    import numpy
+
+    np_dir = os.path.dirname(numpy.__file__)
+    cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-fPIC", "-shared",
+           "-I" + os.path.join(np_dir, "_core", "include"), "-I" + sysconfig.get_paths()["include"],
+           "-o", HOST_OUT, HOST_SRC, os.path.join(np_dir, "random", "lib", "libnpyrandom.a"), "-lm"]
+    os.makedirs(OUT_DIR, exist_ok=True)
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("g++ failed building %s" % HOST_OUT)
+    return HOST_OUT
+
+
 def needs_build():
     if not os.path.exists(OUT):
         return True
@@ -27,6 +51,7 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
+    build_host(force)
     if not force and not needs_build():
         return OUT
     os.makedirs(OUT_DIR, exist_ok=True)

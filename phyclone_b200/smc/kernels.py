@@ -58,6 +58,10 @@ class Kernel(object):
     def rng(self):
         return self._rng
 
+    def fast_draw_address(self):
+        """Address of numpy's bitgen_t if this kernel's draws may be done in C (see samplers._propose_all)."""
+        return None
+
     def clear_proposal_dist_caches(self):
         """utils/dev.py:12-17"""
         self._dist_cache.clear()
@@ -231,9 +235,13 @@ class StateSemiAdaptedProposalDistribution(object):
     """Semi-adapted proposal (smc/kernels/semi_adapted.py:11-183) evaluated on root-level forest states: same
     candidates, order, probabilities and RNG calls as the tree-copying version above, O(#roots) work each."""
 
+    fast_draws = True
+
     def __init__(self, data_point, kernel, parent_particle, parent_state, base_state):
         self.data_point = data_point
         self.kernel = kernel
+        self.roots_array = (np.asarray(parent_particle.tree_roots, dtype=np.int64) if parent_particle is not None
+                            else np.zeros(0, dtype=np.int64))
         self.tree_dist = kernel.tree_dist
         self.parent_particle = parent_particle
         self._rng = kernel.rng
@@ -274,9 +282,12 @@ class StateSemiAdaptedProposalDistribution(object):
             children = []
         else:
             children = self._rng.choice(self.parent_particle.tree_roots, num_children, replace=False)
-        children = frozenset(children)
+        return self.new_node_holder(frozenset(children))
+
+    def new_node_holder(self, children):
+        """get_cached_new_tree (semi_adapted.py:186-194): the new node always goes onto the parent re-read through
+        from_dict; one holder per (parent value, data point, child set)."""
         key = (self._pholder.vkey, self.data_point.idx, children)
-        # the new node always goes onto the parent re-read through from_dict (semi_adapted.py:186-194)
         return self.kernel._new_tree_cache.get(
             key, lambda: StateHolder(self._pholder, self._pstate, self._pstate, NEW, self.data_point, children,
                                      self.tree_dist))
@@ -286,6 +297,13 @@ class SemiAdaptedKernel(Kernel):
     log_half = np.log(0.5)
 
     use_states = True  # evaluate candidates from root-level ForestStates instead of copied trees
+
+    def fast_draw_address(self):
+        if not self.use_states:
+            return None
+        from .. import _hostlib
+
+        return _hostlib.bitgen_address(self._rng)
 
     def _make_proposal(self, data_point, parent_particle, parent_tree):
         if self.use_states:

@@ -7,8 +7,11 @@ Same control flow and RNG call order as the reference; per step the work is arra
 so an SMC step costs two synchronising device round trips whatever the number of particles.
 """
 
+import ctypes as C
+
 import numpy as np
 
+from .. import _hostlib
 from ..tree.tree import Tree
 from ..utils.math import discrete_rvs
 from .swarm import ParticleSwarm, TreeHolder
@@ -51,6 +54,62 @@ class AbstractSMCSampler(object):
     def _propose_particle(self, parent_particle):
         return self.kernel.propose_particle(self.data_points[self.iteration], parent_particle)
 
+    def _propose_all(self, parents):
+        """`[propose_particle(dp, p) for p in parents]` (smc/kernels/base.py:59-67).  When the kernel's proposals
+        are the state-based semi-adapted ones and the RNG is a real numpy Generator, all the draws of the step
+        (coin, multinomial, integers, choice -- in swarm order, from the same bit generator) are made by ONE call
+        into csrc/pcb_host.cpp instead of ~4 Python-level Generator calls per particle."""
+        kernel = self.kernel
+        data_point = self.data_points[self.iteration]
+        addr = kernel.fast_draw_address()
+        n = len(parents)
+        if addr is None or n == 0:
+            self._prepare_proposals(parents)
+            return [self._propose_particle(p) for p in parents]
+        dists, index, dist_of = [], {}, np.empty(n, dtype=np.int32)
+        for i, p in enumerate(parents):
+            key = None if p is None else p.holder.vkey
+            j = index.get(key)
+            if j is None:
+                d = kernel.get_proposal_distribution(data_point, p)
+                if not getattr(d, "fast_draws", False):
+                    return [self._propose_particle(q) for q in parents]
+                j = index[key] = len(dists)
+                dists.append(d)
+            dist_of[i] = j
+        for d in dists:
+            if d._q_dist is None:
+                d._finish()  # the first one resolves the scores of every proposal of the step: one flush
+        q_off = np.zeros(len(dists) + 1, dtype=np.int64)
+        r_off = np.zeros(len(dists) + 1, dtype=np.int64)
+        for j, d in enumerate(dists):
+            q_off[j + 1] = q_off[j] + len(d._q_dist)
+            r_off[j + 1] = r_off[j] + len(d.roots_array)
+        q_flat = np.concatenate([d._q_dist for d in dists])
+        r_flat = np.concatenate([d.roots_array for d in dists] + [np.zeros(0, dtype=np.int64)]).astype(np.int64, copy=False)
+        empty = np.array([1 if d.parent_is_empty_tree else 0 for d in dists], dtype=np.uint8)
+        kind = np.empty(n, dtype=np.int32)
+        pick = np.empty(n, dtype=np.int64)
+        kids = np.empty(max(1, int((r_off[dist_of + 1] - r_off[dist_of]).sum())), dtype=np.int64)
+        koff = np.empty(n + 1, dtype=np.int64)
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        rc = _hostlib.load().pcb_smc_draws(C.c_void_p(addr), n, ptr(dist_of), ptr(q_flat), ptr(q_off), ptr(r_flat),
+                                           ptr(r_off), ptr(empty), ptr(kind), ptr(pick), ptr(kids), ptr(koff))
+        if rc != 0:
+            raise RuntimeError("pcb_smc_draws failed (rc=%d)" % rc)
+        out = []
+        kind_l, pick_l, koff_l, dist_l = kind.tolist(), pick.tolist(), koff.tolist(), dist_of.tolist()
+        create = kernel.create_particle
+        for i, p in enumerate(parents):
+            d = dists[dist_l[i]]
+            if kind_l[i] == 0:
+                holder = d._curr_trees[pick_l[i]]
+            else:
+                holder = d.new_node_holder(frozenset(kids[koff_l[i]:koff_l[i + 1]]))
+            out.append(create(d.log_p(holder), p, holder))
+        kernel.num_extensions += n
+        return out
+
     def _get_log_w(self, particle):
         """base.py:52-58"""
         if self.iteration < self.num_iterations - 1:
@@ -78,9 +137,8 @@ class SMCSampler(AbstractSMCSampler):
             self.swarm = new_swarm
 
     def _update_swarm(self):
-        self._prepare_proposals(self.swarm.particles)
         log_W = self.swarm.log_weights
-        particles = [self._propose_particle(p) for p in self.swarm.particles]
+        particles = self._propose_all(self.swarm.particles)
         new_swarm = ParticleSwarm()
         for parent_log_W, particle in zip(log_W, particles):
             new_swarm.add_particle(parent_log_W + self._get_log_w(particle), particle)
@@ -134,9 +192,8 @@ class ConditionalSMCSampler(AbstractSMCSampler):
         self.swarm = ParticleSwarm()
         uniform_weight = -np.log(self.num_particles)
         self.swarm.add_particle(uniform_weight, self.constrained_path[1])
-        self._prepare_proposals([None])
-        for _ in range(self.num_particles - 1):
-            self.swarm.add_particle(uniform_weight, self._propose_particle(None))
+        for particle in self._propose_all([None] * (self.num_particles - 1)):
+            self.swarm.add_particle(uniform_weight, particle)
         self.iteration += 1
 
     def _resample_swarm(self):
@@ -151,10 +208,9 @@ class ConditionalSMCSampler(AbstractSMCSampler):
             self.swarm = new_swarm
 
     def _update_swarm(self):
-        self._prepare_proposals(self.swarm.particles[1:])
         log_W = self.swarm.log_weights
         retained = self.constrained_path[self.iteration + 1]
-        particles = [retained] + [self._propose_particle(p) for p in self.swarm.particles[1:]]
+        particles = [retained] + self._propose_all(self.swarm.particles[1:])
         new_swarm = ParticleSwarm()
         for parent_log_W, particle in zip(log_W, particles):
             new_swarm.add_particle(parent_log_W + self._get_log_w(particle), particle)

@@ -1,0 +1,70 @@
+"""Several independent chains on ONE GPU, one host process each (BASELINE.json configs[2] at N=1: "8 chains").
+Chains never talk to each other; the GPU time-slices their small launches.  Prints aggregate PG iterations/s.
+usage: python scripts/multi_chain_bench.py --chains 8 --steps 5 --warmup 3"""
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def worker(rank, n, steps, warmup, barrier, q):
+    import numpy as np
+    import torch
+
+    import bench
+    from phyclone_b200 import ops
+    from phyclone_b200.data.base import make_data_points
+    from phyclone_b200.run import Chain
+
+    c = bench.synthetic_counts()
+    cfg = bench.CFG
+    grids = ops.likelihood_grid(c["ref"], c["alt"], c["tumour_content"], c["cn"], c["mu"], c["log_pi"], c["n_geno"],
+                                cfg["grid"], cfg["density"], cfg["precision"])
+    values = ops.cluster_sum(grids, c["cluster_off"])
+    data = make_data_points(values)
+    rng = np.random.default_rng(1).spawn(max(n, 2))[rank] if n > 1 else np.random.default_rng(1)
+    chain = Chain(data, rng, num_particles=cfg["particles"])
+    chain.burnin_step()
+    for _ in range(warmup):
+        chain.step()
+    torch.cuda.synchronize()
+    barrier.wait()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        chain.step()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    barrier.wait()
+    q.put((rank, t0, t1))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--chains", default="1,2,4,8")
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    args = ap.parse_args()
+    ctx = mp.get_context("spawn")
+    for n in [int(x) for x in args.chains.split(",")]:
+        barrier = ctx.Barrier(n)
+        q = ctx.Queue()
+        procs = [ctx.Process(target=worker, args=(r, n, args.steps, args.warmup, barrier, q)) for r in range(n)]
+        for p in procs:
+            p.start()
+        res = [q.get() for _ in range(n)]
+        for p in procs:
+            p.join()
+        t0 = min(r[1] for r in res)
+        t1 = max(r[2] for r in res)
+        print(json.dumps({"chains_on_one_gpu": n, "steps": args.steps, "aggregate_pg_it_per_s": n * args.steps / (t1 - t0),
+                          "per_chain_it_per_s": args.steps / (t1 - t0), "host_cores": os.cpu_count()}))
+
+
+if __name__ == "__main__":
+    main()
