@@ -66,6 +66,21 @@ class DeviceArena:
         self.staged_bytes = 0  # host->device bytes of job tables / id lists so far
         self.job_timing = None  # set to a list to record (start_event, end_event, n_jobs, conv_pairs) per launch
 
+    def grow(self, new_capacity):
+        """Enlarge the arena in place (tile ids stay valid): new zero-filled tensors, old content copied over."""
+        new_capacity = int(new_capacity)
+        if new_capacity <= self.capacity:
+            return
+        with torch.cuda.device(self.device):
+            for name in ("lg", "lin", "rmax"):
+                old = getattr(self, name)
+                new = torch.zeros((new_capacity,) + tuple(old.shape[1:]), dtype=old.dtype, device=self.device)
+                new[: self.capacity].copy_(old)
+                setattr(self, name, new)
+        self.capacity = new_capacity
+        self.alloc.capacity = new_capacity
+        self.c = _lib.Arena(self.layout, self.lg.data_ptr(), self.lin.data_ptr(), self.rmax.data_ptr(), self.capacity)
+
     # ---------------------------------------------------------------- plumbing
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)

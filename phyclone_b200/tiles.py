@@ -32,9 +32,10 @@ class TileStore:
         values = np.ascontiguousarray(values, dtype=np.float64)
         T, S, G = values.shape
         self.T, self.S, self.G = T, S, G
+        tile_bytes = 2 * S * (G + 48) * 8
         if capacity is None:
-            tile_bytes = 2 * S * (G + 48) * 8
-            capacity = int(min(max(16384, 4096 * 50), max(4096, (8 << 30) // tile_bytes)))
+            capacity = int(min(65536, max(4096, (2 << 30) // tile_bytes)))
+        self.max_capacity = int(max(capacity, (64 << 30) // tile_bytes))  # the arena doubles on demand up to 64 GB
         self.arena = DeviceArena(S, G, capacity + 2 * T + 1, device=device, variant=variant)
         self.device = self.arena.device
         self.prior = self.arena.prior
@@ -74,6 +75,15 @@ class TileStore:
         self._pend_jobs = []  # (level, base, kids, out, slot)
         self._pend_scores = []  # kids tuples in slot order
 
+    def _alloc(self):
+        al = self.arena.alloc
+        if al.top >= al.capacity:
+            if al.capacity >= self.max_capacity:
+                raise MemoryError("tile arena exhausted at %d tiles" % al.capacity)
+            self.flush()  # pending ops hold pointers into the current tensors
+            self.arena.grow(min(self.max_capacity, 2 * al.capacity))
+        return al.alloc()
+
     def _lvl(self, ids):
         lv = self._level
         m = 0
@@ -91,7 +101,7 @@ class TileStore:
         if t is not None:
             self.stats["memo_hits"] += 1
             return t
-        t = self.arena.alloc.alloc()
+        t = self._alloc()
         lv = self._lvl(key)
         self._level[t] = lv
         self._pend_adds.append((lv, a, b, t, 1.0))
@@ -105,7 +115,7 @@ class TileStore:
         if t is not None:
             self.stats["memo_hits"] += 1
             return t
-        t = self.arena.alloc.alloc()
+        t = self._alloc()
         lv = self._lvl((a, b))
         self._level[t] = lv
         self._pend_adds.append((lv, a, b, t, -1.0))
@@ -119,7 +129,7 @@ class TileStore:
         if t is not None:
             self.stats["memo_hits"] += 1
             return t
-        t = self.arena.alloc.alloc()
+        t = self._alloc()
         lv = self._lvl(kids + (base,))
         self._level[t] = lv
         self._pend_jobs.append((lv, base, kids, t, -1))

@@ -95,3 +95,20 @@ def test_final_tree_tiles_match_oracle_rebuild():
     olp, olp1 = joint.both(ot)
     assert abs(lp - olp) <= 1e-9 * abs(olp) and abs(lp1 - olp1) <= 1e-9 * abs(olp1)
     print("nodes compared: %d, boundary-band entries: %d" % (len(got), boundary))
+
+
+def test_arena_grows_on_demand():
+    """A deliberately tiny arena must double itself (tile ids stay valid) instead of failing."""
+    from phyclone_b200.run import run_phyclone_chain
+    from phyclone_b200.tiles import TileStore
+
+    g = load_chain("syn12")
+    store = TileStore(g["values"], capacity=64)
+    cap0 = store.arena.capacity
+    res = run_phyclone_chain(1, True, 1.0, _data(g), float("inf"), 3, 16, 1, 1, 0.0, 10**9, "semi-adapted", 0.5,
+                             np.random.default_rng(1), ["s"], 1, 0, 0.0, store=store)
+    assert store.arena.capacity > cap0
+    ref = run_phyclone_chain(1, True, 1.0, _data(g), float("inf"), 3, 16, 1, 1, 0.0, 10**9, "semi-adapted", 0.5,
+                             np.random.default_rng(1), ["s"], 1, 0, 0.0)
+    for a, b in zip(res["trace"], ref["trace"]):
+        assert a["log_p_one"] == b["log_p_one"] and a["alpha"] == b["alpha"]
