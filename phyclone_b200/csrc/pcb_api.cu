@@ -261,8 +261,12 @@ int pcb_make_layout(int32_t S, int32_t G, int32_t variant, pcb_layout* out) {
       const int Q = (G + L - 1) / L;
       if ((Q + 1) / 2 > P) continue;
       if (L == 17 && G <= 13 * 64) continue;  // the widest strip only where 13 cannot cover the grid
-      // executed lane-FMAs per row; prefer the long strip on ties (13 DFMAs per operand pair)
-      const long long c = lane_slots(G, L, P) * (L == 13 ? 9 : 10);
+      // executed lane-FMAs per row, times the rows a CTA pads when S is not a multiple of its 32/P rows
+      // (S=4 with P=4 would leave half of every warp idle: measured 24% vs 33% of peak for L=7,P=8);
+      // the long strip is ~1.3x more efficient per executed FMA (13 DFMAs per operand pair, fewer switches)
+      const int RB = 32 / P;
+      const long long rows = (long long)RB * ((S + RB - 1) / RB);
+      const long long c = lane_slots(G, L, P) * (L == 13 ? 10 : 13) * rows / S;
       if (best < 0 || c < best) best = c, bl = L, bp = P;
     }
   return fill_layout(S, G, bl, bp, out);
