@@ -43,6 +43,26 @@ def build_host(force=False):
     return HOST_OUT
 
 
+MOD_SRC = os.path.join(HERE, "csrc", "pcb_hostmod.cpp")
+
+
+def build_hostmod(force=False):
+    """`_pcbhost` CPython extension (tile-store bookkeeping): plain g++ against Python.h."""
+    import sysconfig
+
+    out = os.path.join(OUT_DIR, "_pcbhost" + sysconfig.get_config_var("EXT_SUFFIX"))
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(MOD_SRC):
+        return out
+    cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden",
+           "-I" + sysconfig.get_paths()["include"], "-o", out, MOD_SRC]
+    os.makedirs(OUT_DIR, exist_ok=True)
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("g++ failed building %s" % out)
+    return out
+
+
 def needs_build():
     if not os.path.exists(OUT):
         return True
@@ -52,6 +72,7 @@ def needs_build():
 
 def build(force=False, verbose=False):
     build_host(force)
+    build_hostmod(force)
     if not force and not needs_build():
         return OUT
     os.makedirs(OUT_DIR, exist_ok=True)

@@ -63,6 +63,7 @@ class DeviceArena:
         self.prior = -float(np.log(G))
         self._staging = {}
         self._rows = self._sums = self._sums_host = None
+        self._pinned_vals = self._staged_vals = None
         self.staged_bytes = 0  # host->device bytes of job tables / id lists so far
         self.job_timing = None  # set to a list to record (start_event, end_event, n_jobs, conv_pairs) per launch
 
@@ -120,6 +121,17 @@ class DeviceArena:
             self.lib.pcb_arena_import_dev(C.byref(self.c), dense.data_ptr(), ids_dev.data_ptr(), n, self._stream())
         )
         self._keep = dense  # keep alive until the stream has consumed it
+
+    def upload_dense(self, values, ids):
+        """Host [n,S,G] float64 -> pinned staging -> HBM -> arena slots `ids`; returns the bytes sent."""
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        if self._pinned_vals is None or self._pinned_vals.shape != values.shape:
+            self._pinned_vals = torch.empty(values.shape, dtype=torch.float64, pin_memory=True)
+            self._staged_vals = torch.empty(values.shape, dtype=torch.float64, device=self.device)
+        self._pinned_vals.numpy()[...] = values
+        self._staged_vals.copy_(self._pinned_vals, non_blocking=True)
+        self.import_tiles(self._staged_vals, ids)
+        return values.nbytes
 
     def export_tiles(self, ids):
         n = len(ids)

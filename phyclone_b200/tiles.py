@@ -27,8 +27,14 @@ from .engine import JOB_ADD_PRIOR, JOB_SCAN, DeviceArena
 
 
 class TileStore:
-    def __init__(self, values, device=None, capacity=None, variant=-1):
+    """Python face of the tile store.  The bookkeeping (memo tables, pending ops, dependency levels, flush
+    packing) lives in the `_pcbhost.TileBook` C++ extension (csrc/pcb_hostmod.cpp); the arithmetic is executed
+    by `arena` (an `engine.DeviceArena`; the CPU tests plug in a NumPy executor with the same interface)."""
+
+    def __init__(self, values, device=None, capacity=None, variant=-1, arena_factory=None):
         """values: [T,S,G] float64 host array with the data points' log-likelihood grids."""
+        from ._hostmod import load as load_hostmod
+
         values = np.ascontiguousarray(values, dtype=np.float64)
         T, S, G = values.shape
         self.T, self.S, self.G = T, S, G
@@ -36,8 +42,11 @@ class TileStore:
         if capacity is None:
             capacity = int(min(65536, max(4096, (2 << 30) // tile_bytes)))
         self.max_capacity = int(max(capacity, (64 << 30) // tile_bytes))  # the arena doubles on demand up to 64 GB
-        self.arena = DeviceArena(S, G, capacity + 2 * T + 1, device=device, variant=variant)
-        self.device = self.arena.device
+        if arena_factory is None:
+            self.arena = DeviceArena(S, G, capacity + 2 * T + 1, device=device, variant=variant)
+        else:
+            self.arena = arena_factory(S, G, capacity + 2 * T + 1)
+        self.device = getattr(self.arena, "device", None)
         self.prior = self.arena.prior
         # permanent tiles: V_d (data values), P_d = prior + V_d (log_p of a singleton node), PRIOR
         al = self.arena.alloc
@@ -45,174 +54,95 @@ class TileStore:
         self.single_id = list(range(al.alloc(T), al.top))
         self.prior_id = al.alloc(1)
         self.arena.import_tiles(np.full((1, S, G), self.prior), [self.prior_id])
-        self._pinned = torch.empty((T, S, G), dtype=torch.float64, pin_memory=True)
-        self._staged = torch.empty((T, S, G), dtype=torch.float64, device=self.device)
         al.freeze()
+        self._values_host = None
         self.upload_values(values)
-        self.stats = {"flushes": 0, "adds": 0, "node_jobs": 0, "scores": 0, "launches": 0, "memo_hits": 0,
-                      "d2h_bytes": 0, "conv_pairs": 0, "flush_s": 0.0, "sync_s": 0.0}
+        self.book = load_hostmod().TileBook(al.permanent, self.arena.capacity)
+        self._stats = {"flushes": 0, "launches": 0, "d2h_bytes": 0, "flush_s": 0.0}
         self.reset()
 
+    @property
+    def stats(self):
+        d = dict(self._stats)
+        d.update(self.book.counters())
+        return d
+
     def upload_values(self, values):
-        """(Re)load the data points' grids: pinned host buffer -> HBM -> arena tiles V_d and P_d = prior + V_d.
+        """(Re)load the data points' grids: host -> HBM -> arena tiles V_d and P_d = prior + V_d.
         Returns the bytes copied host->device."""
-        self._pinned.numpy()[...] = values
-        self._staged.copy_(self._pinned, non_blocking=True)
-        self.arena.import_tiles(self._staged, self.value_id)
+        self.h2d_bytes = self.arena.upload_dense(values, self.value_id)
         self.arena.tile_add([self.prior_id] * self.T, self.value_id, self.single_id, 0.0)
-        self.h2d_bytes = self._pinned.numel() * 8
         return self.h2d_bytes
 
     # ------------------------------------------------------------------ state
     def reset(self):
         """Start a new arena generation: everything but the permanent tiles is forgotten."""
         self.arena.alloc.reset()
-        self._add_memo = {}
-        self._node_memo = {}
-        self._score_memo = {}  # kids tuple -> (lse_sum, last_sum) floats, or pending slot index
-        self._level = {}  # tile id -> dependency level inside the pending batch
-        self._pend_adds = []  # (level, a, b, out, sign)
-        self._pend_jobs = []  # (level, base, kids, out, slot)
-        self._pend_scores = []  # kids tuples in slot order
+        self.book.reset()
 
-    def _alloc(self):
+    def _grow(self):
         al = self.arena.alloc
-        if al.top >= al.capacity:
-            if al.capacity >= self.max_capacity:
-                raise MemoryError("tile arena exhausted at %d tiles" % al.capacity)
-            self.flush()  # pending ops hold pointers into the current tensors
-            self.arena.grow(min(self.max_capacity, 2 * al.capacity))
-        return al.alloc()
-
-    def _lvl(self, ids):
-        lv = self._level
-        m = 0
-        for i in ids:
-            x = lv.get(i, 0)
-            if x > m:
-                m = x
-        return m + 1
+        if al.capacity >= self.max_capacity:
+            raise MemoryError("tile arena exhausted at %d tiles" % al.capacity)
+        self.flush()  # pending ops hold pointers into the current tensors
+        self.arena.grow(min(self.max_capacity, 2 * al.capacity))
+        self.book.set_capacity(self.arena.capacity)
 
     # -------------------------------------------------------------------- ops
     def add(self, a, b):
         """tile(a) + tile(b)   (log_p += value)"""
-        key = (a, b)
-        t = self._add_memo.get(key)
-        if t is not None:
-            self.stats["memo_hits"] += 1
-            return t
-        t = self._alloc()
-        lv = self._lvl(key)
-        self._level[t] = lv
-        self._pend_adds.append((lv, a, b, t, 1.0))
-        self._add_memo[key] = t
+        t = self.book.add(a, b)
+        if t < 0:
+            self._grow()
+            t = self.book.add(a, b)
         return t
 
     def sub(self, a, b):
         """tile(a) - tile(b)   (log_p -= value)"""
-        key = (a, -1 - b)
-        t = self._add_memo.get(key)
-        if t is not None:
-            self.stats["memo_hits"] += 1
-            return t
-        t = self._alloc()
-        lv = self._lvl((a, b))
-        self._level[t] = lv
-        self._pend_adds.append((lv, a, b, t, -1.0))
-        self._add_memo[key] = t
+        t = self.book.sub(a, b)
+        if t < 0:
+            self._grow()
+            t = self.book.sub(a, b)
         return t
 
     def node(self, base, kids):
         """log_r = tile(base) + log_S(kids in order); kids must be non-empty."""
-        key = (base, kids)
-        t = self._node_memo.get(key)
-        if t is not None:
-            self.stats["memo_hits"] += 1
-            return t
-        t = self._alloc()
-        lv = self._lvl(kids + (base,))
-        self._level[t] = lv
-        self._pend_jobs.append((lv, base, kids, t, -1))
-        self._node_memo[key] = t
+        t = self.book.node(base, kids)
+        if t < 0:
+            self._grow()
+            t = self.book.node(base, kids)
         return t
 
     def score(self, kids):
         """Handle for the data terms of a tree whose dummy root folds `kids` (non-empty):
         (sum_s LSE_g, sum_s last column) of prior + log_S(kids).  Resolve with `value()`."""
-        h = self._score_memo.get(kids)
-        if h is None:
-            slot = len(self._pend_scores)
-            self._pend_scores.append(kids)
-            self._pend_jobs.append((self._lvl(kids), -1, kids, -1, slot))
-            h = self._score_memo[kids] = [slot, None]
-        else:
-            self.stats["memo_hits"] += 1
-        return h
+        return self.book.score(kids)
 
     def value(self, handle):
-        if handle[1] is None:
+        v = self.book.value(handle)
+        if v is None:
             self.flush()
-        return handle[1]
+            v = self.book.value(handle)
+        return v
 
     # ------------------------------------------------------------------ flush
     def flush(self):
-        if not (self._pend_adds or self._pend_jobs):
+        book = self.book
+        if not book.has_pending():
             return
-        st = self.stats
+        st = self._stats
         t_begin = time.perf_counter()
         st["flushes"] += 1
-        scores = self._pend_scores
-        n_slots = len(scores)
-        # group by dependency level; within a level the tile adds go first (jobs of the level may not depend on
-        # them, ops of one level never depend on each other)
-        levels = {}
-        for rec in self._pend_adds:
-            levels.setdefault(rec[0], ([], [], []))[0 if rec[4] > 0 else 1].append(rec)
-        for rec in self._pend_jobs:
-            levels.setdefault(rec[0], ([], [], []))[2].append(rec)
-        packed = []
-        plan = []
-        ext = packed.extend
-        for lv in sorted(levels):
-            pos, neg, jobs = levels[lv]
-            for adds, sign in ((pos, 1.0), (neg, -1.0)):
-                if adds:
-                    plan.append(("add", len(packed), len(adds), sign))
-                    ext([r[1] for r in adds])
-                    ext([r[2] for r in adds])
-                    ext([r[3] for r in adds])
-                    st["adds"] += len(adds)
-            if jobs:
-                off = len(packed)
-                koff = 0
-                kids_all = []
-                kext = kids_all.extend
-                for _, base, ks, out, slot in jobs:
-                    c = len(ks)
-                    ext((koff, c, base, out, (JOB_SCAN | JOB_ADD_PRIOR) if slot >= 0 else JOB_SCAN, slot, 0, 0))
-                    kext(ks)
-                    koff += c
-                ext(kids_all)
-                n = len(jobs)
-                plan.append(("jobs", off, n, koff, koff - n))
-                st["node_jobs"] += n
-                st["conv_pairs"] += koff - n
+        packed, plan, n_slots = book.pack()
         st["launches"] += len(plan) + (2 if n_slots else 0)
-        host = self.arena.run_plan(np.asarray(packed, dtype=np.int32), plan, n_slots)
+        host = self.arena.run_plan(np.frombuffer(packed, dtype=np.int32), plan, n_slots)
         if n_slots:
             st["d2h_bytes"] += 16 * n_slots
-            st["scores"] += n_slots
-            lse, last = host[0].tolist(), host[1].tolist()
-            memo = self._score_memo
-            for slot, ks in enumerate(scores):
-                memo[ks][1] = (lse[slot], last[slot])
-        self._pend_adds = []
-        self._pend_jobs = []
-        self._pend_scores = []
-        self._level = {}
+        book.done(host)
         st["flush_s"] += time.perf_counter() - t_begin
 
     def fetch(self, ids):
         """Dense [n,S,G] host copy of tiles (debug / tests / trace export)."""
         self.flush()
-        return self.arena.export_tiles(list(ids)).cpu().numpy()
+        out = self.arena.export_tiles(list(ids))
+        return out.cpu().numpy() if hasattr(out, "cpu") else out

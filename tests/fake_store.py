@@ -1,77 +1,72 @@
-"""TEST-ONLY stand-in for phyclone_b200.tiles.TileStore: same interface, tiles evaluated eagerly on
-the CPU with the NumPy oracle.  It lets the `-m "not gpu"` suite exercise the whole host side of the
-product sampler (forest bookkeeping, proposal enumeration, RNG call order, lazy scoring protocol)
-without a device.  The product never imports this module."""
+"""TEST-ONLY executor for phyclone_b200.tiles.TileStore: the same interface as engine.DeviceArena, tiles
+evaluated on the CPU with the NumPy oracle.  It lets the `-m "not gpu"` suite exercise the whole host side of
+the product sampler -- forest bookkeeping, proposal enumeration, RNG call order, the lazy scoring protocol AND
+the C++ tile-store bookkeeping / flush packing (csrc/pcb_hostmod.cpp) -- without a device.
+The product never imports this module."""
 
 import numpy as np
 
 from oracle import numerics as onum
+from phyclone_b200.engine import JOB_ADD_PRIOR, JOB_SCAN, TileAllocator
+from phyclone_b200.tiles import TileStore
 
 
-class FakeTileStore:
-    def __init__(self, values):
-        values = np.ascontiguousarray(values, dtype=np.float64)
-        T, S, G = values.shape
-        self.T, self.S, self.G = T, S, G
+class FakeArena:
+    def __init__(self, S, G, capacity):
+        self.S, self.G = S, G
+        self.capacity = int(capacity)
+        self.alloc = TileAllocator(self.capacity)
         self.prior = -float(np.log(G))
         self.tiles = {}
-        self.value_id = list(range(T))
-        self.single_id = list(range(T, 2 * T))
-        self.prior_id = 2 * T
-        for i in range(T):
-            self.tiles[i] = values[i]
-            self.tiles[T + i] = np.full((S, G), self.prior) + values[i]
-        self.tiles[self.prior_id] = np.full((S, G), self.prior)
-        self._perm = 2 * T + 1
-        self.stats = {"flushes": 0, "adds": 0, "node_jobs": 0, "scores": 0, "launches": 0, "memo_hits": 0,
-                      "d2h_bytes": 0, "conv_pairs": 0}
-        self.reset()
+        self.staged_bytes = 0
+        self.job_timing = None
 
-    def reset(self):
-        for k in [k for k in self.tiles if k >= self._perm]:
-            del self.tiles[k]
-        self._top = self._perm
-        self._memo = {}
-        self._score = {}
+    def grow(self, new_capacity):
+        self.capacity = self.alloc.capacity = int(new_capacity)
 
-    def _new(self, key, arr):
-        t = self._top
-        self._top += 1
-        self.tiles[t] = arr
-        self._memo[key] = t
-        return t
+    def import_tiles(self, dense, ids):
+        for t, i in zip(np.asarray(dense, dtype=np.float64), ids):
+            self.tiles[int(i)] = t.copy()
 
-    def add(self, a, b):
-        key = ("a", a, b)
-        t = self._memo.get(key)
-        return t if t is not None else self._new(key, self.tiles[a] + self.tiles[b])
+    def upload_dense(self, values, ids):
+        self.import_tiles(values, ids)
+        return np.asarray(values).nbytes
 
-    def sub(self, a, b):
-        key = ("s", a, b)
-        t = self._memo.get(key)
-        return t if t is not None else self._new(key, self.tiles[a] - self.tiles[b])
+    def export_tiles(self, ids):
+        return np.array([self.tiles[int(i)] for i in ids])
 
-    def node(self, base, kids):
-        key = ("n", base, kids)
-        t = self._memo.get(key)
-        if t is None:
-            self.stats["node_jobs"] += 1
-            t = self._new(key, self.tiles[base] + onum.log_s([self.tiles[k] for k in kids]))
-        return t
+    def tile_add(self, a_ids, b_ids, out_ids, addend=0.0, b_sign=1.0):
+        for k, o in enumerate(out_ids):
+            v = self.tiles[int(a_ids[k])]
+            if b_ids is not None and b_ids[k] >= 0:
+                v = v + b_sign * self.tiles[int(b_ids[k])]
+            self.tiles[int(o)] = v + addend if addend != 0.0 else v + 0.0
 
-    def score(self, kids):
-        h = self._score.get(kids)
-        if h is None:
-            tile = self.prior + onum.log_s([self.tiles[k] for k in kids])
-            h = self._score[kids] = [0, onum.root_terms(tile)]
-            self.stats["scores"] += 1
-        return h
+    def run_plan(self, packed, plan, n_slots):
+        out = np.zeros((2, max(n_slots, 1)))
+        for rec in plan:
+            if rec[0] == "add":
+                _, off, n, sign = rec
+                ids = packed[off:off + 3 * n]
+                self.tile_add(ids[:n], ids[n:2 * n], ids[2 * n:], 0.0, sign)
+            else:
+                _, off, n, n_kids, _ = rec
+                tab = packed[off:off + 8 * n].reshape(n, 8)
+                kids = packed[off + 8 * n:off + 8 * n + n_kids]
+                for koff, c, base, outt, flags, slot, _, _ in tab:
+                    assert flags & JOB_SCAN
+                    tile = onum.log_s([self.tiles[int(k)] for k in kids[koff:koff + c]])
+                    if base >= 0:
+                        tile = self.tiles[int(base)] + tile
+                    if flags & JOB_ADD_PRIOR:
+                        tile = self.prior + tile
+                    if outt >= 0:
+                        self.tiles[int(outt)] = tile
+                    if slot >= 0:
+                        out[0, slot], out[1, slot] = onum.root_terms(tile)
+        return np.ascontiguousarray(out[:, :n_slots]) if n_slots else None
 
-    def value(self, handle):
-        return handle[1]
 
-    def flush(self):
-        self.stats["flushes"] += 1
-
-    def fetch(self, ids):
-        return np.array([self.tiles[i] for i in ids])
+def FakeTileStore(values, capacity=None):
+    """The product's TileStore (C++ bookkeeping included) on the NumPy executor."""
+    return TileStore(values, capacity=capacity, arena_factory=FakeArena)
