@@ -29,6 +29,7 @@ struct PendJob {
 struct Book {
   PyObject_HEAD
   int64_t top, permanent, capacity;
+  int prior_id;
   std::unordered_map<uint64_t, int>* add_memo;
   std::unordered_map<std::string, int>* node_memo;
   std::unordered_map<std::string, int>* score_memo;
@@ -84,9 +85,11 @@ thread_local std::vector<int> g_tmp;
 
 int Book_init(Book* self, PyObject* args, PyObject*) {
   long long permanent = 0, capacity = 0;
-  if (!PyArg_ParseTuple(args, "LL", &permanent, &capacity)) return -1;
+  int prior_id = -1;
+  if (!PyArg_ParseTuple(args, "LL|i", &permanent, &capacity, &prior_id)) return -1;
   self->permanent = self->top = permanent;
   self->capacity = capacity;
+  self->prior_id = prior_id;
   self->add_memo = new std::unordered_map<uint64_t, int>();
   self->node_memo = new std::unordered_map<std::string, int>();
   self->score_memo = new std::unordered_map<std::string, int>();
@@ -144,6 +147,23 @@ PyObject* Book_reset(Book* self, PyObject*) {
 // every op returns -1 (no exception) when the arena is full: the caller grows it and retries
 inline bool full(Book* b) { return b->top >= b->capacity; }
 
+// the three recording ops, callable from C++ (ForestState below) as well as from Python
+int book_add(Book* self, int a, int b, bool neg) {
+  const uint64_t key = ((uint64_t)(uint32_t)a << 33) | ((uint64_t)(uint32_t)b << 1) | (neg ? 1u : 0u);
+  auto it = self->add_memo->find(key);
+  if (it != self->add_memo->end()) {
+    ++self->n_hits;
+    return it->second;
+  }
+  if (full(self)) return -1;
+  const int t = (int)self->top++;
+  const int lv = 1 + std::max(level_of(self, a), level_of(self, b));
+  set_level(self, t, lv);
+  self->adds->push_back(PendAdd{lv, a, b, t, neg});
+  (*self->add_memo)[key] = t;
+  return t;
+}
+
 PyObject* add_impl(Book* self, PyObject* const* args, Py_ssize_t nargs, bool neg) {
   if (nargs != 2) {
     PyErr_SetString(PyExc_TypeError, "add(a, b)");
@@ -151,19 +171,7 @@ PyObject* add_impl(Book* self, PyObject* const* args, Py_ssize_t nargs, bool neg
   }
   const long a = PyLong_AsLong(args[0]), b = PyLong_AsLong(args[1]);
   if ((a == -1 || b == -1) && PyErr_Occurred()) return nullptr;
-  const uint64_t key = ((uint64_t)(uint32_t)a << 33) | ((uint64_t)(uint32_t)b << 1) | (neg ? 1u : 0u);
-  auto it = self->add_memo->find(key);
-  if (it != self->add_memo->end()) {
-    ++self->n_hits;
-    return PyLong_FromLong(it->second);
-  }
-  if (full(self)) return PyLong_FromLong(-1);
-  const int t = (int)self->top++;
-  const int lv = 1 + std::max(level_of(self, (int)a), level_of(self, (int)b));
-  set_level(self, t, lv);
-  self->adds->push_back(PendAdd{lv, (int)a, (int)b, t, neg});
-  (*self->add_memo)[key] = t;
-  return PyLong_FromLong(t);
+  return PyLong_FromLong(book_add(self, (int)a, (int)b, neg));
 }
 
 PyObject* Book_add(Book* self, PyObject* const* args, Py_ssize_t nargs) { return add_impl(self, args, nargs, false); }
@@ -177,6 +185,25 @@ inline std::string key_of(int base, const std::vector<int>& kids) {
   return k;
 }
 
+int book_node(Book* self, int base, const std::vector<int>& kids) {
+  std::string key = key_of(base, kids);
+  auto it = self->node_memo->find(key);
+  if (it != self->node_memo->end()) {
+    ++self->n_hits;
+    return it->second;
+  }
+  if (full(self)) return -1;
+  const int t = (int)self->top++;
+  int lv = level_of(self, base);
+  for (int k : kids) lv = std::max(lv, level_of(self, k));
+  ++lv;
+  set_level(self, t, lv);
+  self->jobs->push_back(PendJob{lv, base, t, -1, (uint32_t)self->kids->size(), (uint32_t)kids.size()});
+  self->kids->insert(self->kids->end(), kids.begin(), kids.end());
+  self->node_memo->emplace(std::move(key), t);
+  return t;
+}
+
 PyObject* Book_node(Book* self, PyObject* const* args, Py_ssize_t nargs) {
   if (nargs != 2) {
     PyErr_SetString(PyExc_TypeError, "node(base, kids)");
@@ -186,33 +213,24 @@ PyObject* Book_node(Book* self, PyObject* const* args, Py_ssize_t nargs) {
   if (base == -1 && PyErr_Occurred()) return nullptr;
   std::vector<int>& kids = g_tmp;
   if (!ints_of(args[1], kids)) return nullptr;
-  std::string key = key_of((int)base, kids);
-  auto it = self->node_memo->find(key);
-  if (it != self->node_memo->end()) {
-    ++self->n_hits;
-    return PyLong_FromLong(it->second);
-  }
-  if (full(self)) return PyLong_FromLong(-1);
-  const int t = (int)self->top++;
-  int lv = level_of(self, (int)base);
-  for (int k : kids) lv = std::max(lv, level_of(self, k));
-  ++lv;
-  set_level(self, t, lv);
-  self->jobs->push_back(PendJob{lv, (int)base, t, -1, (uint32_t)self->kids->size(), (uint32_t)kids.size()});
-  self->kids->insert(self->kids->end(), kids.begin(), kids.end());
-  self->node_memo->emplace(std::move(key), t);
-  return PyLong_FromLong(t);
+  return PyLong_FromLong(book_node(self, (int)base, kids));
 }
+
+int book_score(Book* self, const std::vector<int>& kids);
 
 // score(kids) -> score id (resolve with value())
 PyObject* Book_score(Book* self, PyObject* arg) {
   std::vector<int>& kids = g_tmp;
   if (!ints_of(arg, kids)) return nullptr;
+  return PyLong_FromLong(book_score(self, kids));
+}
+
+int book_score(Book* self, const std::vector<int>& kids) {
   std::string key = key_of(-7, kids);
   auto it = self->score_memo->find(key);
   if (it != self->score_memo->end()) {
     ++self->n_hits;
-    return PyLong_FromLong(it->second);
+    return it->second;
   }
   const int sid = (int)self->sc_ready->size();
   self->sc_ready->push_back(0);
@@ -226,7 +244,7 @@ PyObject* Book_score(Book* self, PyObject* arg) {
   self->jobs->push_back(PendJob{lv, -1, -1, slot, (uint32_t)self->kids->size(), (uint32_t)kids.size()});
   self->kids->insert(self->kids->end(), kids.begin(), kids.end());
   self->score_memo->emplace(std::move(key), sid);
-  return PyLong_FromLong(sid);
+  return sid;
 }
 
 // value(score id) -> (lse_sum, last_sum) or None while the score is still pending
@@ -354,8 +372,499 @@ PyMethodDef Book_methods[] = {
 
 PyTypeObject BookType = {PyVarObject_HEAD_INIT(nullptr, 0)};
 
+// =====================================================================================================
+// ForestState: root-level snapshot of an SMC forest (see smc/forest_state.py for the semantics).
+// Immutable; extensions create new objects.  All tile ops go straight into a TileBook.
+// =====================================================================================================
+#include <cmath>
+
+std::vector<double> g_log;    // g_log[n] = log(n) exactly as NumPy computes it (set from Python)
+std::vector<double> g_rterm;  // FS-CRP root-count term per number of roots (tree/distributions.py:103-133)
+
+inline double lf(long n) { return std::lgamma((double)n + 1.0); }
+inline double tlog(long n) { return (size_t)n < g_log.size() ? g_log[(size_t)n] : std::log((double)n); }
+
+inline uint64_t mix64(uint64_t x) {
+  x ^= x >> 30;
+  x *= 0xbf58476d1ce4e5b9ULL;
+  x ^= x >> 27;
+  x *= 0x94d049bb133111ebULL;
+  x ^= x >> 31;
+  return x;
+}
+inline uint64_t edge_hash(long e, long s, long d) {
+  return mix64(mix64(mix64((uint64_t)e + 0x9e3779b97f4a7c15ULL) ^ (uint64_t)s) ^ (uint64_t)d);
+}
+inline uint64_t data_hash(long node, long pos, long idx) {
+  return mix64(mix64(mix64((uint64_t)node + 0x632be59bd9b4e019ULL) ^ (uint64_t)pos) ^ (uint64_t)idx) ^ 0x5bd1e995ULL;
+}
+
+enum { K_ATTACH = 0, K_NEW = 1, K_OUTLIER = 2 };
+
+struct FState {
+  PyObject_HEAD
+  std::vector<long>* roots;
+  std::vector<int>*lr, *lp, *ndata, *size, *slot, *gidx;
+  std::vector<std::vector<int>>* kids;
+  long n_nodes, n_slots, n_edges, n_out, last_added;
+  int has_last;
+  double crp, mult, oprior, omarg;
+  uint64_t skey;
+  PyObject* roots_tuple;
+};
+
+extern PyTypeObject FStateType;
+
+FState* fstate_alloc() {
+  FState* s = PyObject_New(FState, &FStateType);
+  if (!s) return nullptr;
+  s->roots = new std::vector<long>();
+  s->lr = new std::vector<int>();
+  s->lp = new std::vector<int>();
+  s->ndata = new std::vector<int>();
+  s->size = new std::vector<int>();
+  s->slot = new std::vector<int>();
+  s->gidx = new std::vector<int>();
+  s->kids = new std::vector<std::vector<int>>();
+  s->n_nodes = 0;
+  s->n_slots = 1;
+  s->n_edges = s->n_out = 0;
+  s->last_added = 0;
+  s->has_last = 0;
+  s->crp = s->mult = s->oprior = s->omarg = 0.0;
+  s->skey = 0;
+  s->roots_tuple = nullptr;
+  return s;
+}
+
+void FState_dealloc(FState* s) {
+  delete s->roots;
+  delete s->lr;
+  delete s->lp;
+  delete s->ndata;
+  delete s->size;
+  delete s->slot;
+  delete s->gidx;
+  delete s->kids;
+  Py_XDECREF(s->roots_tuple);
+  PyObject_Del(s);
+}
+
+PyObject* roots_tuple_of(FState* s) {
+  if (!s->roots_tuple) {
+    PyObject* t = PyTuple_New((Py_ssize_t)s->roots->size());
+    if (!t) return nullptr;
+    for (size_t i = 0; i < s->roots->size(); ++i) PyTuple_SET_ITEM(t, (Py_ssize_t)i, PyLong_FromLong((*s->roots)[i]));
+    s->roots_tuple = t;
+  }
+  Py_INCREF(s->roots_tuple);
+  return s->roots_tuple;
+}
+
+inline int index_of(FState* s, long node) {
+  for (size_t j = 0; j < s->roots->size(); ++j)
+    if ((*s->roots)[j] == node) return (int)j;
+  return -1;
+}
+
+struct DataPt {
+  int idx, value_id, single_id;
+  double op, opn, marg;
+};
+inline bool parse_dp(PyObject* o, DataPt& d) {
+  return PyArg_ParseTuple(o, "iiiddd", &d.idx, &d.value_id, &d.single_id, &d.op, &d.opn, &d.marg) != 0;
+}
+
+inline bool longs_of(PyObject* seq, std::vector<long>& out) {
+  out.clear();
+  PyObject* it = PyObject_GetIter(seq);
+  if (!it) return false;
+  while (PyObject* item = PyIter_Next(it)) {
+    const long v = PyLong_AsLong(item);
+    Py_DECREF(item);
+    if (v == -1 && PyErr_Occurred()) {
+      Py_DECREF(it);
+      return false;
+    }
+    out.push_back(v);
+  }
+  Py_DECREF(it);
+  return !PyErr_Occurred();
+}
+
+// (log_p prior, log_p_one prior) from running statistics: tree/distributions.py:39-133, same operation
+// order as smc/forest_state.py::_priors
+inline void priors(double log_alpha, long n, double crp, double mult, const int* sizes, size_t n_sizes, double oprior,
+                   double omarg, double& lp, double& lp1) {
+  const double base = (double)n * log_alpha + crp;
+  lp = base - (double)(n - 1) * tlog(n + 1) - mult;
+  double ways = 0.0;
+  for (size_t i = 0; i < n_sizes; ++i) ways += (double)(sizes[i] - 1) * tlog(sizes[i]);
+  lp1 = base + (-ways + g_rterm[n_sizes]) - mult;
+  const double extra = oprior + omarg;
+  lp += extra;
+  lp1 += extra;
+}
+
+// forest_state(roots, lr, lp, kids, ndata, size, slot, gidx, n_nodes, n_slots, n_edges, crp, mult, oprior, omarg,
+//              n_out, skey, last_added | None)
+PyObject* mod_forest_state(PyObject*, PyObject* args) {
+  PyObject *roots, *lr, *lp, *kids, *ndata, *size, *slot, *gidx, *last;
+  long n_nodes, n_slots, n_edges, n_out;
+  double crp, mult, oprior, omarg;
+  unsigned long long skey;
+  if (!PyArg_ParseTuple(args, "OOOOOOOOlllddddlKO", &roots, &lr, &lp, &kids, &ndata, &size, &slot, &gidx, &n_nodes, &n_slots,
+                        &n_edges, &crp, &mult, &oprior, &omarg, &n_out, &skey, &last))
+    return nullptr;
+  FState* s = fstate_alloc();
+  if (!s) return nullptr;
+  bool ok = longs_of(roots, *s->roots) && ints_of(lr, *s->lr) && ints_of(lp, *s->lp) && ints_of(ndata, *s->ndata) &&
+            ints_of(size, *s->size) && ints_of(slot, *s->slot) && ints_of(gidx, *s->gidx);
+  if (ok) {
+    PyObject* it = PyObject_GetIter(kids);
+    ok = it != nullptr;
+    if (ok) {
+      while (PyObject* item = PyIter_Next(it)) {
+        std::vector<int> k;
+        const bool good = ints_of(item, k);
+        Py_DECREF(item);
+        if (!good) {
+          ok = false;
+          break;
+        }
+        s->kids->push_back(std::move(k));
+      }
+      Py_DECREF(it);
+    }
+  }
+  if (!ok) {
+    Py_DECREF(s);
+    return nullptr;
+  }
+  s->n_nodes = n_nodes;
+  s->n_slots = n_slots;
+  s->n_edges = n_edges;
+  s->n_out = n_out;
+  s->crp = crp;
+  s->mult = mult;
+  s->oprior = oprior;
+  s->omarg = omarg;
+  s->skey = skey;
+  if (last != Py_None) {
+    s->last_added = PyLong_AsLong(last);
+    s->has_last = 1;
+  }
+  return (PyObject*)s;
+}
+
+// extend(book, kind, dp, arg) -> thawed successor state, or None if the arena is full
+PyObject* FState_extend(FState* self, PyObject* args) {
+  Book* book;
+  int kind;
+  PyObject *dpo, *arg;
+  if (!PyArg_ParseTuple(args, "O!iOO", &BookType, &book, &kind, &dpo, &arg)) return nullptr;
+  DataPt dp;
+  if (!parse_dp(dpo, dp)) return nullptr;
+  const size_t R = self->roots->size();
+  long node = 0;
+  std::vector<long> taken_names;
+  int lp_new = -1, lr_new = -1, j_at = -1;
+  std::vector<int> take, keep, nk;
+  // record the tile ops first: nothing is allocated if the arena turns out to be full
+  if (kind == K_ATTACH) {
+    node = PyLong_AsLong(arg);
+    if (node == -1 && PyErr_Occurred()) return nullptr;
+    j_at = index_of(self, node);
+    if (j_at < 0) {
+      PyErr_SetString(PyExc_KeyError, "node is not a root of this state");
+      return nullptr;
+    }
+    lp_new = (*self->lp)[j_at] == book->prior_id ? dp.single_id : book_add(book, (*self->lp)[j_at], dp.value_id, false);
+    if (lp_new < 0) Py_RETURN_NONE;
+    lr_new = (*self->kids)[j_at].empty() ? lp_new : book_node(book, lp_new, (*self->kids)[j_at]);
+    if (lr_new < 0) Py_RETURN_NONE;
+  } else if (kind == K_NEW) {
+    if (!longs_of(arg, taken_names)) return nullptr;
+    for (size_t j = 0; j < R; ++j) {
+      bool in = false;
+      for (long t : taken_names) in |= (t == (*self->roots)[j]);
+      (in ? take : keep).push_back((int)j);
+    }
+    for (int j : take) nk.push_back((*self->lr)[j]);  // descending slot order = thawed child order
+    lp_new = dp.single_id;
+    lr_new = nk.empty() ? lp_new : book_node(book, lp_new, nk);
+    if (lr_new < 0) Py_RETURN_NONE;
+  }
+  FState* s = fstate_alloc();
+  if (!s) return nullptr;
+  s->n_out = self->n_out;
+  s->omarg = self->omarg;
+  s->oprior = self->oprior;
+  s->has_last = 1;
+  if (kind == K_OUTLIER) {
+    *s->roots = *self->roots;
+    *s->lr = *self->lr;
+    *s->lp = *self->lp;
+    *s->kids = *self->kids;
+    *s->ndata = *self->ndata;
+    *s->size = *self->size;
+    *s->slot = *self->slot;
+    *s->gidx = *self->gidx;
+    s->n_nodes = self->n_nodes;
+    s->n_slots = self->n_slots;
+    s->n_edges = self->n_edges;
+    s->crp = self->crp;
+    s->mult = self->mult;
+    s->skey = self->skey ^ data_hash(-1, self->n_out, dp.idx);
+    s->n_out = self->n_out + 1;
+    s->omarg = self->omarg + dp.marg;
+    if (dp.op != 0.0) s->oprior = self->oprior + dp.op;
+    s->last_added = -1;
+    return (PyObject*)s;
+  }
+  if (dp.op != 0.0) s->oprior = self->oprior + dp.opn;
+  if (kind == K_ATTACH) {
+    const int n = (*self->ndata)[j_at];
+    *s->roots = *self->roots;
+    *s->kids = *self->kids;
+    *s->size = *self->size;
+    *s->slot = *self->slot;
+    *s->gidx = *self->gidx;
+    *s->lp = *self->lp;
+    *s->lr = *self->lr;
+    *s->ndata = *self->ndata;
+    (*s->lp)[j_at] = lp_new;
+    (*s->lr)[j_at] = lr_new;
+    (*s->ndata)[j_at] = n + 1;
+    s->n_nodes = self->n_nodes;
+    s->n_slots = self->n_slots;
+    s->n_edges = self->n_edges;
+    s->mult = self->mult;
+    s->crp = self->crp + (n >= 1 ? lf(n) - lf(n - 1) : 0.0);
+    s->skey = self->skey ^ data_hash(node, n, dp.idx);
+    s->last_added = node;
+    return (PyObject*)s;
+  }
+  const long name = self->n_nodes, gi = self->n_slots, root_gi = 0;
+  s->roots->push_back(name);
+  s->lr->push_back(lr_new);
+  s->lp->push_back(lp_new);
+  s->kids->push_back(nk);
+  s->ndata->push_back(1);
+  int sz = 1;
+  for (int j : take) sz += (*self->size)[j];
+  s->size->push_back(sz);
+  s->slot->push_back((int)self->n_edges);
+  s->gidx->push_back((int)gi);
+  for (int j : keep) {
+    s->roots->push_back((*self->roots)[j]);
+    s->lr->push_back((*self->lr)[j]);
+    s->lp->push_back((*self->lp)[j]);
+    s->kids->push_back((*self->kids)[j]);
+    s->ndata->push_back((*self->ndata)[j]);
+    s->size->push_back((*self->size)[j]);
+    s->slot->push_back((*self->slot)[j]);
+    s->gidx->push_back((*self->gidx)[j]);
+  }
+  s->n_nodes = self->n_nodes + 1;
+  s->n_slots = self->n_slots + 1;
+  s->n_edges = self->n_edges + 1;
+  const long k = (long)take.size();
+  s->mult = self->mult - lf((long)R) + lf((long)R - k + 1) + lf(k);
+  s->crp = self->crp;
+  uint64_t key = self->skey ^ edge_hash(self->n_edges, root_gi, gi) ^ data_hash(name, 0, dp.idx);
+  for (int j : take) {
+    const long e = (*self->slot)[j], c = (*self->gidx)[j];
+    key ^= edge_hash(e, root_gi, c) ^ edge_hash(e, gi, c);
+  }
+  s->skey = key;
+  s->last_added = name;
+  return (PyObject*)s;
+}
+
+// score_attach_all(book, dp, nodes, log_alpha) -> [(prior_p, prior_one, score id, n children of node)] | None
+PyObject* FState_score_attach_all(FState* self, PyObject* args) {
+  Book* book;
+  PyObject *dpo, *nodes_o;
+  double log_alpha;
+  if (!PyArg_ParseTuple(args, "O!OOd", &BookType, &book, &dpo, &nodes_o, &log_alpha)) return nullptr;
+  DataPt dp;
+  if (!parse_dp(dpo, dp)) return nullptr;
+  std::vector<long> nodes;
+  if (!longs_of(nodes_o, nodes)) return nullptr;
+  double oprior = self->oprior;
+  if (dp.op != 0.0) oprior = oprior + dp.opn;
+  const long n = self->n_nodes;
+  const double head = (double)n * log_alpha;
+  double ways = 0.0;
+  for (int z : *self->size) ways += (double)(z - 1) * tlog(z);
+  const double tail_p = -(double)(n - 1) * tlog(n + 1) - self->mult + (oprior + self->omarg);
+  const double tail_one = (-ways + g_rterm[self->size->size()]) - self->mult + (oprior + self->omarg);
+  std::vector<int> kids_t;
+  PyObject* out = PyList_New(0);
+  if (!out) return nullptr;
+  for (long node : nodes) {
+    const int j = index_of(self, node);
+    if (j < 0) {
+      Py_DECREF(out);
+      PyErr_SetString(PyExc_KeyError, "node is not a root of the base state");
+      return nullptr;
+    }
+    const int m = (*self->ndata)[j];
+    const double crp = head + (self->crp + (m >= 1 ? lf(m) - lf(m - 1) : 0.0));
+    const int lr = book_add(book, (*self->lr)[j], dp.value_id, false);  // log_r += value (tree/tree_node.py:47-52)
+    if (lr < 0) {
+      Py_DECREF(out);
+      Py_RETURN_NONE;
+    }
+    kids_t = *self->lr;
+    kids_t[j] = lr;
+    const int sid = book_score(book, kids_t);
+    PyObject* rec = Py_BuildValue("(ddin)", crp + tail_p, crp + tail_one, sid, (Py_ssize_t)(*self->kids)[j].size());
+    PyList_Append(out, rec);
+    Py_DECREF(rec);
+  }
+  return out;
+}
+
+// score_new(book, dp, children in adoption order, log_alpha) -> (prior_p, prior_one, sid, roots tuple, k) | None
+PyObject* FState_score_new(FState* self, PyObject* args) {
+  Book* book;
+  PyObject *dpo, *children_o;
+  double log_alpha;
+  if (!PyArg_ParseTuple(args, "O!OOd", &BookType, &book, &dpo, &children_o, &log_alpha)) return nullptr;
+  DataPt dp;
+  if (!parse_dp(dpo, dp)) return nullptr;
+  std::vector<long> children;
+  if (!longs_of(children_o, children)) return nullptr;
+  double oprior = self->oprior;
+  if (dp.op != 0.0) oprior = oprior + dp.opn;
+  const size_t R = self->roots->size();
+  std::vector<int> order;
+  for (long c : children) {
+    const int j = index_of(self, c);
+    if (j < 0) {
+      PyErr_SetString(PyExc_KeyError, "child is not a root of the base state");
+      return nullptr;
+    }
+    order.push_back(j);
+  }
+  // children adopted in the given order, each new edge at the HEAD of the adjacency list: fold order is reversed
+  std::vector<int> kids_t;
+  for (size_t i = order.size(); i-- > 0;) kids_t.push_back((*self->lr)[order[i]]);
+  const int lp_t = dp.single_id;
+  const int lr = kids_t.empty() ? lp_t : book_node(book, lp_t, kids_t);
+  if (lr < 0) Py_RETURN_NONE;
+  std::vector<char> taken(R, 0);
+  for (int j : order) taken[(size_t)j] = 1;
+  const long k = (long)order.size();
+  const double mult = self->mult - lf((long)R) + lf((long)R - k + 1) + lf(k);
+  std::vector<int> sizes, root_kids;
+  int sz = 1;
+  for (int j : order) sz += (*self->size)[j];
+  sizes.push_back(sz);
+  root_kids.push_back(lr);
+  PyObject* roots = PyTuple_New((Py_ssize_t)(R - (size_t)k + 1));
+  if (!roots) return nullptr;
+  PyTuple_SET_ITEM(roots, 0, PyLong_FromLong(self->n_nodes));
+  Py_ssize_t pos = 1;
+  for (size_t j = 0; j < R; ++j)
+    if (!taken[j]) {
+      sizes.push_back((*self->size)[j]);
+      root_kids.push_back((*self->lr)[j]);
+      PyTuple_SET_ITEM(roots, pos++, PyLong_FromLong((*self->roots)[j]));
+    }
+  double lp, lp1;
+  priors(log_alpha, self->n_nodes + 1, self->crp, mult, sizes.data(), sizes.size(), oprior, self->omarg, lp, lp1);
+  const int sid = book_score(book, root_kids);
+  return Py_BuildValue("(ddiNn)", lp, lp1, sid, roots, (Py_ssize_t)k);
+}
+
+// score_outlier(book, dp, log_alpha) -> (prior_p, prior_one, sid or -1, roots tuple)
+PyObject* FState_score_outlier(FState* self, PyObject* args) {
+  Book* book;
+  PyObject* dpo;
+  double log_alpha;
+  if (!PyArg_ParseTuple(args, "O!Od", &BookType, &book, &dpo, &log_alpha)) return nullptr;
+  DataPt dp;
+  if (!parse_dp(dpo, dp)) return nullptr;
+  double oprior = self->oprior;
+  if (dp.op != 0.0) oprior = oprior + dp.op;
+  const double omarg = self->omarg + dp.marg;
+  double lp, lp1;
+  priors(log_alpha, self->n_nodes, self->crp, self->mult, self->size->data(), self->size->size(), oprior, omarg, lp, lp1);
+  const int sid = self->lr->empty() ? -1 : book_score(book, *self->lr);
+  PyObject* roots = roots_tuple_of(self);
+  if (!roots) return nullptr;
+  return Py_BuildValue("(ddiN)", lp, lp1, sid, roots);
+}
+
+PyObject* FState_get_roots(FState* self, void*) { return roots_tuple_of(self); }
+PyObject* FState_get_n_nodes(FState* self, void*) { return PyLong_FromLong(self->n_nodes); }
+PyObject* FState_get_skey(FState* self, void*) { return PyLong_FromUnsignedLongLong(self->skey); }
+PyObject* FState_get_last(FState* self, void*) {
+  if (!self->has_last) Py_RETURN_NONE;
+  return PyLong_FromLong(self->last_added);
+}
+PyObject* FState_get_lr(FState* self, void*) {
+  PyObject* t = PyTuple_New((Py_ssize_t)self->lr->size());
+  if (!t) return nullptr;
+  for (size_t i = 0; i < self->lr->size(); ++i) PyTuple_SET_ITEM(t, (Py_ssize_t)i, PyLong_FromLong((*self->lr)[i]));
+  return t;
+}
+
+PyMethodDef FState_methods[] = {
+    {"extend", (PyCFunction)FState_extend, METH_VARARGS, "thawed successor state (None if the arena is full)"},
+    {"score_attach_all", (PyCFunction)FState_score_attach_all, METH_VARARGS, ""},
+    {"score_new", (PyCFunction)FState_score_new, METH_VARARGS, ""},
+    {"score_outlier", (PyCFunction)FState_score_outlier, METH_VARARGS, ""},
+    {nullptr, nullptr, 0, nullptr}};
+
+PyGetSetDef FState_getset[] = {{"roots", (getter)FState_get_roots, nullptr, "root names, in order", nullptr},
+                               {"n_nodes", (getter)FState_get_n_nodes, nullptr, "", nullptr},
+                               {"skey", (getter)FState_get_skey, nullptr, "structure hash", nullptr},
+                               {"last_added", (getter)FState_get_last, nullptr, "", nullptr},
+                               {"lr", (getter)FState_get_lr, nullptr, "log_r tile ids of the roots", nullptr},
+                               {nullptr, nullptr, nullptr, nullptr, nullptr}};
+
+PyTypeObject FStateType = {PyVarObject_HEAD_INIT(nullptr, 0)};
+
+PyObject* mod_set_tables(PyObject*, PyObject* args) {
+  PyObject *logs, *rterms;
+  if (!PyArg_ParseTuple(args, "OO", &logs, &rterms)) return nullptr;
+  for (int which = 0; which < 2; ++which) {
+    PyObject* fast = PySequence_Fast(which ? rterms : logs, "expected a sequence of floats");
+    if (!fast) return nullptr;
+    std::vector<double>& dst = which ? g_rterm : g_log;
+    dst.clear();
+    for (Py_ssize_t i = 0; i < PySequence_Fast_GET_SIZE(fast); ++i) dst.push_back(PyFloat_AsDouble(PySequence_Fast_GET_ITEM(fast, i)));
+    Py_DECREF(fast);
+    if (PyErr_Occurred()) return nullptr;
+  }
+  Py_RETURN_NONE;
+}
+
+PyObject* mod_edge_hash(PyObject*, PyObject* args) {
+  long e, s, d;
+  if (!PyArg_ParseTuple(args, "lll", &e, &s, &d)) return nullptr;
+  return PyLong_FromUnsignedLongLong(edge_hash(e, s, d));
+}
+PyObject* mod_data_hash(PyObject*, PyObject* args) {
+  long node, pos, idx;
+  if (!PyArg_ParseTuple(args, "lll", &node, &pos, &idx)) return nullptr;
+  return PyLong_FromUnsignedLongLong(data_hash(node, pos, idx));
+}
+
+PyMethodDef mod_methods[] = {
+    {"forest_state", mod_forest_state, METH_VARARGS, "build a ForestState from Python sequences"},
+    {"set_tables", mod_set_tables, METH_VARARGS, "log(n) and r_term(n) tables"},
+    {"edge_hash", mod_edge_hash, METH_VARARGS, "structure-hash contribution of an edge (slot, src, dst)"},
+    {"data_hash", mod_data_hash, METH_VARARGS, "structure-hash contribution of a data point (node, position, idx)"},
+    {nullptr, nullptr, 0, nullptr}};
+
+
 PyModuleDef moddef = {PyModuleDef_HEAD_INIT, "_pcbhost", "host-side bookkeeping of the phyclone_b200 tile store", -1,
-                      nullptr};
+                      mod_methods};
 
 }  // namespace
 
@@ -372,5 +881,14 @@ PyMODINIT_FUNC PyInit__pcbhost(void) {
   if (!m) return nullptr;
   Py_INCREF(&BookType);
   PyModule_AddObject(m, "TileBook", (PyObject*)&BookType);
+  FStateType.tp_name = "_pcbhost.ForestState";
+  FStateType.tp_basicsize = sizeof(FState);
+  FStateType.tp_flags = Py_TPFLAGS_DEFAULT;
+  FStateType.tp_dealloc = (destructor)FState_dealloc;
+  FStateType.tp_methods = FState_methods;
+  FStateType.tp_getset = FState_getset;
+  if (PyType_Ready(&FStateType) < 0) return nullptr;
+  Py_INCREF(&FStateType);
+  PyModule_AddObject(m, "ForestState", (PyObject*)&FStateType);
   return m;
 }

@@ -7,17 +7,22 @@ from .. import ops
 
 
 class DataPoint(object):
-    __slots__ = ("idx", "value", "name", "outlier_prob", "outlier_marginal_prob", "outlier_prob_not")
+    __slots__ = ("idx", "value", "name", "outlier_prob", "outlier_marginal_prob", "outlier_prob_not", "_t", "_ts")
 
     def __init__(self, idx, value, name=None, outlier_prob=0, outlier_prob_not=1, outlier_marginal_prob=None):
         self.idx = idx
         self.value = value
+        self._t = self._ts = None  # host tuple cached by smc/forest_state.py for one tile store
         self.name = idx if name is None else name
         self.outlier_prob = outlier_prob
         self.outlier_prob_not = outlier_prob_not
         if outlier_marginal_prob is None:  # data/base.py:31-37, on the device
             outlier_marginal_prob = float(ops.outlier_marginal(np.asarray(value)))
         self.outlier_marginal_prob = outlier_marginal_prob
+
+    def __reduce__(self):  # the cached host tuple points at a tile store: never pickled
+        return (DataPoint, (self.idx, self.value, self.name, self.outlier_prob, self.outlier_prob_not,
+                            self.outlier_marginal_prob))
 
     def __hash__(self):
         return hash(self.name)

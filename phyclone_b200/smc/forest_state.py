@@ -18,34 +18,46 @@ Two orders matter and are kept apart exactly as in the reference (SURVEY.md App.
 
 import numpy as np
 
-from ..utils.math import cached_log_factorial as lf
+from .._hostmod import load as _load_hostmod
 
 ATTACH, NEW, OUTLIER = 0, 1, 2
 
+_hm = _load_hostmod()
+_tables = [None, 0]
+
+
+def ensure_tables(prior, n):
+    """Hand the extension log(k) and the FS-CRP root-count term r(k), k <= n, computed with NumPy exactly as the
+    Python prior does (tree/distributions.py:39-133), so both sides add the same doubles."""
+    if _tables[0] != prior._c_const or _tables[1] < n:
+        n = max(n, 64)
+        logs = [0.0] + [float(np.log(k)) for k in range(1, n + 2)]
+        _hm.set_tables(logs, [float(prior._compute_r_term(k)) for k in range(n + 1)])
+        _tables[0], _tables[1] = prior._c_const, n
+
+
+def host_tuple(store, dp):
+    """(idx, value tile, singleton log_p tile, outlier prob, not-outlier prob, outlier marginal) of a data point"""
+    try:
+        if dp._ts is store:
+            return dp._t
+    except AttributeError:  # a foreign data point class: not cached
+        return (dp.idx, store.value_id[dp.idx], store.single_id[dp.idx], dp.outlier_prob, dp.outlier_prob_not,
+                dp.outlier_marginal_prob)
+    dp._t = (dp.idx, store.value_id[dp.idx], store.single_id[dp.idx], dp.outlier_prob, dp.outlier_prob_not,
+             dp.outlier_marginal_prob)
+    dp._ts = store
+    return dp._t
+
 
 class ForestState(object):
-    __slots__ = ("roots", "lr", "lp", "kids", "ndata", "size", "slot", "gidx", "n_nodes", "n_slots", "n_edges",
-                 "crp", "mult", "oprior", "omarg", "n_out", "skey", "last_added", "index", "store", "grid_size")
-
-    def index_of(self, node):
-        ix = self.index
-        if ix is None:
-            ix = self.index = {r: j for j, r in enumerate(self.roots)}
-        return ix[node]
+    """Constructors of `_pcbhost.ForestState` (csrc/pcb_hostmod.cpp): roots in order with their log_r / log_p tile
+    ids, ordered child tiles, data counts, subtree sizes, edge slots and graph indices, plus the running prior
+    statistics (crp sum, multiplicity, outlier prior, outlier marginal) and the structure hash."""
 
     @staticmethod
-    def empty(store, grid_size):
-        s = ForestState()
-        s.roots = s.lr = s.lp = s.kids = s.ndata = s.size = s.slot = s.gidx = ()
-        s.n_nodes, s.n_slots, s.n_edges = 0, 1, 0
-        s.crp = s.mult = s.omarg = 0.0
-        s.oprior = 0
-        s.n_out = 0
-        s.skey = 0
-        s.last_added = None
-        s.index = None
-        s.store, s.grid_size = store, grid_size
-        return s
+    def empty(store, grid_size=None):
+        return _hm.forest_state((), (), (), (), (), (), (), (), 0, 1, 0, 0.0, 0.0, 0.0, 0.0, 0, 0, None)
 
     @staticmethod
     def from_tree(tree):
@@ -56,89 +68,25 @@ class ForestState(object):
         crp, mult, size, oprior, omarg = tree.prior_terms()
         root = tree._node_indices[tree._ROOT_NODE_NAME]
         gis = g.successor_indices(root)
-        s = ForestState()
-        s.gidx = tuple(gis)
-        s.roots = tuple(g.payload[i] for i in gis)
-        s.lr = tuple(tree._lr[i] for i in gis)
-        s.lp = tuple(tree._lp[i] for i in gis)
-        s.kids = tuple(tuple(tree._lr[c] for c in g.successor_indices(i)) for i in gis)
-        s.ndata = tuple(len(tree._data[r]) for r in s.roots)
-        s.size = tuple(size[i] for i in gis)
-        s.slot = tuple(g.inn[i][0] for i in gis)
-        s.n_nodes = g.n_nodes - 1
-        s.n_slots = len(g.payload)
-        s.n_edges = len(g.esrc)
-        s.crp, s.mult, s.oprior, s.omarg = crp, mult, oprior, omarg
-        s.n_out = len(tree._data[tree._OUTLIER_NODE_NAME])
-        s.skey = tree.structure_key()[0]
-        s.last_added = tree._last_node_added_to
-        s.index = None
-        s.store, s.grid_size = tree.store, tree.grid_size
-        return s
+        roots = [g.payload[i] for i in gis]
+        return _hm.forest_state(
+            roots, [tree._lr[i] for i in gis], [tree._lp[i] for i in gis],
+            [[tree._lr[c] for c in g.successor_indices(i)] for i in gis], [len(tree._data[r]) for r in roots],
+            [size[i] for i in gis], [g.inn[i][0] for i in gis], gis, g.n_nodes - 1, len(g.payload), len(g.esrc),
+            crp, mult, oprior, omarg, len(tree._data[tree._OUTLIER_NODE_NAME]), tree.structure_key()[0],
+            tree._last_node_added_to)
 
-    # ---------------------------------------------------------------- thawed successor of a thawed state
-    def extend(self, kind, dp, arg):
-        """State of `from_dict(to_dict(self + edit))`; `self` must itself be a thawed state."""
-        st = self.store
-        s = ForestState()
-        s.store, s.grid_size, s.index = st, self.grid_size, None
-        s.n_out, s.omarg, s.oprior = self.n_out, self.omarg, self.oprior
-        if kind == OUTLIER:
-            for f in ("roots", "lr", "lp", "kids", "ndata", "size", "slot", "gidx", "n_nodes", "n_slots", "n_edges",
-                      "crp", "mult"):
-                setattr(s, f, getattr(self, f))
-            s.skey = self.skey ^ hash((-1, self.n_out, dp.idx, "d"))
-            s.n_out = self.n_out + 1
-            s.omarg = self.omarg + dp.outlier_marginal_prob
-            if dp.outlier_prob != 0:
-                s.oprior = self.oprior + dp.outlier_prob
-            s.last_added = -1
-            return s
-        if dp.outlier_prob != 0:
-            s.oprior = self.oprior + dp.outlier_prob_not
-        v = st.value_id[dp.idx]
-        if kind == ATTACH:
-            j = self.index_of(arg)
-            n = self.ndata[j]
-            lp = st.single_id[dp.idx] if self.lp[j] == st.prior_id else st.add(self.lp[j], v)
-            lr = st.node(lp, self.kids[j]) if self.kids[j] else lp
-            s.roots, s.kids, s.size, s.slot, s.gidx = self.roots, self.kids, self.size, self.slot, self.gidx
-            s.lp = self.lp[:j] + (lp,) + self.lp[j + 1:]
-            s.lr = self.lr[:j] + (lr,) + self.lr[j + 1:]
-            s.ndata = self.ndata[:j] + (n + 1,) + self.ndata[j + 1:]
-            s.n_nodes, s.n_slots, s.n_edges, s.mult = self.n_nodes, self.n_slots, self.n_edges, self.mult
-            s.crp = self.crp + (lf(n) - lf(n - 1) if n >= 1 else 0.0)
-            s.skey = self.skey ^ hash((arg, n, dp.idx, "d"))
-            s.last_added = arg
-            return s
-        # NEW root adopting the roots in `arg` (a frozenset of names)
-        take = [j for j, r in enumerate(self.roots) if r in arg]  # descending slot order = thawed child order
-        keep = [j for j, r in enumerate(self.roots) if r not in arg]
-        name = self.n_nodes
-        gi = self.n_slots
-        root_gi = 0
-        lp = st.single_id[dp.idx]
-        kids = tuple(self.lr[j] for j in take)
-        lr = st.node(lp, kids) if kids else lp
-        s.roots = (name,) + tuple(self.roots[j] for j in keep)
-        s.lr = (lr,) + tuple(self.lr[j] for j in keep)
-        s.lp = (lp,) + tuple(self.lp[j] for j in keep)
-        s.kids = (kids,) + tuple(self.kids[j] for j in keep)
-        s.ndata = (1,) + tuple(self.ndata[j] for j in keep)
-        s.size = (1 + sum(self.size[j] for j in take),) + tuple(self.size[j] for j in keep)
-        s.slot = (self.n_edges,) + tuple(self.slot[j] for j in keep)
-        s.gidx = (gi,) + tuple(self.gidx[j] for j in keep)
-        s.n_nodes, s.n_slots, s.n_edges = self.n_nodes + 1, self.n_slots + 1, self.n_edges + 1
-        R, k = len(self.roots), len(take)
-        s.mult = self.mult - lf(R) + lf(R - k + 1) + lf(k)
-        s.crp = self.crp
-        key = self.skey ^ hash((self.n_edges, root_gi, gi)) ^ hash((name, 0, dp.idx, "d"))
-        for j in take:
-            e, c = self.slot[j], self.gidx[j]
-            key ^= hash((e, root_gi, c)) ^ hash((e, gi, c))
-        s.skey = key
-        s.last_added = name
-        return s
+
+def extend(state, store, kind, dp, arg):
+    """State of `from_dict(to_dict(state + edit))`; `state` must itself be a thawed state."""
+    t = host_tuple(store, dp)
+    if kind == NEW:
+        arg = tuple(arg)
+    s = state.extend(store.book, kind, t, arg)
+    if s is None:  # arena full: grow it and record again (ops already recorded are memoised)
+        store._grow()
+        s = state.extend(store.book, kind, t, arg)
+    return s
 
 
 class StateScore(object):
@@ -185,70 +133,35 @@ def _priors(prior, n, crp, mult, sizes, oprior, omarg):
     return log_p + extra, log_p_one + extra
 
 
-def score_edit(base, kind, dp, arg, tree_dist):
+def score_edit(base, store, kind, dp, arg, tree_dist):
     """(StateScore, as-built roots order, children of the node the point went to) of `base + edit`, where
     `base` is the state of the tree the reference would have copied (thawed parent, or the retained path's
     as-built tree)."""
-    st = base.store
-    prior = tree_dist.prior
-    oprior, omarg = base.oprior, base.omarg
+    t = host_tuple(store, dp)
+    log_alpha = tree_dist.prior.log_alpha
     if kind == OUTLIER:
-        if dp.outlier_prob != 0:
-            oprior = oprior + dp.outlier_prob
-        omarg = omarg + dp.outlier_marginal_prob
-        lp, lp1 = _priors(prior, base.n_nodes, base.crp, base.mult, base.size, oprior, omarg)
-        handle = st.score(base.lr) if base.lr else None
-        return StateScore(lp, lp1, handle, st), base.roots, 0
-    if dp.outlier_prob != 0:
-        oprior = oprior + dp.outlier_prob_not
-    v = st.value_id[dp.idx]
+        pp, p1, sid, roots = base.score_outlier(store.book, t, log_alpha)
+        return StateScore(pp, p1, None if sid < 0 else sid, store), roots, 0
     if kind == ATTACH:
-        j = base.index_of(arg)
-        n = base.ndata[j]
-        crp = base.crp + (lf(n) - lf(n - 1) if n >= 1 else 0.0)
-        lr = st.add(base.lr[j], v)  # log_r += value on the node itself (tree/tree_node.py:47-52)
-        lp, lp1 = _priors(prior, base.n_nodes, crp, base.mult, base.size, oprior, omarg)
-        handle = st.score(base.lr[:j] + (lr,) + base.lr[j + 1:])
-        return StateScore(lp, lp1, handle, st), base.roots, len(base.kids[j])
+        (score, nkids), = score_attach_all(base, store, dp, [arg], tree_dist)
+        return score, base.roots, nkids
     # NEW: children adopted in the set's iteration order, each new edge at the head of the adjacency list
-    order = [base.index_of(c) for c in arg]
-    kids = tuple(base.lr[j] for j in reversed(order))
-    lp_t = st.single_id[dp.idx]
-    lr = st.node(lp_t, kids) if kids else lp_t
-    taken = set(order)
-    keep = [j for j in range(len(base.roots)) if j not in taken]
-    R, k = len(base.roots), len(order)
-    mult = base.mult - lf(R) + lf(R - k + 1) + lf(k)
-    sizes = (1 + sum(base.size[j] for j in order),) + tuple(base.size[j] for j in keep)
-    lp, lp1 = _priors(prior, base.n_nodes + 1, base.crp, mult, sizes, oprior, omarg)
-    handle = st.score((lr,) + tuple(base.lr[j] for j in keep))
-    roots = (base.n_nodes,) + tuple(base.roots[j] for j in keep)
-    return StateScore(lp, lp1, handle, st), roots, k
+    arg = tuple(arg)
+    rec = base.score_new(store.book, t, arg, log_alpha)
+    if rec is None:
+        store._grow()
+        rec = base.score_new(store.book, t, arg, log_alpha)
+    pp, p1, sid, roots, k = rec
+    return StateScore(pp, p1, sid, store), roots, k
 
 
-def score_attach_all(base, dp, nodes, tree_dist):
-    """`score_edit(base, ATTACH, dp, node)` for every node of `nodes` with the shared prior terms computed once;
+def score_attach_all(base, store, dp, nodes, tree_dist):
+    """Scores of attaching `dp` to every root in `nodes`, the shared prior terms computed once;
     returns [(StateScore, number of children of the node)]."""
-    st = base.store
-    prior = tree_dist.prior
-    oprior = base.oprior
-    if dp.outlier_prob != 0:
-        oprior = oprior + dp.outlier_prob_not
-    n = base.n_nodes
-    head = n * prior.log_alpha
-    ways = 0
-    for z in base.size:
-        ways += (z - 1) * _log(z)
-    tail_p = -(n - 1) * _log(n + 1) - base.mult + (oprior + base.omarg)
-    tail_one = (-ways + prior._compute_r_term(len(base.size))) - base.mult + (oprior + base.omarg)
-    v = st.value_id[dp.idx]
-    lr_all = base.lr
-    out = []
-    for node in nodes:
-        j = base.index_of(node)
-        m = base.ndata[j]
-        crp = head + (base.crp + (lf(m) - lf(m - 1) if m >= 1 else 0.0))
-        lr = st.add(lr_all[j], v)
-        handle = st.score(lr_all[:j] + (lr,) + lr_all[j + 1:])
-        out.append((StateScore(crp + tail_p, crp + tail_one, handle, st), len(base.kids[j])))
-    return out
+    t = host_tuple(store, dp)
+    log_alpha = tree_dist.prior.log_alpha
+    recs = base.score_attach_all(store.book, t, nodes, log_alpha)
+    if recs is None:
+        store._grow()
+        recs = base.score_attach_all(store.book, t, nodes, log_alpha)
+    return [(StateScore(pp, p1, sid, store), nkids) for pp, p1, sid, nkids in recs]

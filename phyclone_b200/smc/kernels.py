@@ -13,7 +13,7 @@ import numpy as np
 
 from ..tree.tree import Tree
 from ..utils.math import cached_log_binomial_coefficient, discrete_rvs, log_binomial_coefficient, log_normalize
-from .forest_state import ATTACH, NEW, OUTLIER, ForestState, score_attach_all
+from .forest_state import ATTACH, NEW, OUTLIER, ForestState, ensure_tables, score_attach_all
 from .swarm import Particle, StateHolder, TreeHolder
 
 
@@ -250,18 +250,19 @@ class StateSemiAdaptedProposalDistribution(object):
         ph = parent_particle._holder if parent_particle is not None else None
         self._pholder = ph
         td = self.tree_dist
+        st = self._store = kernel.store
         trees = []
         if parent_particle is not None and len(parent_particle.tree_roots):
-            nodes = parent_particle.tree_roots
+            nodes = parent_particle.tree_roots.tolist()
             shared_roots = np.asarray(base_state.roots)  # attaching does not change the as-built root order
-            for node, (score, nkids) in zip(nodes, score_attach_all(base_state, data_point, nodes.tolist(), td)):
-                trees.append(StateHolder(ph, parent_state, base_state, ATTACH, data_point, node, td,
+            for node, (score, nkids) in zip(nodes, score_attach_all(base_state, st, data_point, nodes, td)):
+                trees.append(StateHolder(st, ph, parent_state, base_state, ATTACH, data_point, node, td,
                                          prescored=(score, nkids, shared_roots)))
         if kernel.outlier_proposal_prob > 0:
-            trees.append(StateHolder(ph, parent_state, base_state, OUTLIER, data_point, None, td))
+            trees.append(StateHolder(st, ph, parent_state, base_state, OUTLIER, data_point, None, td))
         self.parent_is_empty_tree = parent_particle is None or len(parent_particle.tree_roots) == 0
         if self.parent_is_empty_tree:
-            trees.append(StateHolder(ph, parent_state, base_state, NEW, data_point, frozenset(), td))
+            trees.append(StateHolder(st, ph, parent_state, base_state, NEW, data_point, frozenset(), td))
         else:
             self._cached_log_old_num_roots = np.log(len(parent_particle.tree_roots) + 1)
         self._curr_trees = trees
@@ -289,8 +290,8 @@ class StateSemiAdaptedProposalDistribution(object):
         from_dict; one holder per (parent value, data point, child set)."""
         key = (self._pholder.vkey, self.data_point.idx, children)
         return self.kernel._new_tree_cache.get(
-            key, lambda: StateHolder(self._pholder, self._pstate, self._pstate, NEW, self.data_point, children,
-                                     self.tree_dist))
+            key, lambda: StateHolder(self._store, self._pholder, self._pstate, self._pstate, NEW, self.data_point,
+                                     children, self.tree_dist))
 
 
 class SemiAdaptedKernel(Kernel):
@@ -307,6 +308,7 @@ class SemiAdaptedKernel(Kernel):
 
     def _make_proposal(self, data_point, parent_particle, parent_tree):
         if self.use_states:
+            ensure_tables(self.tree_dist.prior, self.store.T + 2)
             if parent_particle is None:
                 empty = ForestState.empty(self.store, data_point.grid_size)
                 return StateSemiAdaptedProposalDistribution(data_point, self, None, empty, empty)

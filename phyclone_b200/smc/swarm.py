@@ -86,16 +86,16 @@ class StateHolder(object):
                  "node_last_added_to", "num_children_on_node_that_matters", "outlier_node_name", "log_pdf", "_tstate",
                  "_thawed", "_store", "_grid_size", "_vkey")
 
-    def __init__(self, parent_holder, parent_state, base_state, kind, dp, arg, tree_dist, prescored=None):
+    def __init__(self, store, parent_holder, parent_state, base_state, kind, dp, arg, tree_dist, prescored=None):
         from .forest_state import NEW, OUTLIER, score_edit
 
         self.uid = next(_uid)
         self.kind, self.dp, self.arg = kind, dp, arg
         self._parent_holder = parent_holder
         self._parent_state = parent_state
-        self._store, self._grid_size = base_state.store, base_state.grid_size
+        self._store, self._grid_size = store, dp.grid_size
         if prescored is None:
-            self._score, roots, nkids = score_edit(base_state, kind, dp, arg, tree_dist)
+            self._score, roots, nkids = score_edit(base_state, store, kind, dp, arg, tree_dist)
             self.tree_roots = np.asarray(roots)
         else:  # (StateScore, children of the node, shared as-built roots array) from score_attach_all
             self._score, nkids, self.tree_roots = prescored
@@ -122,7 +122,9 @@ class StateHolder(object):
 
     def thawed_state(self):
         if self._tstate is None:
-            self._tstate = self._parent_state.extend(self.kind, self.dp, self.arg)
+            from .forest_state import extend
+
+            self._tstate = extend(self._parent_state, self._store, self.kind, self.dp, self.arg)
         return self._tstate
 
     @property

@@ -57,7 +57,7 @@ class TileStore:
         al.freeze()
         self._values_host = None
         self.upload_values(values)
-        self.book = load_hostmod().TileBook(al.permanent, self.arena.capacity)
+        self.book = load_hostmod().TileBook(al.permanent, self.arena.capacity, self.prior_id)
         self._stats = {"flushes": 0, "launches": 0, "d2h_bytes": 0, "flush_s": 0.0}
         self.reset()
 

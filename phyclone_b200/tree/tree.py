@@ -11,8 +11,12 @@ of batched launches.  Copying a tree copies a few small lists and dicts, never a
 from collections import defaultdict
 from itertools import chain
 
+from .._hostmod import load as _load_hostmod
 from ..utils.math import cached_log_factorial
 from .graph import SlotDiGraph
+
+_edge_hash = _load_hostmod().edge_hash  # the structure hash is shared with the extension's ForestState
+_data_hash = _load_hostmod().data_hash
 
 NO_TILE = -1
 
@@ -91,10 +95,10 @@ class Tree(object):
             s, d = g.esrc, g.edst
             for e in range(len(s)):
                 if s[e] >= 0:
-                    k ^= hash((e, s[e], d[e]))
+                    k ^= _edge_hash(e, s[e], d[e])
             for node, lst in self._data.items():
                 for pos, dp in enumerate(lst):
-                    k ^= hash((node, pos, dp.idx, "d"))
+                    k ^= _data_hash(node, pos, dp.idx)
             self._skey = k
         return (self._skey, self._last_node_added_to, self._graph.n_nodes)
 
@@ -288,7 +292,7 @@ class Tree(object):
             self._data[node] = old + tuple(data)
             if self._skey is not None:
                 for pos, dp in enumerate(data, len(old)):
-                    self._skey ^= hash((node, pos, dp.idx, "d"))
+                    self._skey ^= _data_hash(node, pos, dp.idx)
             self._pt_attach(node, data, len(old))
             self._absorb(i, data)
         return i
@@ -305,13 +309,13 @@ class Tree(object):
         k = self._skey
         e = g.add_edge(r, i)
         if k is not None:
-            k ^= hash((e, r, i))
+            k ^= _edge_hash(e, r, i)
         for child in children:
             ci = self._node_indices[child]
             g.remove_edge(r, ci)
             e = g.add_edge(i, ci)
             if k is not None:
-                k ^= hash((e, r, ci)) ^ hash((e, i, ci))  # the freed slot is the one re-used
+                k ^= _edge_hash(e, r, ci) ^ _edge_hash(e, i, ci)  # the freed slot is the one re-used
         self._skey = k
         pt = self._pt
         if pt is not None:
@@ -333,7 +337,7 @@ class Tree(object):
         old = self._data[node]
         self._data[node] = old + (data_point,)
         if self._skey is not None:
-            self._skey ^= hash((node, len(old), data_point.idx, "d"))
+            self._skey ^= _data_hash(node, len(old), data_point.idx)
         self._pt_attach(node, (data_point,), len(old))
         self._last_node_added_to = node
         if node != self._OUTLIER_NODE_NAME:
