@@ -197,7 +197,7 @@ def run_ours(args):
         return float(ms.item())
 
     # ---- timed region 1: inputs resident in HBM
-    store.arena.job_timing = []
+    store.arena.start_timing(1200 * args.steps + 2048)
     s0 = dict(chain.stats)
     launches0 = ops.launch_count()
     staged0 = store.arena.staged_bytes
@@ -205,7 +205,7 @@ def run_ours(args):
         ms = timed(args.steps)
     launches = ops.launch_count() - launches0
     s1 = dict(chain.stats)
-    job_timing, store.arena.job_timing = store.arena.job_timing, None
+    job_timing = store.arena.stop_timing()
     kernel_ms = sum(a.elapsed_time(b) for a, b, _, _ in job_timing)
     conv_pairs = sum(t[3] for t in job_timing)
     flop = conv_pairs * CFG["samples"] * CFG["grid"] * (CFG["grid"] + 1)  # 2 flop x S*G*(G+1)/2 FMA per pair conv
@@ -249,6 +249,12 @@ def run_ours(args):
         except Exception:  # noqa: BLE001
             pass
         ext = (s1["extensions"] - s0["extensions"]) * world
+        traffic, traffic_src = None, None
+        try:  # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture of this command
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_node_jobs_traffic.json")))
+            traffic, traffic_src = tj["dram_bytes_per_launch"], "profiles/r1_node_jobs_traffic.json (ncu --set full)"
+        except Exception:  # noqa: BLE001
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -262,7 +268,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "kernel": "node_jobs_kernel", "achieved": achieved / 1e12,
-                         "peak": fp64_peak / 1e12, "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": None,
+                         "peak": fp64_peak / 1e12, "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": traffic, "traffic_source": traffic_src,
                          "launches": len(job_timing), "avg_launch_us": 1e3 * kernel_ms / n_launch,
                          "flop_per_launch": flop / n_launch, "kernel_share_of_step": kernel_ms / ms,
                          "peak_source": "pcb_fp64_peak (dependent-DFMA-chain microbenchmark) measured in this run; "

@@ -156,6 +156,23 @@ int pcb_cluster_sum_host(const double* grids, const int64_t* cluster_off, int64_
 /* DataPoint.outlier_marginal_prob for K tiles.              data/base.py:31-37 */
 int pcb_outlier_marginal_host(const double* values, int64_t K, int32_t S, int32_t G, double* out);
 
+/* MAP cellular prevalences of B trees: the max-plus twin of the node fold with back-pointers.
+ *   process_trace/map.py:48-64 compute_max_likelihood, :67-93 compute_log_S (prefix max, ties to the earliest
+ *   index), :96-134 compute_log_D / _compute_log_D_n (max_j child[j] + D[i-j], ties to the largest j; D starts at 0),
+ *   :137-166 set_max_assignment (walk down from index G-1 of the tree's root).
+ * Nodes are numbered 0..n_nodes-1 over all trees; post_order[tree_off[t]..tree_off[t+1]) lists tree t's nodes
+ * children-first with its root last; child_idx[child_off[v]..child_off[v+1]) are v's children in fold order
+ * (ascending edge slot = the networkx successor order the reference folds in).
+ * Out: max_idx[n_nodes][S] (ccf = max_idx/(G-1), map.py:169-173) and, if not NULL, log_R_max[n_nodes][S][G].
+ * The _dev form takes device pointers and caller-provided scratch (d_choice [E][S][G], s_choice [N][S][G]). */
+int pcb_map_trees_host(const double* node_log_p, const int32_t* tree_off, const int32_t* post_order,
+                       const int32_t* child_off, const int32_t* child_idx, int64_t n_trees, int64_t n_nodes,
+                       int64_t n_edges, int32_t S, int32_t G, int32_t* max_idx, double* log_r_max);
+int pcb_map_trees_dev(const double* node_log_p, const int32_t* tree_off, const int32_t* post_order,
+                      const int32_t* child_off, const int32_t* child_idx, int64_t n_trees, int64_t n_nodes,
+                      int64_t n_edges, int32_t S, int32_t G, double* log_r_max, int32_t* d_choice, int32_t* s_choice,
+                      int32_t* max_idx, void* stream);
+
 /* ParticleSwarm.log_norm_const / log_weights / weights / ess.  smc/swarm/swarm.py:21-61 */
 int pcb_swarm_weights_host(const double* log_w, int64_t N, double* log_Z, double* log_W, double* W, double* ess);
 /* log_normalize + exp + renormalise per candidate segment.

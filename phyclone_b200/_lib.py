@@ -60,6 +60,8 @@ SIGNATURES = {
     "pcb_likelihood_grid_dev": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _i64, _i32, _i32, _i32, _i32, _f64, _P, _P]),
     "pcb_cluster_sum_host": (C.c_int, [_P, _P, _i64, _i32, _i32, _P]),
     "pcb_outlier_marginal_host": (C.c_int, [_P, _i64, _i32, _i32, _P]),
+    "pcb_map_trees_host": (C.c_int, [_P, _P, _P, _P, _P, _i64, _i64, _i64, _i32, _i32, _P, _P]),
+    "pcb_map_trees_dev": (C.c_int, [_P, _P, _P, _P, _P, _i64, _i64, _i64, _i32, _i32, _P, _P, _P, _P, _P]),
     "pcb_swarm_weights_host": (C.c_int, [_P, _i64, _P, _P, _P, _P]),
     "pcb_normalize_segments_host": (C.c_int, [_P, _P, _i64, _P, _P, _P]),
     "pcb_normalize_segments_dev": (C.c_int, [_P, _P, _i64, _P, _P, _P, _P, _P]),

@@ -544,6 +544,71 @@ int pcb_outlier_marginal_host(const double* values, int64_t K, int32_t S, int32_
   return PCB_OK;
 }
 
+// ---- MAP prevalences (max-plus fold with back-pointers) ---------------------------------------------------
+int pcb_map_trees_dev(const double* node_log_p, const int32_t* tree_off, const int32_t* post_order,
+                      const int32_t* child_off, const int32_t* child_idx, int64_t n_trees, int64_t n_nodes,
+                      int64_t n_edges, int32_t S, int32_t G, double* log_r_max, int32_t* d_choice, int32_t* s_choice,
+                      int32_t* max_idx, void* stream) {
+  if (n_trees <= 0 || n_nodes <= 0) return PCB_OK;
+  if (!node_log_p || !tree_off || !post_order || !child_off || !log_r_max || !s_choice || !max_idx ||
+      (n_edges > 0 && (!child_idx || !d_choice)))
+    return fail(PCB_ERR_ARG, "map_trees_dev: null pointer");
+  if (S < 1 || G < 1 || G > 4096) return fail(PCB_ERR_ARG, "map_trees_dev: need S >= 1 and 1 <= G <= 4096");
+  if (n_trees * S > 2147483647ll) return fail(PCB_ERR_ARG, "map_trees_dev: too many trees for one launch");
+  pcb::MapParams p{node_log_p, tree_off, post_order, child_off, child_idx, log_r_max, d_choice, s_choice, max_idx, S, G};
+  const int threads = std::min(1024, 32 * ((G + 31) / 32));
+  const size_t smem = (size_t)3 * G * 8;
+  if (smem > 48 * 1024)
+    PCB_CUDA(cudaFuncSetAttribute(pcb::map_trees_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  pcb::map_trees_kernel<<<(unsigned)(n_trees * S), threads, smem, (cudaStream_t)stream>>>(p);
+  PCB_LAUNCH_CHECK();
+  return PCB_OK;
+}
+
+int pcb_map_trees_host(const double* node_log_p, const int32_t* tree_off, const int32_t* post_order,
+                       const int32_t* child_off, const int32_t* child_idx, int64_t n_trees, int64_t n_nodes,
+                       int64_t n_edges, int32_t S, int32_t G, int32_t* max_idx, double* log_r_max) {
+  if (n_trees <= 0 || n_nodes <= 0) return PCB_OK;
+  if (!node_log_p || !tree_off || !post_order || !child_off || !max_idx || (n_edges > 0 && !child_idx))
+    return fail(PCB_ERR_ARG, "map_trees: null pointer");
+  // structure checks on the host copy: a malformed tree must not send the kernel out of bounds
+  if (tree_off[0] != 0 || tree_off[n_trees] != n_nodes || child_off[0] != 0 || child_off[n_nodes] != n_edges)
+    return fail(PCB_ERR_ARG, "map_trees: offsets do not cover the nodes / edges");
+  for (int64_t i = 0; i < n_nodes; ++i)
+    if (post_order[i] < 0 || post_order[i] >= n_nodes || child_off[i + 1] < child_off[i])
+      return fail(PCB_ERR_ARG, "map_trees: bad post-order entry or child offsets");
+  for (int64_t e = 0; e < n_edges; ++e)
+    if (child_idx[e] < 0 || child_idx[e] >= n_nodes) return fail(PCB_ERR_ARG, "map_trees: child index out of range");
+  HostScratch& hs = g_hs;
+  const size_t tile = (size_t)S * G;
+  const size_t n_int = (size_t)(n_trees + 1) + n_nodes + (n_nodes + 1) + std::max<int64_t>(n_edges, 1);
+  int rc;
+  if ((rc = hs.in.ensure(n_nodes * tile * 8))) return rc;
+  if ((rc = hs.out.ensure(n_nodes * tile * 8))) return rc;
+  if ((rc = hs.ids.ensure(n_int * 4))) return rc;
+  if ((rc = hs.jobs.ensure(std::max<int64_t>(n_edges, 1) * tile * 4))) return rc;
+  if ((rc = hs.kids.ensure(n_nodes * tile * 4))) return rc;
+  if ((rc = hs.misc.ensure((size_t)n_nodes * S * 4))) return rc;
+  int32_t* d_tree_off = hs.ids.as<int32_t>();
+  int32_t* d_post = d_tree_off + (n_trees + 1);
+  int32_t* d_child_off = d_post + n_nodes;
+  int32_t* d_child_idx = d_child_off + (n_nodes + 1);
+  PCB_CUDA(cudaMemcpyAsync(hs.in.p, node_log_p, n_nodes * tile * 8, cudaMemcpyHostToDevice, 0));
+  PCB_CUDA(cudaMemcpyAsync(d_tree_off, tree_off, (size_t)(n_trees + 1) * 4, cudaMemcpyHostToDevice, 0));
+  PCB_CUDA(cudaMemcpyAsync(d_post, post_order, (size_t)n_nodes * 4, cudaMemcpyHostToDevice, 0));
+  PCB_CUDA(cudaMemcpyAsync(d_child_off, child_off, (size_t)(n_nodes + 1) * 4, cudaMemcpyHostToDevice, 0));
+  if (n_edges > 0) PCB_CUDA(cudaMemcpyAsync(d_child_idx, child_idx, (size_t)n_edges * 4, cudaMemcpyHostToDevice, 0));
+  PCB_CUDA(cudaMemsetAsync(hs.misc.p, 0, (size_t)n_nodes * S * 4, 0));
+  if ((rc = pcb_map_trees_dev(hs.in.as<double>(), d_tree_off, d_post, d_child_off, d_child_idx, n_trees, n_nodes, n_edges,
+                              S, G, hs.out.as<double>(), hs.jobs.as<int32_t>(), hs.kids.as<int32_t>(),
+                              hs.misc.as<int32_t>(), nullptr)))
+    return rc;
+  PCB_CUDA(cudaMemcpyAsync(max_idx, hs.misc.p, (size_t)n_nodes * S * 4, cudaMemcpyDeviceToHost, 0));
+  if (log_r_max) PCB_CUDA(cudaMemcpyAsync(log_r_max, hs.out.p, n_nodes * tile * 8, cudaMemcpyDeviceToHost, 0));
+  PCB_CUDA(cudaStreamSynchronize(0));
+  return PCB_OK;
+}
+
 int pcb_normalize_segments_dev(const double* log_p, const int64_t* seg_off_dev, int64_t U, double* log_q, double* q,
                                 double* log_norm, double* ess, void* stream) {
   if (U <= 0) return PCB_OK;

@@ -686,6 +686,101 @@ __global__ void resample_kernel(const double* __restrict__ W, long long N, const
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// MAP assignment of cellular prevalences: the max-plus (Viterbi) twin of the node fold, with back-pointers.
+// Reference: process_trace/map.py:48-170 (compute_max_likelihood, compute_log_S, compute_log_D,
+// _compute_log_D_n, set_max_assignment), pure-Python loops there.
+// Rows (samples) never interact, so ONE CTA walks a whole tree for one row: bottom-up over the post-order
+// (D <- max_j child[j] + D[i-j] per child, ties to the LARGEST j as the reference's `>=` scan; then the prefix
+// max with ties to the EARLIEST index, its strict `>`), intermediate rows in global memory (L2-resident),
+// then thread 0 walks back down from index G-1 of the dummy root.
+// ---------------------------------------------------------------------------------------------------------
+struct MapParams {
+  const double* log_p;       // [N][S][G] node log_p tiles
+  const int* tree_off;       // [B+1] node range of each tree inside post_order
+  const int* post_order;     // [N]   node ids, children before parents, the tree's root last
+  const int* child_off;      // [N+1]
+  const int* child_idx;      // [E]   children of each node in fold order
+  double* log_r_max;         // [N][S][G] out
+  int* d_choice;             // [E][S][G] scratch: argmax j of each fold step
+  int* s_choice;             // [N][S][G] scratch: argmax of the prefix max
+  int* max_idx;              // [N][S] out
+  int S, G;
+};
+
+__global__ void map_trees_kernel(MapParams p) {
+  extern __shared__ double map_smem[];
+  const int G = p.G, S = p.S;
+  double* A = map_smem;       // child's log_R_max row
+  double* D0 = A + G;         // running D, double-buffered
+  double* D1 = D0 + G;
+  const int t = blockIdx.x / S, s = blockIdx.x % S;
+  const int k0 = p.tree_off[t], k1 = p.tree_off[t + 1];
+  const double ninf = -__longlong_as_double(0x7ff0000000000000ll);
+  for (int k = k0; k < k1; ++k) {
+    const int v = p.post_order[k];
+    const int c0 = p.child_off[v], c1 = p.child_off[v + 1];
+    const size_t row_v = ((size_t)v * S + s) * G;
+    if (c0 == c1) {
+      for (int i = threadIdx.x; i < G; i += blockDim.x) p.log_r_max[row_v + i] = p.log_p[row_v + i];
+      __syncthreads();
+      continue;
+    }
+    double* Dp = D0;
+    double* Dn = D1;
+    for (int i = threadIdx.x; i < G; i += blockDim.x) Dp[i] = 0.0;
+    for (int e = c0; e < c1; ++e) {
+      const size_t row_c = ((size_t)p.child_idx[e] * S + s) * G;
+      for (int i = threadIdx.x; i < G; i += blockDim.x) A[i] = p.log_r_max[row_c + i];
+      __syncthreads();
+      const size_t row_e = ((size_t)e * S + s) * G;
+      for (int i = threadIdx.x; i < G; i += blockDim.x) {
+        double best = ninf;
+        int ch = 0;
+        for (int j = 0; j <= i; ++j) {
+          const double val = A[j] + Dp[i - j];
+          if (val >= best) {
+            best = val;
+            ch = j;
+          }
+        }
+        Dn[i] = best;
+        p.d_choice[row_e + i] = ch;
+      }
+      __syncthreads();
+      double* tmp = Dp;
+      Dp = Dn;
+      Dn = tmp;
+    }
+    for (int i = threadIdx.x; i < G; i += blockDim.x) {
+      double run = Dp[0];
+      int ch = 0;
+      for (int j = 1; j <= i; ++j)
+        if (Dp[j] > run) {
+          run = Dp[j];
+          ch = j;
+        }
+      p.s_choice[row_v + i] = ch;
+      p.log_r_max[row_v + i] = p.log_p[row_v + i] + run;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && k1 > k0) {
+    p.max_idx[(size_t)p.post_order[k1 - 1] * S + s] = G - 1;
+    for (int k = k1 - 1; k >= k0; --k) {
+      const int v = p.post_order[k];
+      const int c0 = p.child_off[v], c1 = p.child_off[v + 1];
+      if (c0 == c1) continue;
+      int tot = p.s_choice[((size_t)v * S + s) * G + p.max_idx[(size_t)v * S + s]];
+      for (int e = c1 - 1; e >= c0; --e) {
+        const int m = p.d_choice[((size_t)e * S + s) * G + tot];
+        p.max_idx[(size_t)p.child_idx[e] * S + s] = m;
+        tot -= m;
+      }
+    }
+  }
+}
+
 // dependent DFMA chains: the measured FP64 roofline denominator
 __global__ void fp64_peak_kernel(double* out, int iters, double seed) {
   double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,

@@ -66,6 +66,27 @@ class DeviceArena:
         self._pinned_vals = self._staged_vals = None
         self.staged_bytes = 0  # host->device bytes of job tables / id lists so far
         self.job_timing = None  # set to a list to record (start_event, end_event, n_jobs, conv_pairs) per launch
+        self._event_pool = []
+
+    def start_timing(self, n_events=8192):
+        """Time every node-jobs launch with a CUDA event pair from a pre-created pool (creating events inside the
+        measured region would cost more than the launches they time)."""
+        stream = torch.cuda.current_stream(self.device)
+        while len(self._event_pool) < n_events:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(stream)  # forces creation
+            self._event_pool.append(e)
+        self.job_timing = []
+
+    def stop_timing(self):
+        timing, self.job_timing = self.job_timing, None
+        return timing
+
+    def _event_pair(self):
+        pool = self._event_pool
+        if len(pool) >= 2:
+            return pool.pop(), pool.pop()
+        return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def grow(self, new_capacity):
         """Enlarge the arena in place (tile ids stay valid): new zero-filled tensors, old content copied over."""
@@ -140,6 +161,31 @@ class DeviceArena:
         _lib.check(self.lib.pcb_arena_export_dev(C.byref(self.c), ids_dev.data_ptr(), n, out.data_ptr(), self._stream()))
         return out
 
+    def map_trees(self, lp_ids, tree_off, post_order, child_off, child_idx):
+        """MAP prevalence indices (process_trace/map.py:48-166) of a batch of trees whose node log_p tiles live in
+        this arena: tiles are gathered on the device, one launch walks every (tree, sample) pair, only the
+        [N,S] index table comes back.  Arguments as `ops.map_trees`, with tile ids instead of dense log_p."""
+        n, n_trees, n_edges = len(lp_ids), len(tree_off) - 1, len(child_idx)
+        if n == 0:
+            return np.zeros((0, self.S), dtype=np.int32)
+        with torch.cuda.device(self.device):
+            dense = self.export_tiles(lp_ids)
+            ints = np.concatenate([np.asarray(x, dtype=np.int32).reshape(-1)
+                                   for x in (tree_off, post_order, child_off, child_idx)])
+            d = self._to_dev_i32(ints, "map")
+            p_tree = d.data_ptr()
+            p_post = p_tree + 4 * (n_trees + 1)
+            p_coff = p_post + 4 * n
+            p_cidx = p_coff + 4 * (n + 1)
+            r_max = torch.empty_like(dense)
+            d_choice = torch.empty((max(n_edges, 1), self.S, self.G), dtype=torch.int32, device=self.device)
+            s_choice = torch.empty((n, self.S, self.G), dtype=torch.int32, device=self.device)
+            max_idx = torch.zeros((n, self.S), dtype=torch.int32, device=self.device)
+            _lib.check(self.lib.pcb_map_trees_dev(dense.data_ptr(), p_tree, p_post, p_coff, p_cidx, n_trees, n, n_edges,
+                                                  self.S, self.G, r_max.data_ptr(), d_choice.data_ptr(),
+                                                  s_choice.data_ptr(), max_idx.data_ptr(), self._stream()))
+            return max_idx.cpu().numpy()
+
     def tile_add(self, a_ids, b_ids, out_ids, addend=0.0, b_sign=1.0):
         """out = a (+/- b) + addend in the log domain; refreshes lin / rmax of `out`."""
         n = len(out_ids)
@@ -174,7 +220,7 @@ class DeviceArena:
             pl, pt = rows[0].data_ptr(), rows[1].data_ptr()
         timing = self.job_timing
         if timing is not None:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0, e1 = self._event_pair()
             e0.record(torch.cuda.current_stream(self.device))
         _lib.check(
             self.lib.pcb_node_jobs_dev(C.byref(self.c), base, base + 4 * n * JOB_INTS, n, self.prior, pl, pt, self._stream())
@@ -211,7 +257,7 @@ class DeviceArena:
                 _, off, n, n_kids, conv_pairs = rec
                 p0 = base + 4 * off
                 if timing is not None:
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0, e1 = self._event_pair()
                     e0.record(stream_obj)
                 _lib.check(lib.pcb_node_jobs_dev(arena_ref, p0, p0 + 4 * n * JOB_INTS, n, prior, pl, pt, stream))
                 if timing is not None:

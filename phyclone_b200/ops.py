@@ -149,6 +149,23 @@ def outlier_marginal(values):
     return out[0] if single else out
 
 
+def map_trees(node_log_p, tree_off, post_order, child_off, child_idx, want_log_r_max=False):
+    """MAP prevalence indices of a batch of trees (reference process_trace/map.py:48-166).
+    node_log_p [N,S,G]; tree_off [B+1]; post_order [N] (children first, each tree's root last); child_off [N+1];
+    child_idx [E] in fold order.  Returns max_idx [N,S] int32 (and log_R_max [N,S,G] if asked)."""
+    lib = _lib.require_device()
+    lp = _f64(node_log_p)
+    N, S, G = lp.shape
+    to, po, co, ci = (np.ascontiguousarray(x, dtype=np.int32) for x in (tree_off, post_order, child_off, child_idx))
+    if len(po) != N or len(co) != N + 1:
+        raise ValueError("map_trees: post_order / child_off do not match the number of nodes")
+    max_idx = np.zeros((N, S), dtype=np.int32)
+    lrm = np.empty((N, S, G)) if want_log_r_max else None
+    _lib.check(lib.pcb_map_trees_host(_ptr(lp), _ptr(to), _ptr(po), _ptr(co), _ptr(ci) if len(ci) else None,
+                                      len(to) - 1, N, len(ci), S, G, _ptr(max_idx), None if lrm is None else _ptr(lrm)))
+    return (max_idx, lrm) if want_log_r_max else max_idx
+
+
 def swarm_weights(log_w):
     """(log_Z, log_W, W, ess) of `ParticleSwarm` (reference smc/swarm/swarm.py:21-61)."""
     lib = _lib.require_device()

@@ -42,6 +42,18 @@ class FakeArena:
                 v = v + b_sign * self.tiles[int(b_ids[k])]
             self.tiles[int(o)] = v + addend if addend != 0.0 else v + 0.0
 
+    def map_trees(self, lp_ids, tree_off, post_order, child_off, child_idx):
+        from oracle import map as omap
+
+        lp = self.export_tiles(lp_ids)
+        out = np.zeros((len(lp_ids), self.S), dtype=np.int32)
+        kids = [list(child_idx[child_off[v]:child_off[v + 1]]) for v in range(len(lp_ids))]
+        for t in range(len(tree_off) - 1):
+            order = list(post_order[tree_off[t]:tree_off[t + 1]])
+            idx, _ = omap.map_tree(lp, kids, order)
+            out[order] = idx[order]
+        return out
+
     def run_plan(self, packed, plan, n_slots):
         out = np.zeros((2, max(n_slots, 1)))
         for rec in plan:

@@ -1,71 +1,41 @@
-"""TEST/PROFILING-ONLY tile store: no arithmetic at all, scores are a cheap deterministic function of the
-operand ids.  Lets the host bookkeeping of the product sampler be profiled on a CPU box."""
+"""TEST/PROFILING-ONLY executor: no tile arithmetic at all, scores are a cheap deterministic function of the slot.
+Lets the host bookkeeping of the product sampler (Python + the _pcbhost extension) be profiled on a CPU box."""
 
 import numpy as np
 
+from phyclone_b200.engine import TileAllocator
+from phyclone_b200.tiles import TileStore
 
-class NullTileStore:
-    def __init__(self, values):
-        T, S, G = values.shape
-        self.T, self.S, self.G = T, S, G
+
+class NullArena:
+    def __init__(self, S, G, capacity):
+        self.S, self.G = S, G
+        self.capacity = int(capacity)
+        self.alloc = TileAllocator(self.capacity)
         self.prior = -float(np.log(G))
-        self.value_id = list(range(T))
-        self.single_id = list(range(T, 2 * T))
-        self.prior_id = 2 * T
-        self._perm = 2 * T + 1
-        self.base = [float(-200.0 - 3.0 * (i % 7)) for i in range(T)]
-        self.stats = {"flushes": 0, "adds": 0, "node_jobs": 0, "scores": 0, "launches": 0, "memo_hits": 0,
-                      "d2h_bytes": 0, "conv_pairs": 0}
-        self.reset()
+        self.staged_bytes = 0
+        self.job_timing = None
+        self._n = 0
 
-    def reset(self):
-        self._top = self._perm
-        self._memo = {}
-        self._score = {}
-        self._w = {}
+    def grow(self, new_capacity):
+        self.capacity = self.alloc.capacity = int(new_capacity)
 
-    def _weight(self, t):
-        if t < self.T:
-            return self.base[t]
-        if t < 2 * self.T:
-            return self.base[t - self.T]
-        return self._w.get(t, 0.0)
+    def import_tiles(self, dense, ids):
+        pass
 
-    def _new(self, key, w):
-        t = self._top
-        self._top += 1
-        self._memo[key] = t
-        self._w[t] = w
-        return t
+    def upload_dense(self, values, ids):
+        return np.asarray(values).nbytes
 
-    def add(self, a, b):
-        key = ("a", a, b)
-        t = self._memo.get(key)
-        return t if t is not None else self._new(key, self._weight(a) + self._weight(b))
+    def tile_add(self, *a, **k):
+        pass
 
-    def sub(self, a, b):
-        key = ("s", a, b)
-        t = self._memo.get(key)
-        return t if t is not None else self._new(key, self._weight(a) - self._weight(b))
+    def run_plan(self, packed, plan, n_slots):
+        if not n_slots:
+            return None
+        self._n += 1
+        base = -200.0 - 3.0 * ((np.arange(n_slots) * 7 + self._n) % 11)
+        return np.ascontiguousarray(np.stack([base, base - 3.0]))
 
-    def node(self, base, kids):
-        key = ("n", base, kids)
-        t = self._memo.get(key)
-        if t is None:
-            self.stats["node_jobs"] += 1
-            t = self._new(key, self._weight(base) + sum(self._weight(k) for k in kids) - 2.0 * len(kids))
-        return t
 
-    def score(self, kids):
-        h = self._score.get(kids)
-        if h is None:
-            w = sum(self._weight(k) for k in kids) - 1.5 * len(kids)
-            h = self._score[kids] = [0, (w, w - 3.0)]
-            self.stats["scores"] += 1
-        return h
-
-    def value(self, handle):
-        return handle[1]
-
-    def flush(self):
-        self.stats["flushes"] += 1
+def NullTileStore(values):
+    return TileStore(values, arena_factory=NullArena)
