@@ -173,6 +173,10 @@ int pcb_map_trees_dev(const double* node_log_p, const int32_t* tree_off, const i
                       int64_t n_edges, int32_t S, int32_t G, double* log_r_max, int32_t* d_choice, int32_t* s_choice,
                       int32_t* max_idx, void* stream);
 
+/* conv_log for B pairs of length-n vectors: per-output max-shifted direct log-space convolution, no floor.
+ *                                                           utils/math.py:212-238 (used by the reference's tests) */
+int pcb_conv_log_host(const double* log_x, const double* log_y, double* out, int64_t B, int32_t n);
+
 /* ParticleSwarm.log_norm_const / log_weights / weights / ess.  smc/swarm/swarm.py:21-61 */
 int pcb_swarm_weights_host(const double* log_w, int64_t N, double* log_Z, double* log_W, double* W, double* ess);
 /* log_normalize + exp + renormalise per candidate segment.

@@ -276,3 +276,23 @@ def ancestors_from_uniforms(W, uniforms):
     cdf = np.cumsum(np.asarray(W, dtype=np.float64))
     cdf[-1] = np.inf
     return np.searchsorted(cdf, np.asarray(uniforms, dtype=np.float64), side="right").astype(np.int64)
+
+
+def conv_log(log_x, log_y):
+    """utils/math.py:212-238: out[k] = LSE_{j<=k}(x[j] + y[k-j]) with a per-output max shift, no floor."""
+    n = len(log_x)
+    out = np.empty(n)
+    for k in range(n):
+        v = log_x[: k + 1] + log_y[k::-1]
+        m = v.max()
+        acc = 0.0
+        for t in np.exp(v - m):
+            acc += t
+        out[k] = np.log(acc) + m
+    return out
+
+
+def non_log_conv(child_log_r, prev_log_d):
+    """utils/math.py:266-282: conv_pair for one row; np.convolve(R, D) there is np.convolve(x2, x1) of
+    conv_pair(c1=D, c2=R), including the order in which the two maxima are added back."""
+    return conv_pair(np.asarray(prev_log_d)[None, :], np.asarray(child_log_r)[None, :])[0]

@@ -62,6 +62,7 @@ SIGNATURES = {
     "pcb_outlier_marginal_host": (C.c_int, [_P, _i64, _i32, _i32, _P]),
     "pcb_map_trees_host": (C.c_int, [_P, _P, _P, _P, _P, _i64, _i64, _i64, _i32, _i32, _P, _P]),
     "pcb_map_trees_dev": (C.c_int, [_P, _P, _P, _P, _P, _i64, _i64, _i64, _i32, _i32, _P, _P, _P, _P, _P]),
+    "pcb_conv_log_host": (C.c_int, [_P, _P, _P, _i64, _i32]),
     "pcb_swarm_weights_host": (C.c_int, [_P, _i64, _P, _P, _P, _P]),
     "pcb_normalize_segments_host": (C.c_int, [_P, _P, _i64, _P, _P, _P]),
     "pcb_normalize_segments_dev": (C.c_int, [_P, _P, _i64, _P, _P, _P, _P, _P]),

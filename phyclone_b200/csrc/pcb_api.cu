@@ -609,6 +609,26 @@ int pcb_map_trees_host(const double* node_log_p, const int32_t* tree_off, const 
   return PCB_OK;
 }
 
+int pcb_conv_log_host(const double* log_x, const double* log_y, double* out, int64_t B, int32_t n) {
+  if (B <= 0 || n <= 0) return PCB_OK;
+  if (!log_x || !log_y || !out) return fail(PCB_ERR_ARG, "conv_log: null pointer");
+  HostScratch& hs = g_hs;
+  const size_t bytes = (size_t)B * n * 8;
+  int rc;
+  if ((rc = hs.in.ensure(2 * bytes))) return rc;
+  if ((rc = hs.out.ensure(bytes))) return rc;
+  double* dx = hs.in.as<double>();
+  double* dy = dx + (size_t)B * n;
+  PCB_CUDA(cudaMemcpyAsync(dx, log_x, bytes, cudaMemcpyHostToDevice, 0));
+  PCB_CUDA(cudaMemcpyAsync(dy, log_y, bytes, cudaMemcpyHostToDevice, 0));
+  const long long total = (long long)B * n;
+  pcb::conv_log_kernel<<<(unsigned)((total + 127) / 128), 128>>>(dx, dy, hs.out.as<double>(), B, n);
+  PCB_LAUNCH_CHECK();
+  PCB_CUDA(cudaMemcpyAsync(out, hs.out.p, bytes, cudaMemcpyDeviceToHost, 0));
+  PCB_CUDA(cudaStreamSynchronize(0));
+  return PCB_OK;
+}
+
 int pcb_normalize_segments_dev(const double* log_p, const int64_t* seg_off_dev, int64_t U, double* log_q, double* q,
                                 double* log_norm, double* ess, void* stream) {
   if (U <= 0) return PCB_OK;

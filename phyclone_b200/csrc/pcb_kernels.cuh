@@ -781,6 +781,23 @@ __global__ void map_trees_kernel(MapParams p) {
   }
 }
 
+// conv_log (utils/math.py:212-238): out[k] = log sum_{j<=k} exp(x[j] + y[k-j] - max_j) + max_j, the per-OUTPUT
+// max-shifted direct convolution (no floor).  The reference uses it in its tests only; one thread per output,
+// terms summed in the reference's order.
+__global__ void conv_log_kernel(const double* x, const double* y, double* out, long long B, int n) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * n) return;
+  const long long b = t / n;
+  const int k = (int)(t % n);
+  const double* xr = x + b * n;
+  const double* yr = y + b * n;
+  double m = -__longlong_as_double(0x7ff0000000000000ll);
+  for (int j = 0; j <= k; ++j) m = fmax(m, xr[j] + yr[k - j]);
+  double acc = 0.0;
+  for (int j = 0; j <= k; ++j) acc += exp(xr[j] + yr[k - j] - m);
+  out[t] = log(acc) + m;
+}
+
 // dependent DFMA chains: the measured FP64 roofline denominator
 __global__ void fp64_peak_kernel(double* out, int iters, double seed) {
   double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,

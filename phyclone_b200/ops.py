@@ -166,6 +166,19 @@ def map_trees(node_log_p, tree_off, post_order, child_off, child_idx, want_log_r
     return (max_idx, lrm) if want_log_r_max else max_idx
 
 
+def conv_log(log_x, log_y):
+    """`conv_log` (reference utils/math.py:212-238) for [n] or [B,n] vectors."""
+    lib = _lib.require_device()
+    x, y = _f64(log_x), _f64(log_y)
+    if x.shape != y.shape:
+        raise ValueError("conv_log: shape mismatch")
+    single = x.ndim == 1
+    a, b = (x[None], y[None]) if single else (x, y)
+    out = np.empty_like(a)
+    _lib.check(lib.pcb_conv_log_host(_ptr(a), _ptr(b), _ptr(out), a.shape[0], a.shape[1]))
+    return out[0] if single else out
+
+
 def swarm_weights(log_w):
     """(log_Z, log_W, W, ess) of `ParticleSwarm` (reference smc/swarm/swarm.py:21-61)."""
     lib = _lib.require_device()

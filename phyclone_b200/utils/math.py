@@ -72,3 +72,33 @@ def discrete_rvs(p, rng):
     """utils/math.py:19-21"""
     p = p / np.sum(p)
     return rng.multinomial(1, p).argmax()
+
+
+def conv_log(log_x, log_y, ans=None):
+    """utils/math.py:212-238: direct log-space convolution with a per-output max shift (no floor); device kernel.
+    `ans`, if given, is filled in place like the reference's output argument."""
+    from .. import ops
+
+    out = ops.conv_log(log_x, log_y)
+    if ans is None:
+        return out
+    ans[...] = out
+    return ans
+
+
+def fft_convolve_two_children(child_1, child_2):
+    """utils/math.py:241-263: the reference's FFT evaluation of the `_np_conv_dims` contract (per-row max shift,
+    truncation to G terms, `<= 0 -> 1e-100` floor) for G >= 1000.  Here the same contract is evaluated by the
+    direct-sum kernel, i.e. without the FFT's round-off noise; G <= 1088."""
+    from .. import ops
+
+    return ops.np_conv_dims(child_1, child_2)
+
+
+def non_log_conv(child_log_R, prev_log_D_n):
+    """utils/math.py:266-282: the 1-D form of `_np_conv_dims`."""
+    from .. import ops
+
+    a = np.asarray(child_log_R, dtype=np.float64)
+    b = np.asarray(prev_log_D_n, dtype=np.float64)
+    return ops.np_conv_dims(b[None, None, :], a[None, None, :])[0, 0]  # np.convolve(R, D): R is the second operand
