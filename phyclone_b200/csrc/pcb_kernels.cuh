@@ -56,6 +56,13 @@ struct JobKernelParams {
 // old window and Y[i-p+L] once it has entered, so no register is ever copied; X[L-1-p] dies
 // after step p and is refilled at once with the NEXT body's entering element, which makes X
 // the "Y" of the next body: the caller alternates step(X,Y) / step(Y,X).
+// predicated select that the compiler cannot turn into a branch
+__device__ __forceinline__ double select_f64(bool c, double a, double b) {
+  double d;
+  asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\tselp.f64 %0, %1, %2, p;\n\t}" : "=d"(d) : "d"(a), "d"(b), "r"((int)c));
+  return d;
+}
+
 template <int L>
 struct ConvLane {
   const double* a;
@@ -100,6 +107,23 @@ __device__ __forceinline__ void conv_step(ConvLane<L>& st, double (&X)[L], doubl
   }
 }
 
+// Body number Q is, for every lane that still runs, the LAST body of its second strip: the multipliers are
+// b[k2..k2+L) and the window has slid down to a[i-p], so the entering elements (Y) are all lead zeros.  Only the
+// i >= p triangle contributes and nothing is refilled: L(L-1)/2 DFMAs and 2L loads less, warp-uniformly.
+// (The last body of a lane's FIRST strip is triangular too, but it falls on body number u, which differs from
+// lane to lane, so skipping it there would only add divergence.)
+template <int L>
+__device__ __forceinline__ void conv_step_last(const ConvLane<L>& st, const double (&X)[L], const double (&bv)[L],
+                                               double (&y2)[L]) {
+  if (!st.active) return;
+#pragma unroll
+  for (int p = 0; p < L; ++p) {
+    const double bj = bv[p];
+#pragma unroll
+    for (int i = p; i < L; ++i) y2[i] = fma(bj, X[i - p], y2[i]);
+  }
+}
+
 // Raw sums come back in registers: y1 = strip u, y2 = strip Q-1-u (y2 only, for the middle
 // unit of an odd Q).
 template <int L>
@@ -124,9 +148,17 @@ __device__ __forceinline__ void conv_unit(const double* __restrict__ a, const do
     Y[L - 1 - i] = active ? a[k0 - 1 - i] : 0.0;
     bv[i] = active ? b[i] : 0.0;
   }
-  for (int it = 0; it <= Q; it += 2) {  // warp-uniform; Q+1 bodies per lane (one spare when Q is even)
+  // warp-uniform: bodies 0..Q-1 in full, body Q as a triangle
+  int it = 0;
+  for (; it + 2 <= Q; it += 2) {
     conv_step<L>(st, X, Y, bv, y1, y2);
     conv_step<L>(st, Y, X, bv, y1, y2);
+  }
+  if (it < Q) {  // Q odd: one more full body, then the triangle reads the window that body left in Y
+    conv_step<L>(st, X, Y, bv, y1, y2);
+    conv_step_last<L>(st, Y, bv, y2);
+  } else {
+    conv_step_last<L>(st, X, bv, y2);
   }
 }
 
@@ -259,10 +291,11 @@ __global__ void __launch_bounds__(32) node_jobs_kernel(const JobKernelParams p) 
     // on pad columns, which must stay zero anyway.
     const int nv2 = lane_ok ? min(L, G - k2) : 0;
     const bool v1 = lane_ok && two;
+    const double fl1 = v1 ? kFloor : 0.0;  // a whole strip of an idle lane stores zeros
 #pragma unroll
     for (int i = 0; i < L; ++i) {
-      y2[i] = (i < nv2) ? ((y2[i] > 0.0) ? y2[i] : kFloor) : 0.0;
-      y1[i] = v1 ? ((y1[i] > 0.0) ? y1[i] : kFloor) : 0.0;
+      y2[i] = select_f64(y2[i] > 0.0 && i < nv2, y2[i], (i < nv2) ? kFloor : 0.0);
+      y1[i] = select_f64(y1[i] > 0.0 && v1, y1[i], fl1);
     }
     double mx[L];
 #pragma unroll
