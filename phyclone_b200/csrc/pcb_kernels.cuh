@@ -87,8 +87,16 @@ __device__ __forceinline__ void conv_step(ConvLane<L>& st, double (&X)[L], doubl
   }
   st.bn += L;
   st.an -= L;
-  if (--st.left == 0) {
-    if (st.second) {  // switch to the lane's second strip; Y is the window of the next step
+  --st.left;
+  if (st.second) {
+    // The strip switch happens at a different body for every lane of a row, so the warp runs this block once per
+    // lane: keep it small.  One body before the switch the refill pointers are redirected (predicated, no branch)
+    // so that the regular in-body refills already fetch the second strip's entering elements and b[0..L);
+    // at the switch only the new window is loaded.
+    const bool redirect = st.left == 1;
+    st.an = redirect ? st.a + st.k2 - 1 : st.an;
+    st.bn = redirect ? st.b : st.bn;
+    if (st.left == 0) {  // Y is the window of the next step, X already holds its entering elements
       st.second = false;
       st.left = st.k2 / L + 1;
 #pragma unroll
@@ -96,14 +104,12 @@ __device__ __forceinline__ void conv_step(ConvLane<L>& st, double (&X)[L], doubl
         y1[i] = y2[i];
         y2[i] = 0.0;
         Y[i] = st.a[st.k2 + i];
-        X[L - 1 - i] = st.a[st.k2 - 1 - i];
-        bv[i] = st.b[i];
       }
       st.an = st.a + st.k2 - 1 - L;
       st.bn = st.b + L;
-    } else {
-      st.active = false;
     }
+  } else if (st.left == 0) {
+    st.active = false;
   }
 }
 
@@ -137,8 +143,9 @@ __device__ __forceinline__ void conv_unit(const double* __restrict__ a, const do
   st.left = u + 1;
   st.active = active;
   st.second = st.k2 != k0;
-  st.an = a + k0 - 1 - L;
-  st.bn = b + L;
+  const bool redirect0 = st.second && st.left == 1;  // the first strip is a single body: refill for the second
+  st.an = redirect0 ? a + st.k2 - 1 : a + k0 - 1 - L;
+  st.bn = redirect0 ? b : b + L;
   double X[L], Y[L], bv[L];
 #pragma unroll
   for (int i = 0; i < L; ++i) {
