@@ -156,6 +156,17 @@ int pcb_cluster_sum_host(const double* grids, const int64_t* cluster_off, int64_
 /* DataPoint.outlier_marginal_prob for K tiles.              data/base.py:31-37 */
 int pcb_outlier_marginal_host(const double* values, int64_t K, int32_t S, int32_t G, double* out);
 
+/* One flush of the lazily recorded tile algebra (phyclone_b200/tiles.py) in a single call: copies the packed id lists /
+ * job tables from pinned host memory, runs the plan's launches in dependency order on `stream` -- tile adds
+ * (tree/tree_node.py:42-59) and node jobs (tree/tree_node.py:61-71, tree/distributions.py:197-200) -- reduces the score
+ * rows over samples and copies [2][n_slots] sums to `sums_host`; synchronises the stream only if n_slots > 0.
+ * plan: n_rec x 6 int32 {kind 0=add | 1=jobs, offset into packed, n, n_kids, negate, 0}; add ids are laid out
+ * [a | b | out], a job table (n x 8 int32) is followed by its n_kids child ids.  events: NULL or 2 CUDA events per
+ * record, recorded around the node-jobs launches. */
+int pcb_run_plan_dev(const pcb_arena* arena, const int32_t* packed_host, int64_t n_ints, int32_t* packed_dev,
+                     const int32_t* plan, int32_t n_rec, double prior, double* rows_lse, double* rows_last,
+                     int64_t n_slots, double* sums_dev, double* sums_host, void* const* events, void* stream);
+
 /* MAP cellular prevalences of B trees: the max-plus twin of the node fold with back-pointers.
  *   process_trace/map.py:48-64 compute_max_likelihood, :67-93 compute_log_S (prefix max, ties to the earliest
  *   index), :96-134 compute_log_D / _compute_log_D_n (max_j child[j] + D[i-j], ties to the largest j; D starts at 0),

@@ -365,6 +365,44 @@ int pcb_reduce_rows_dev(const double* rows_dev, int64_t n_slots, int32_t S, doub
   return PCB_OK;
 }
 
+// One flush of the host's tile store in ONE call: stage the packed id lists / job tables (pinned host -> device),
+// run every launch of the plan in dependency order, reduce the score rows and copy the sums back.
+// plan: n_rec records of 6 int32: {kind (0 = tile add, 1 = node jobs), offset into packed, n, n_kids, negate, 0}.
+// events: NULL, or 2 CUDA events per record (recorded around node-jobs launches only: the bench's kernel timing).
+int pcb_run_plan_dev(const pcb_arena* a, const int32_t* packed_host, int64_t n_ints, int32_t* packed_dev,
+                     const int32_t* plan, int32_t n_rec, double prior, double* rows_lse, double* rows_last,
+                     int64_t n_slots, double* sums_dev, double* sums_host, void* const* events, void* stream) {
+  int rc = check_arena(a);
+  if (rc) return rc;
+  if (n_rec <= 0) return PCB_OK;
+  if (!packed_host || !packed_dev || !plan) return fail(PCB_ERR_ARG, "run_plan: null pointer");
+  if (n_slots > 0 && (!rows_lse || !rows_last || !sums_dev || !sums_host))
+    return fail(PCB_ERR_ARG, "run_plan: score buffers missing");
+  cudaStream_t st = (cudaStream_t)stream;
+  PCB_CUDA(cudaMemcpyAsync(packed_dev, packed_host, (size_t)n_ints * 4, cudaMemcpyHostToDevice, st));
+  for (int r = 0; r < n_rec; ++r) {
+    const int32_t* rec = plan + 6 * r;
+    const int64_t off = rec[1], n = rec[2];
+    if (off < 0 || n < 0 || off + (rec[0] == 0 ? 3 * n : 8 * n + rec[3]) > n_ints)
+      return fail(PCB_ERR_ARG, "run_plan: record outside the packed buffer");
+    const int32_t* p0 = packed_dev + off;
+    if (rec[0] == 0) {
+      if ((rc = pcb_tile_add_dev(a, p0, p0 + n, p0 + 2 * n, n, rec[4] ? -1.0 : 1.0, 0.0, stream))) return rc;
+    } else {
+      if (events) PCB_CUDA(cudaEventRecord((cudaEvent_t)events[2 * r], st));
+      if ((rc = pcb_node_jobs_dev(a, p0, p0 + 8 * n, n, prior, rows_lse, rows_last, stream))) return rc;
+      if (events) PCB_CUDA(cudaEventRecord((cudaEvent_t)events[2 * r + 1], st));
+    }
+  }
+  if (n_slots > 0) {
+    if ((rc = pcb_reduce_rows_dev(rows_lse, n_slots, a->layout.S, sums_dev, stream))) return rc;
+    if ((rc = pcb_reduce_rows_dev(rows_last, n_slots, a->layout.S, sums_dev + n_slots, stream))) return rc;
+    PCB_CUDA(cudaMemcpyAsync(sums_host, sums_dev, (size_t)n_slots * 16, cudaMemcpyDeviceToHost, st));
+    PCB_CUDA(cudaStreamSynchronize(st));
+  }
+  return PCB_OK;
+}
+
 // ---- host-buffer entry points ---------------------------------------------------
 int pcb_np_conv_dims_host(const double* c1, const double* c2, double* out, int64_t B, int32_t S, int32_t G) {
   if (!c1 || !c2 || !out || B < 0) return fail(PCB_ERR_ARG, "np_conv_dims: null pointer");

@@ -275,6 +275,7 @@ PyObject* Book_pack(Book* self, PyObject*) {
   packed.reserve(self->adds->size() * 3 + self->jobs->size() * 8 + self->kids->size());
   PyObject* plan = PyList_New(0);
   if (!plan) return nullptr;
+  std::vector<int32_t> raw;  // the same plan as 6 int32 per record, for pcb_run_plan_dev
   std::vector<const PendAdd*> sel;
   std::vector<const PendJob*> selj;
   for (int lv = 1; lv <= max_level; ++lv) {
@@ -288,6 +289,8 @@ PyObject* Book_pack(Book* self, PyObject*) {
       for (const PendAdd* a : sel) packed.push_back(a->b);
       for (const PendAdd* a : sel) packed.push_back(a->out);
       PyObject* rec = Py_BuildValue("(snnd)", "add", (Py_ssize_t)off, (Py_ssize_t)n, neg ? -1.0 : 1.0);
+      const int32_t rr[6] = {0, (int32_t)off, (int32_t)n, 0, neg, 0};
+      raw.insert(raw.end(), rr, rr + 6);
       PyList_Append(plan, rec);
       Py_DECREF(rec);
       self->n_adds += (int64_t)n;
@@ -308,13 +311,16 @@ PyObject* Book_pack(Book* self, PyObject*) {
       packed.insert(packed.end(), self->kids->begin() + j->kid_off, self->kids->begin() + j->kid_off + j->n_kids);
     PyObject* rec = Py_BuildValue("(snnnn)", "jobs", (Py_ssize_t)off, (Py_ssize_t)n, (Py_ssize_t)koff,
                                   (Py_ssize_t)(koff - (int32_t)n));
+    const int32_t rr[6] = {1, (int32_t)off, (int32_t)n, koff, 0, 0};
+    raw.insert(raw.end(), rr, rr + 6);
     PyList_Append(plan, rec);
     Py_DECREF(rec);
     self->n_jobs += (int64_t)n;
     self->n_pairs += (int64_t)(koff - (int32_t)n);
   }
   PyObject* bytes = PyBytes_FromStringAndSize((const char*)packed.data(), (Py_ssize_t)(packed.size() * 4));
-  PyObject* out = Py_BuildValue("(NNn)", bytes, plan, (Py_ssize_t)self->pending_scores->size());
+  PyObject* raw_bytes = PyBytes_FromStringAndSize((const char*)raw.data(), (Py_ssize_t)(raw.size() * 4));
+  PyObject* out = Py_BuildValue("(NNnN)", bytes, plan, (Py_ssize_t)self->pending_scores->size(), raw_bytes);
   return out;
 }
 
@@ -364,7 +370,7 @@ PyMethodDef Book_methods[] = {
     {"score", (PyCFunction)Book_score, METH_O, "score handle of a dummy root folding kids"},
     {"value", (PyCFunction)Book_value, METH_O, "(lse_sum, last_sum) or None while pending"},
     {"has_pending", (PyCFunction)Book_has_pending, METH_NOARGS, ""},
-    {"pack", (PyCFunction)Book_pack, METH_NOARGS, "(packed bytes, plan, n_slots) of the pending batch"},
+    {"pack", (PyCFunction)Book_pack, METH_NOARGS, "(packed bytes, plan, n_slots, plan as int32 x 6 records) of the pending batch"},
     {"done", (PyCFunction)Book_done, METH_O, "hand back the [2, n_slots] scores of the packed batch"},
     {"set_capacity", (PyCFunction)Book_set_capacity, METH_O, ""},
     {"counters", (PyCFunction)Book_counters, METH_NOARGS, ""},

@@ -67,6 +67,8 @@ class DeviceArena:
         self.staged_bytes = 0  # host->device bytes of job tables / id lists so far
         self.job_timing = None  # set to a list to record (start_event, end_event, n_jobs, conv_pairs) per launch
         self._event_pool = []
+        self._plan_synced = True
+        self._plan_np = self._sums_np = None
 
     def start_timing(self, n_events=8192):
         """Time every node-jobs launch with a CUDA event pair from a pre-created pool (creating events inside the
@@ -86,7 +88,11 @@ class DeviceArena:
         pool = self._event_pool
         if len(pool) >= 2:
             return pool.pop(), pool.pop()
-        return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stream = torch.cuda.current_stream(self.device)
+        pair = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for e in pair:
+            e.record(stream)  # forces creation: the raw handle is handed to the C library
+        return pair
 
     def grow(self, new_capacity):
         """Enlarge the arena in place (tile ids stay valid): new zero-filled tensors, old content copied over."""
@@ -229,50 +235,62 @@ class DeviceArena:
             e1.record(torch.cuda.current_stream(self.device))
             timing.append((e0, e1, n, int(tab[:, 1].sum()) - n))
 
-    def run_plan(self, packed, plan, n_slots):
+    def run_plan(self, packed, plan, n_slots, plan_raw=None):
         """Execute one flush: `packed` (int32) holds every id list / job table of the batch and is sent to the
         device in ONE pinned copy; `plan` is a list of launches over it:
             ("add", offset, n, sign)          ids at offset: [a | b | out], n each
             ("jobs", offset, n, n_kids, cp)   table at offset (n*8 ints) followed by n_kids child ids
+        (`plan_raw`: the same as bytes of 6 int32 per record).  The whole flush is one `pcb_run_plan_dev` call.
         Returns a host float64 array [2, n_slots] with the summed score rows (synchronises), or None."""
-        lib, arena_ref, prior = self.lib, C.byref(self.c), self.prior
+        n_rec = len(plan)
+        if n_rec == 0:
+            return None
+        if plan_raw is None:
+            raw = np.zeros((n_rec, 6), dtype=np.int32)
+            for r, rec in enumerate(plan):
+                raw[r, :5] = (0, rec[1], rec[2], 0, rec[3] < 0) if rec[0] == "add" else (1, rec[1], rec[2], rec[3], 0)
+            plan_raw = raw.tobytes()
         stream_obj = torch.cuda.current_stream(self.device)
-        stream = C.c_void_p(stream_obj.cuda_stream)
-        base = self._to_dev_i32(packed, "plan").data_ptr()
-        pl = pt = None
+        n_ints = packed.shape[0]
+        st = self._staging.get("plan")
+        if st is None or st[0].shape[0] < n_ints:
+            stream_obj.synchronize()  # a copy out of the old pinned buffer may still be in flight
+            cap = max(4096, int(n_ints * 1.5))
+            st = self._staging["plan"] = (torch.empty(cap, dtype=torch.int32, pin_memory=True),
+                                          torch.empty(cap, dtype=torch.int32, device=self.device), None)
+            self._plan_np = st[0].numpy()
+        elif not self._plan_synced:
+            stream_obj.synchronize()  # the previous copy out of the pinned buffer must have drained
+        self._plan_np[:n_ints] = packed
+        self.staged_bytes += 4 * n_ints
+        pl = pt = sd = sh = None
         if n_slots:
             if self._rows is None or self._rows.shape[1] < n_slots:
                 cap = max(4096, int(n_slots * 1.5))
                 self._rows = torch.empty((2, cap, self.S), dtype=torch.float64, device=self.device)
                 self._sums = torch.empty(2 * cap, dtype=torch.float64, device=self.device)
                 self._sums_host = torch.empty(2 * cap, dtype=torch.float64, pin_memory=True)
+                self._sums_np = self._sums_host.numpy()
             pl, pt = self._rows[0].data_ptr(), self._rows[1].data_ptr()
+            sd, sh = self._sums.data_ptr(), self._sums_host.data_ptr()
         timing = self.job_timing
-        for rec in plan:
-            if rec[0] == "add":
-                _, off, n, sign = rec
-                p0 = base + 4 * off
-                _lib.check(lib.pcb_tile_add_dev(arena_ref, p0, p0 + 4 * n, p0 + 8 * n, n, sign, 0.0, stream))
-            else:
-                _, off, n, n_kids, conv_pairs = rec
-                p0 = base + 4 * off
-                if timing is not None:
-                    e0, e1 = self._event_pair()
-                    e0.record(stream_obj)
-                _lib.check(lib.pcb_node_jobs_dev(arena_ref, p0, p0 + 4 * n * JOB_INTS, n, prior, pl, pt, stream))
-                if timing is not None:
-                    e1.record(stream_obj)
-                    timing.append((e0, e1, n, conv_pairs))
+        events = None
+        if timing is not None:
+            pairs = [self._event_pair() for _ in range(n_rec)]
+            events = (C.c_void_p * (2 * n_rec))(*[e.cuda_event for pr in pairs for e in pr])
+        _lib.check(self.lib.pcb_run_plan_dev(C.byref(self.c), st[0].data_ptr(), n_ints, st[1].data_ptr(), plan_raw, n_rec,
+                                             self.prior, pl, pt, n_slots, sd, sh, events,
+                                             C.c_void_p(stream_obj.cuda_stream)))
+        self._plan_synced = bool(n_slots)
+        if timing is not None:
+            for (e0, e1), rec in zip(pairs, plan):
+                if rec[0] != "add":
+                    timing.append((e0, e1, rec[2], rec[4]))
+                else:
+                    self._event_pool.extend((e0, e1))
         if not n_slots:
             return None
-        # rows of the two score kinds are [cap, S] blocks: reduce each over S, copy both to pinned memory
-        # the two score kinds are reduced into one contiguous [2*n_slots] run: a single contiguous D2H copy
-        sp = self._sums.data_ptr()
-        _lib.check(lib.pcb_reduce_rows_dev(pl, n_slots, self.S, sp, stream))
-        _lib.check(lib.pcb_reduce_rows_dev(pt, n_slots, self.S, sp + 8 * n_slots, stream))
-        self._sums_host[: 2 * n_slots].copy_(self._sums[: 2 * n_slots], non_blocking=True)
-        stream_obj.synchronize()
-        return self._sums_host.numpy()[: 2 * n_slots].reshape(2, n_slots)
+        return self._sums_np[: 2 * n_slots].reshape(2, n_slots)
 
     def reduce_rows(self, rows):
         """rows: contiguous [2, n_slots, S] -> [2, n_slots] (sum over samples in order), one launch."""

@@ -133,9 +133,9 @@ class TileStore:
         st = self._stats
         t_begin = time.perf_counter()
         st["flushes"] += 1
-        packed, plan, n_slots = book.pack()
+        packed, plan, n_slots, plan_raw = book.pack()
         st["launches"] += len(plan) + (2 if n_slots else 0)
-        host = self.arena.run_plan(np.frombuffer(packed, dtype=np.int32), plan, n_slots)
+        host = self.arena.run_plan(np.frombuffer(packed, dtype=np.int32), plan, n_slots, plan_raw)
         if n_slots:
             st["d2h_bytes"] += 16 * n_slots
         book.done(host)

@@ -54,7 +54,7 @@ class FakeArena:
             out[order] = idx[order]
         return out
 
-    def run_plan(self, packed, plan, n_slots):
+    def run_plan(self, packed, plan, n_slots, plan_raw=None):
         out = np.zeros((2, max(n_slots, 1)))
         for rec in plan:
             if rec[0] == "add":

@@ -29,7 +29,7 @@ class NullArena:
     def tile_add(self, *a, **k):
         pass
 
-    def run_plan(self, packed, plan, n_slots):
+    def run_plan(self, packed, plan, n_slots, plan_raw=None):
         if not n_slots:
             return None
         self._n += 1
