@@ -231,7 +231,7 @@ def run_ours(args):
 
             r = bench_variant(CFG["samples"], CFG["grid"], -1, 32768, 8, 4096, 5)
             sat = {"achieved": r["tflops"], "unit": "TFLOP/s", "frac": r["tflops"] * 1e12 / fp64_peak,
-                   "launch": "32768 jobs x 8 children"}
+                   "launch": "32768 jobs x 8 children", "layout": "L=%d, P=%d (same as the timed chain)" % (r["L"], r["P"])}
         except Exception as e:  # noqa: BLE001
             sat = {"error": str(e)}
 

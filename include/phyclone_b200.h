@@ -63,7 +63,8 @@ typedef struct {
   int64_t tile_elems;    /* S * pitch                                */
 } pcb_layout;
 
-/* variant < 0 picks the default strip/lane configuration for (S, G) */
+/* variant = 100*L + P fixes the strip/lane configuration; -1 picks the throughput-optimal one for (S, G) (saturated
+ * batches), -2 the latency-optimal one (narrow strips: a single chain launches a handful of jobs at a time). */
 int pcb_make_layout(int32_t S, int32_t G, int32_t variant, pcb_layout* out);
 
 /* An arena is three caller-owned device arrays:

@@ -252,6 +252,16 @@ int pcb_make_layout(int32_t S, int32_t G, int32_t variant, pcb_layout* out) {
     if (env && *env) variant = atoi(env);
   }
   if (variant >= 0) return fill_layout(S, G, variant / 100, variant % 100, out);
+  if (variant == -2) {
+    // latency-optimised: a single chain launches a handful of jobs at a time, so the device is empty and the
+    // time of a launch is the time of ONE lane's strip pair; take the narrowest strip whose pairs fit a row group
+    for (int L : {7, 13, 17}) {
+      const int U = ((G + L - 1) / L + 1) / 2;
+      for (int P : {4, 8, 16, 32})
+        if (U <= P) return fill_layout(S, G, L, P, out);
+    }
+    return fail(PCB_ERR_ARG, "layout: grid too large");
+  }
   // default: fewest executed lane-FMAs among the conflict-free (odd strip) configurations with
   // at least 7 FMAs per shared-memory operand pair
   long long best = -1;
