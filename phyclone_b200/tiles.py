@@ -61,7 +61,7 @@ class TileStore:
         self._values_host = None
         self.upload_values(values)
         self.book = load_hostmod().TileBook(al.permanent, self.arena.capacity, self.prior_id)
-        self._stats = {"flushes": 0, "launches": 0, "d2h_bytes": 0, "flush_s": 0.0}
+        self._stats = {"flushes": 0, "launches": 0, "d2h_bytes": 0, "flush_s": 0.0, "device_wait_s": 0.0}
         self.reset()
 
     @property
@@ -138,7 +138,9 @@ class TileStore:
         st["flushes"] += 1
         packed, plan, n_slots, plan_raw = book.pack()
         st["launches"] += len(plan) + (2 if n_slots else 0)
+        t_run = time.perf_counter()
         host = self.arena.run_plan(np.frombuffer(packed, dtype=np.int32), plan, n_slots, plan_raw)
+        st["device_wait_s"] += time.perf_counter() - t_run
         if n_slots:
             st["d2h_bytes"] += 16 * n_slots
         book.done(host)
