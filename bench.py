@@ -91,7 +91,7 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU arms
-def oracle_chain_rate(iters, warmup, quiet=True):
+def oracle_chain_rate(iters, warmup, chain=0, n_chains=1):
     """PG iterations/s of the CPU port of the reference (oracle/sampler.py, with the reference's tile
     caches on: its real configuration) on the same workload; 1 core (a chain is single-threaded)."""
     from oracle import sampler as osm
@@ -101,7 +101,7 @@ def oracle_chain_rate(iters, warmup, quiet=True):
                          density=CFG["density"], precision=CFG["precision"])
     data = [osm.Datum(i, v) for i, v in enumerate(syn["values"])]
     marks = []
-    res = osm.run_chain(data, np.random.default_rng(1), warmup + iters, burnin=1, num_particles=CFG["particles"],
+    res = osm.run_chain(data, chain_rng(chain, n_chains), warmup + iters, burnin=1, num_particles=CFG["particles"],
                         proposal=CFG["proposal"], resample_threshold=CFG["resample_threshold"], use_tile_caches=True,
                         on_iteration=lambda i, e: marks.append(time.perf_counter()))
     t0 = marks[warmup - 1] if warmup > 0 else None
@@ -118,14 +118,31 @@ def run_reference_arm(args):
     # bounded sample: at ~10 s per iteration, cap the timed iterations so the run ends within a few minutes
     iters = min(args.steps, 12)
     warm = min(max(args.warmup, 1), 2)
-    rate, elapsed, ext = oracle_chain_rate(iters, warm)
-    sample = ("%d timed PG iterations of the config after 1 burn-in + %d warm-up iterations (%.1f s); a chain is "
-              "single-threaded in the reference" % (iters, warm, elapsed))
+    n_chains = max(args.gpus, 1)  # the GPU arm runs one chain per GPU: same job here
+    cores = min(n_chains, os.cpu_count() or 1)
+    if n_chains == 1:
+        rate, elapsed, ext = oracle_chain_rate(iters, warm)
+    else:
+        # the reference runs its chains in a ProcessPoolExecutor, one single-threaded process per chain (run.py:111-149)
+        from concurrent.futures import ProcessPoolExecutor
+
+        with ProcessPoolExecutor(max_workers=cores) as pool:
+            t0 = time.perf_counter()
+            futs = [pool.submit(oracle_chain_rate, iters, warm, c, n_chains) for c in range(n_chains)]
+            done = [f.result() for f in futs]
+            wall = time.perf_counter() - t0
+        # whole-job rate over the timed iterations: chains ran side by side (queued if there are fewer cores)
+        waves = -(-n_chains // cores)
+        elapsed = max(d[1] for d in done) * waves if waves > 1 else max(d[1] for d in done)
+        rate = n_chains * iters / elapsed
+        elapsed = wall
+    sample = ("%d timed PG iterations per chain, %d chain(s) in %d process(es), after 1 burn-in + %d warm-up iterations "
+              "(%.1f s wall); a chain is single-threaded in the reference" % (iters, n_chains, cores, warm, elapsed))
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 / rate, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": dict(CFG, workload=WORKLOAD),
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": dict(CFG, workload=WORKLOAD, chains=n_chains),
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "CPU port of the reference sampler (oracle/sampler.py, tile caches on); /root/reference is a Python "
