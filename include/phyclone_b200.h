@@ -60,10 +60,13 @@ typedef struct {
   int32_t pitch;         /* doubles per padded row                   */
   int32_t lead;          /* leading zero doubles per row (== L)      */
   int32_t rows_per_cta;  /* rows of one tile handled by one CTA      */
+  int32_t kernel;        /* 0: lane-per-unit job kernel, 1: unit-per-warp ("wide", 32 rows of 32/S jobs per CTA) */
+  int32_t reserved;
   int64_t tile_elems;    /* S * pitch                                */
 } pcb_layout;
 
-/* variant = 100*L + P fixes the strip/lane configuration; -1 picks the throughput-optimal one for (S, G) (saturated
+/* variant = 100*L + P fixes the strip/lane configuration (10000 + 100*L: the unit-per-warp kernel, S an even
+ * divisor of 32); -1 picks the throughput-optimal one for (S, G) (saturated
  * batches), -2 the latency-optimal one (narrow strips: a single chain launches a handful of jobs at a time). */
 int pcb_make_layout(int32_t S, int32_t G, int32_t variant, pcb_layout* out);
 

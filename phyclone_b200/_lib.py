@@ -21,6 +21,8 @@ class Layout(C.Structure):
         ("pitch", C.c_int32),
         ("lead", C.c_int32),
         ("rows_per_cta", C.c_int32),
+        ("kernel", C.c_int32),
+        ("reserved", C.c_int32),
         ("tile_elems", C.c_int64),
     ]
 

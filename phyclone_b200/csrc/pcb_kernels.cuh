@@ -26,6 +26,7 @@ struct JobKernelParams {
   double* sc_last;  // [slots][S]
   long long tile_elems;
   double prior;
+  long long n_jobs;
   int S, G, Q, U, P, pitch, lead, RB, row_blocks;
   int double_b;  // 1: two operand buffers (next child prefetched during the fold step), 0: one
 };
@@ -73,7 +74,9 @@ struct ConvLane {
   bool active, second;
 };
 
-template <int L>
+// TRI: the body is the last one of the current strip (its diagonal block): the entering elements are lead zeros,
+// so only the i >= p triangle is accumulated.  Only usable where the strip lengths are warp-uniform.
+template <int L, bool TRI = false>
 __device__ __forceinline__ void conv_step(ConvLane<L>& st, double (&X)[L], double (&Y)[L], double (&bv)[L],
                                           double (&y1)[L], double (&y2)[L]) {
   if (!st.active) return;
@@ -81,7 +84,7 @@ __device__ __forceinline__ void conv_step(ConvLane<L>& st, double (&X)[L], doubl
   for (int p = 0; p < L; ++p) {
     const double bj = bv[p];
 #pragma unroll
-    for (int i = 0; i < L; ++i) y2[i] = fma(bj, (i >= p) ? X[i - p] : Y[i - p + L], y2[i]);
+    for (int i = TRI ? p : 0; i < L; ++i) y2[i] = fma(bj, (i >= p) ? X[i - p] : Y[i - p + L], y2[i]);
     X[L - 1 - p] = st.an[-p];
     bv[p] = st.bn[p];
   }
@@ -132,7 +135,7 @@ __device__ __forceinline__ void conv_step_last(const ConvLane<L>& st, const doub
 
 // Raw sums come back in registers: y1 = strip u, y2 = strip Q-1-u (y2 only, for the middle
 // unit of an odd Q).
-template <int L>
+template <int L, bool UNIFORM = false>
 __device__ __forceinline__ void conv_unit(const double* __restrict__ a, const double* __restrict__ b, int u, int Q,
                                           bool active, double (&y1)[L], double (&y2)[L]) {
   const int k0 = u * L;
@@ -157,6 +160,30 @@ __device__ __forceinline__ void conv_unit(const double* __restrict__ a, const do
   }
   // warp-uniform: bodies 0..Q-1 in full, body Q as a triangle
   int it = 0;
+  if (UNIFORM) {
+    // unit-per-warp mapping: u (hence every strip length) is the same for all lanes, so the diagonal body of the
+    // FIRST strip (body number u) can run as a triangle too
+    for (; it + 2 <= Q; it += 2) {
+      if (it == u && st.second)
+        conv_step<L, true>(st, X, Y, bv, y1, y2);
+      else
+        conv_step<L>(st, X, Y, bv, y1, y2);
+      if (it + 1 == u && st.second)
+        conv_step<L, true>(st, Y, X, bv, y1, y2);
+      else
+        conv_step<L>(st, Y, X, bv, y1, y2);
+    }
+    if (it < Q) {
+      if (it == u && st.second)
+        conv_step<L, true>(st, X, Y, bv, y1, y2);
+      else
+        conv_step<L>(st, X, Y, bv, y1, y2);
+      conv_step_last<L>(st, Y, bv, y2);
+    } else {
+      conv_step_last<L>(st, X, bv, y2);
+    }
+    return;
+  }
   for (; it + 2 <= Q; it += 2) {
     conv_step<L>(st, X, Y, bv, y1, y2);
     conv_step<L>(st, Y, X, bv, y1, y2);
@@ -425,6 +452,252 @@ __global__ void __launch_bounds__(32) node_jobs_kernel(const JobKernelParams p) 
     if (slot >= 0) {
       p.sc_lse[(size_t)slot * p.S + row] = (vmax == -INFINITY) ? -INFINITY : vmax + log(esum);
       p.sc_last[(size_t)slot * p.S + row] = yrow[G - 1];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// node_jobs_wide_kernel: the same job, mapped UNIT-PER-WARP.  A CTA of P warps owns 32 consecutive rows of the
+// flattened (job, row) space -- 32/S whole jobs; the layout guarantees S | 32 -- warp u handles strip pair u of all
+// 32 rows, lane = row.  Every lane of a warp now has the same strip lengths, so the strip switch and all body
+// bookkeeping are warp-uniform (in the lane-per-unit kernel above the four lanes of a row switch at four
+// different bodies and the warp runs the switch block four times), two 4-row jobs fill a warp when S = 4, and
+// per-row scalars need no shuffles.  The price: the P warps of a CTA exchange the row maxima through shared
+// memory and meet at two CTA barriers per fold step.  Rows of one warp sit `pitch` doubles apart, so the layout
+// uses an ODD pitch (16 lanes of a 64-bit access hit 16 different bank pairs).
+// Shared memory: [256 B: mbarriers][A: 32*pitch][B: 32*pitch][red: P*32][M: 32][256 B slack].
+// ---------------------------------------------------------------------------------
+template <int L>
+__global__ void __launch_bounds__(128) node_jobs_wide_kernel(const JobKernelParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  const int P = p.P, G = p.G, pitch = p.pitch, lead = p.lead, Q = p.Q, S = p.S;
+  double* bufA = reinterpret_cast<double*>(smem_raw + kSmemHead);
+  double* bufB = bufA + 32 * pitch;
+  double* red = bufB + 32 * pitch;
+  double* Msh = red + P * 32;
+  const int tid = threadIdx.x, u = tid >> 5, lane = tid & 31;
+  const long long g0 = (long long)blockIdx.x * 32;
+  const long long total_rows = p.n_jobs * S;
+  const int job_first = (int)(g0 / S);
+  const int jobs_here = (int)min((long long)(32 / S), p.n_jobs - job_first);
+  const uint32_t job_bytes = (uint32_t)S * pitch * 8u;
+
+  // ---- fold phase identity: lane = row slot ---------------------------------------
+  const bool row_ok = g0 + lane < total_rows;
+  const int jl = lane / S;
+  const int row = lane - jl * S;
+  const int32_t* jr = p.jobs + (size_t)(job_first + (row_ok ? jl : 0)) * 8;
+  const int coff = jr[0];
+  const int C = row_ok ? jr[1] : 0;
+  const int Cmax = __reduce_max_sync(0xffffffffu, C);
+  // B is loaded at the start for jobs with a second child, and for single-child jobs that need the log tile
+  const bool needB0 = row_ok && (C >= 2 || !((jr[4] & 1) && jr[2] < 0 && jr[3] < 0));
+  const bool armed0 = __any_sync(0xffffffffu, needB0);
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int nb = 0;
+    for (int q = 0; q < jobs_here; ++q) {
+      const int32_t* r = p.jobs + (size_t)(job_first + q) * 8;
+      nb += (r[1] >= 2 || !((r[4] & 1) && r[2] < 0 && r[3] < 0)) ? 1 : 0;
+    }
+    mbar_expect_tx(&bars[0], (uint32_t)jobs_here * job_bytes);
+    if (nb) mbar_expect_tx(&bars[1], (uint32_t)nb * job_bytes);
+    for (int q = 0; q < jobs_here; ++q) {
+      const int32_t* r = p.jobs + (size_t)(job_first + q) * 8;
+      const int c0 = p.children[r[0]];
+      tma_load_1d(bufA + (size_t)q * S * pitch, p.lin + (size_t)c0 * p.tile_elems, job_bytes, &bars[0]);
+      if (r[1] >= 2) {
+        const int c1 = p.children[r[0] + 1];
+        tma_load_1d(bufB + (size_t)q * S * pitch, p.lin + (size_t)c1 * p.tile_elems, job_bytes, &bars[1]);
+      } else if (!((r[4] & 1) && r[2] < 0 && r[3] < 0)) {
+        tma_load_1d(bufB + (size_t)q * S * pitch, p.lg + (size_t)c0 * p.tile_elems, job_bytes, &bars[1]);
+      }
+    }
+  }
+  double M = row_ok ? p.rmax[(size_t)p.children[coff] * S + row] : 0.0;
+  mbar_wait(&bars[0], 0);
+  int phase = 0;
+  if (armed0) {
+    mbar_wait(&bars[1], 0);
+    phase = 1;
+  }
+
+  double* a_row = bufA + lane * pitch + lead;
+  const double* b_row = bufB + lane * pitch + lead;
+  const bool unit_ok = u < p.U;
+  const int k1 = u * L, k2 = (Q - 1 - u) * L;
+  const bool two = k2 != k1;
+
+  // ---- left fold over the children (tree/utils.py:33-47) --------------------------
+  for (int j = 1; j < Cmax; ++j) {
+    if (j >= 2) {
+      mbar_wait(&bars[1], phase & 1);
+      ++phase;
+    }
+    const bool act = row_ok && j < C && unit_ok;
+    double y1[L], y2[L];
+    conv_unit<L, true>(a_row, b_row, u, Q, act, y1, y2);
+    const int nv2 = act ? min(L, G - k2) : 0;
+    const bool v1 = act && two;
+    const double fl1 = v1 ? kFloor : 0.0;
+#pragma unroll
+    for (int i = 0; i < L; ++i) {
+      y2[i] = select_f64(y2[i] > 0.0 && i < nv2, y2[i], (i < nv2) ? kFloor : 0.0);
+      y1[i] = select_f64(y1[i] > 0.0 && v1, y1[i], fl1);
+    }
+    double mx[L];
+#pragma unroll
+    for (int i = 0; i < L; ++i) mx[i] = (y1[i] > y2[i]) ? y1[i] : y2[i];
+#pragma unroll
+    for (int w = 1; w < L; w <<= 1)
+#pragma unroll
+      for (int i = 0; i + w < L; i += 2 * w) mx[i] = (mx[i] > mx[i + w]) ? mx[i] : mx[i + w];
+    red[u * 32 + lane] = mx[0];
+    __syncthreads();  // row maxima published; every warp is done reading A and B
+    if (tid == 0 && j + 1 < Cmax) {  // single operand buffer: refill it for the jobs that have another child
+      fence_proxy_async();
+      int nb = 0;
+      for (int q = 0; q < jobs_here; ++q) nb += (p.jobs[(size_t)(job_first + q) * 8 + 1] > j + 1) ? 1 : 0;
+      mbar_expect_tx(&bars[1], (uint32_t)nb * job_bytes);
+      for (int q = 0; q < jobs_here; ++q) {
+        const int32_t* r = p.jobs + (size_t)(job_first + q) * 8;
+        if (r[1] > j + 1)
+          tma_load_1d(bufB + (size_t)q * S * pitch, p.lin + (size_t)p.children[r[0] + j + 1] * p.tile_elems, job_bytes,
+                      &bars[1]);
+      }
+    }
+    double ymax = red[lane];
+    for (int w = 1; w < P; ++w) ymax = fmax(ymax, red[w * 32 + lane]);
+    const bool rowact = row_ok && j < C;
+    const double mB = rowact ? p.rmax[(size_t)p.children[coff + j] * S + row] : 0.0;
+    double scale = 1.0;
+    bool tiny = false;
+    if (rowact) {
+      if (j < C - 1) {
+        // re-normalise the running product exactly where the reference re-max-shifts it
+        M += mB + log(ymax);
+        tiny = !(ymax >= 1e-290);
+        scale = 1.0 / ymax;
+      } else {
+        M += mB;
+      }
+    }
+    if (act) {
+      if (!tiny) {
+#pragma unroll
+        for (int i = 0; i < L; ++i) a_row[k2 + i] = y2[i] * scale;
+        if (two) {
+#pragma unroll
+          for (int i = 0; i < L; ++i) a_row[k1 + i] = y1[i] * scale;
+        }
+      } else {  // 1/ymax would overflow: divide
+#pragma unroll
+        for (int i = 0; i < L; ++i) a_row[k2 + i] = y2[i] / ymax;
+        if (two) {
+#pragma unroll
+          for (int i = 0; i < L; ++i) a_row[k1 + i] = y1[i] / ymax;
+        }
+      }
+    }
+    __syncthreads();  // A updated in place; `red` may be rewritten
+  }
+  if (u == 0) Msh[lane] = M;
+  __syncthreads();
+
+  // ---- epilogue identity: P lanes per row, rows 0..31 of the CTA; everything below is convergent within a warp
+  // (a warp may hold rows of jobs with different flags), so the group shuffles are executed by all lanes and only
+  // loads / stores are predicated ----------------------------------------------------------------------------------
+  const int erow = tid / P;
+  const int lir = tid & (P - 1);
+  const bool e_ok = g0 + erow < total_rows;
+  const int ejl = erow / S;
+  const int er = erow - ejl * S;
+  const int32_t* ej = p.jobs + (size_t)(job_first + (e_ok ? ejl : 0)) * 8;
+  const int eC = ej[1], base = ej[2], outt = ej[3], flags = ej[4], slot = ej[5];
+  const bool scan = flags & 1;
+  const double addc = (flags & 2) ? p.prior : 0.0;
+  const bool shortcut = scan && base < 0 && outt < 0;
+  const double Me = Msh[erow];
+  double* yrow = bufA + erow * pitch + lead;
+  const double* brow = bufB + erow * pitch + lead;
+
+  {  // dummy-root scoring without materialising the tile
+    const bool on = e_ok && shortcut;
+    double t1 = 0.0, t2 = 0.0;
+    if (on)
+      for (int k = lir; k < G; k += P) {
+        const double y = yrow[k];
+        t1 += y;
+        t2 = fma((double)(G - k), y, t2);
+      }
+    t1 = group_sum(t1, P);
+    t2 = group_sum(t2, P);
+    if (on && lir == 0 && slot >= 0) {
+      p.sc_lse[(size_t)slot * S + er] = (Me + addc) + log(t2);
+      p.sc_last[(size_t)slot * S + er] = (Me + addc) + log(t1);
+    }
+  }
+  const bool full = e_ok && !shortcut;
+  {  // elementwise log_D / log_S
+    const bool cs = full && eC >= 2 && scan;
+    const int chunk = (G + P - 1) / P;
+    const int kbeg = min(G, lir * chunk), kend = min(G, kbeg + chunk);
+    double loc = 0.0;
+    if (cs)
+      for (int k = kbeg; k < kend; ++k) loc += yrow[k];
+    double run = group_excl_scan(loc, P, lir);
+    if (cs)
+      for (int k = kbeg; k < kend; ++k) {
+        run += yrow[k];
+        yrow[k] = log(run) + Me;
+      }
+    if (full && eC >= 2 && !scan)
+      for (int k = lir; k < G; k += P) yrow[k] = log(yrow[k]) + Me;
+    row_prefix_lse(brow, yrow, G, P, lir, full && eC == 1 && scan);
+    if (full && eC == 1 && !scan)
+      for (int k = lir; k < G; k += P) yrow[k] = brow[k];
+  }
+  __syncwarp();
+  double vmax = -INFINITY;
+  if (full) {
+    const double* bptr = (base >= 0) ? p.lg + (size_t)base * p.tile_elems + (size_t)er * pitch + lead : nullptr;
+    for (int k = lir; k < G; k += P) {
+      double v = yrow[k];
+      if (bptr) v = bptr[k] + v;
+      v += addc;
+      yrow[k] = v;
+      vmax = fmax(vmax, v);
+    }
+  }
+  vmax = group_max(vmax, P);
+  double esum = 0.0;
+  if (full) {
+    double* olg = (outt >= 0) ? p.lg + (size_t)outt * p.tile_elems + (size_t)er * pitch + lead : nullptr;
+    double* olin = (outt >= 0) ? p.lin + (size_t)outt * p.tile_elems + (size_t)er * pitch + lead : nullptr;
+    for (int k = lir; k < G; k += P) {
+      const double v = yrow[k];
+      const double e = (v == -INFINITY) ? 0.0 : exp(v - vmax);
+      esum += e;
+      if (olg) {
+        olg[k] = v;
+        olin[k] = e;
+      }
+    }
+  }
+  esum = group_sum(esum, P);
+  __syncwarp();
+  if (full && lir == 0) {
+    if (outt >= 0) p.rmax[(size_t)outt * S + er] = vmax;
+    if (slot >= 0) {
+      p.sc_lse[(size_t)slot * S + er] = (vmax == -INFINITY) ? -INFINITY : vmax + log(esum);
+      p.sc_last[(size_t)slot * S + er] = yrow[G - 1];
     }
   }
 }

@@ -25,7 +25,7 @@ def _conv_cases(golden):
     return sorted(k[len("conv_out_"):] for k in golden.files if k.startswith("conv_out_"))
 
 
-VARIANTS = ["", "516", "708", "716", "908", "1304", "1308", "1316", "732"]
+VARIANTS = ["", "516", "708", "716", "908", "1304", "1308", "1316", "732", "11304", "11704"]
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
@@ -249,3 +249,56 @@ def test_device_arena_jobs_match_oracle(golden):
     ref2 = onum.root_terms(prior + onum.log_s([node, tiles[8]]))
     assert_close(sc2[:, 0], ref2, rtol=1e-9, what="second generation")
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("variant", [-1, 1304, 708, 11304, 10704])
+@pytest.mark.parametrize("S,G,n_jobs", [(4, 101, 37), (8, 101, 21), (2, 64, 50), (16, 101, 5)])
+def test_mixed_job_batches_match_oracle(variant, S, G, n_jobs):
+    """One launch with jobs of every kind side by side -- 1..6 children, dummy-root scores, nodes with and without
+    log_p / output tile / score slot -- which in the unit-per-warp kernel (variants >= 10000) share CTAs and warps."""
+    from phyclone_b200 import _lib, engine
+
+    rng = np.random.default_rng(100 * S + G + n_jobs)
+    n_in = 24
+    tiles = np.log(rng.uniform(0.1, 1000, size=(n_in, S, G)))
+    tiles[3] = -((np.arange(G)[None] - rng.uniform(0, G, (S, 1))) ** 2) * 4.0  # floors
+    tiles[7, :, : G // 2] -= 900.0
+    try:
+        ar = engine.DeviceArena(S, G, n_in + n_jobs + 4, variant=variant)
+    except _lib.PcbError as e:
+        assert "layout" in str(e)
+        pytest.skip("variant %d does not cover (%d, %d)" % (variant, S, G))
+    ar.import_tiles(tiles, list(range(n_in)))
+    prior = ar.prior
+    jobs, kids, want = [], [], []
+    for j in range(n_jobs):
+        C = int(rng.integers(1, 7))
+        ch = [int(c) for c in rng.integers(0, n_in, C)]
+        kind = int(rng.integers(4))
+        off = len(kids)
+        kids.extend(ch)
+        out = n_in + j
+        kid_tiles = [tiles[c] for c in ch]
+        if kind == 0:  # dummy-root score only
+            jobs.append(engine.make_job(off, C, base=-1, out=-1, flags=engine.JOB_SCAN | engine.JOB_ADD_PRIOR, slot=j))
+            want.append((None, prior + onum.log_s(kid_tiles)))
+        elif kind == 1:  # node: log_p + log_S, stored and scored
+            base = int(rng.integers(0, n_in))
+            jobs.append(engine.make_job(off, C, base=base, out=out, flags=engine.JOB_SCAN, slot=j))
+            want.append((out, onum.node_log_r(tiles[base], kid_tiles)))
+        elif kind == 2:  # log_S only, stored, no score
+            jobs.append(engine.make_job(off, C, base=-1, out=out, flags=engine.JOB_SCAN, slot=-1))
+            want.append((out, onum.log_s(kid_tiles)))
+        else:  # log_D (no scan), stored
+            jobs.append(engine.make_job(off, C, base=-1, out=out, flags=0, slot=j))
+            want.append((out, onum.log_d_chain(kid_tiles) if C > 1 else kid_tiles[0]))
+    sc = ar.run_jobs(np.array(jobs), np.array(kids), n_slots=n_jobs).cpu().numpy()
+    for j, (out, tile) in enumerate(want):
+        if out is not None:
+            got = ar.export_tiles([out]).cpu().numpy()[0]
+            assert_close_bucketed(got, tile, what="job %d tile" % j, max_boundary=16)
+        if jobs[j][5] >= 0:
+            lse, last = onum.root_terms(tile)
+            assert sc[0, j] == pytest.approx(lse, rel=1e-9), j
+            if np.isfinite(last) and tile[:, -1].min() > tile.max() - 600:
+                assert sc[1, j] == pytest.approx(last, rel=1e-9), j
