@@ -100,13 +100,19 @@ class AbstractSMCSampler(object):
         out = []
         kind_l, pick_l, koff_l, dist_l = kind.tolist(), pick.tolist(), koff.tolist(), dist_of.tolist()
         create = kernel.create_particle
+        memo = {}  # particles that drew the same thing from the same proposal share holder and log_q
         for i, p in enumerate(parents):
-            d = dists[dist_l[i]]
-            if kind_l[i] == 0:
-                holder = d._curr_trees[pick_l[i]]
-            else:
-                holder = d.new_node_holder(frozenset(kids[koff_l[i]:koff_l[i + 1]]))
-            out.append(create(d.log_p(holder), p, holder))
+            j = dist_l[i]
+            key = (j, pick_l[i]) if kind_l[i] == 0 else (j, -1, kids[koff_l[i]:koff_l[i + 1]].tobytes())
+            hit = memo.get(key)
+            if hit is None:
+                d = dists[j]
+                if kind_l[i] == 0:
+                    holder = d._curr_trees[pick_l[i]]
+                else:
+                    holder = d.new_node_holder(frozenset(kids[koff_l[i]:koff_l[i + 1]]))
+                hit = memo[key] = (d.log_p(holder), holder)
+            out.append(create(hit[0], p, hit[1]))
         kernel.num_extensions += n
         return out
 
