@@ -4,6 +4,7 @@
 and one TileStore (the device arena holding every tile of the chain).
 """
 
+import sys
 import time
 
 import numpy as np
@@ -51,6 +52,8 @@ class Chain(object):
                  num_samples_prune_regraph=1, device=None, store=None):
         self.data = data
         self.rng = rng
+        # the tree walks recurse once per level and a forest over T data points can be T deep
+        sys.setrecursionlimit(max(sys.getrecursionlimit(), 4 * len(data) + 1000))
         if store is None:
             store = TileStore(np.array([dp.value for dp in data]), device=device)
         self.store = store

@@ -151,18 +151,22 @@ class StateHolder(object):
             from ..tree.tree import Tree
             from .forest_state import ATTACH, NEW
 
-            if self._parent_holder is None:
-                t = Tree(self._grid_size, self._store)
-            else:
-                t = self._parent_holder.tree
-            if self.kind == ATTACH:
-                t.add_data_point_to_node(self.dp, self.arg)
-            elif self.kind == NEW:
-                t.create_root_node(children=self.arg, data=[self.dp])
-            else:
-                t.add_data_point_to_outliers(self.dp)
-            t.outliers  # noqa: B018 -- key-creation side effect of scoring a tree (see distributions.prepare)
-            self._thawed = t.thawed_copy()
+            # iterative (a genealogy is as long as the data set: 2000 edits at config #5)
+            chain, h = [], self
+            while isinstance(h, StateHolder) and h._thawed is None:
+                chain.append(h)
+                h = h._parent_holder
+            t = Tree(self._grid_size, self._store) if h is None else h.tree
+            for hh in reversed(chain):
+                if hh.kind == ATTACH:
+                    t.add_data_point_to_node(hh.dp, hh.arg)
+                elif hh.kind == NEW:
+                    t.create_root_node(children=hh.arg, data=[hh.dp])
+                else:
+                    t.add_data_point_to_outliers(hh.dp)
+                t.outliers  # noqa: B018 -- key-creation side effect of scoring a tree (see distributions.prepare)
+                t = t.thawed_copy()
+            self._thawed = t
         return self._thawed.copy()
 
 

@@ -141,15 +141,14 @@ class SlotDiGraph:
     # -------------------------------------------------------------- adjacency
     def successor_indices(self, i):
         edst = self.edst
-        out = self.out[i]
-        if len(out) < 2:
-            return [edst[e] for e in out]
-        seen, res = set(), []
-        for e in out:
-            t = edst[e]
-            if t not in seen:
-                seen.add(t)
-                res.append(t)
+        res = [edst[e] for e in self.out[i]]
+        if len(res) > 1 and len(set(res)) != len(res):  # parallel edges: each successor once, first occurrence
+            seen, uniq = set(), []
+            for t in res:
+                if t not in seen:
+                    seen.add(t)
+                    uniq.append(t)
+            return uniq
         return res
 
     def predecessor_indices(self, i):

@@ -68,3 +68,26 @@ def test_host_sampler_matches_oracle_with_many_outliers():
         assert np.array_equal(own_a, own_b) and np.array_equal(par_a, par_b), "topology differs at entry %d" % i
         assert abs(a["log_p_one"] - b["log_p_one"]) <= 1e-9 * abs(b["log_p_one"])
         assert abs(a["alpha"] - b["alpha"]) <= 1e-9 * abs(b["alpha"])
+
+
+def test_genealogy_longer_than_the_recursion_limit():
+    """Config #5 has 2000 data points: the replay of a particle's edits and the tree walks must not depend on
+    Python's default recursion limit (a no-arithmetic executor keeps this fast)."""
+    import inspect
+    import sys
+
+    from phyclone_b200.data.base import DataPoint
+    from phyclone_b200.run import Chain
+    from tests.null_store import NullTileStore
+
+    T = 320
+    vals = np.zeros((T, 2, 8))
+    data = [DataPoint(i, vals[i], outlier_marginal_prob=-10.0) for i in range(T)]
+    saved = sys.getrecursionlimit()
+    try:
+        chain = Chain(data, np.random.default_rng(3), num_particles=4, store=NullTileStore(vals))
+        sys.setrecursionlimit(len(inspect.stack()) + 250)  # fewer frames than edits in a genealogy
+        chain.burnin_step()
+        assert sum(len(v) for v in chain.tree.to_dict()["node_data"].values()) == T
+    finally:
+        sys.setrecursionlimit(saved)
