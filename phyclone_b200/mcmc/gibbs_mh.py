@@ -56,7 +56,14 @@ class DataPointSampler(object):
         g, lp, lr, idx = tree._graph, tree._lp, tree._lr, tree._node_indices
         root = idx[tree._ROOT_NODE_NAME]
         v = st.value_id[data_point.idx]
-        succ = g.successor_indices
+        succ_cache = {}
+
+        def succ(i, _get=succ_cache.get, _raw=g.successor_indices):  # the same node is asked for by every candidate below it
+            r = _get(i)
+            if r is None:
+                r = succ_cache[i] = _raw(i)
+            return r
+
         pred = g.predecessor_indices
         crp, mult, size, oprior, omarg = tree.prior_terms()
         n_nodes = tree.get_number_of_nodes()

@@ -66,17 +66,22 @@ class AbstractSMCSampler(object):
         if addr is None or n == 0:
             self._prepare_proposals(parents)
             return [self._propose_particle(p) for p in parents]
-        dists, index, dist_of = [], {}, np.empty(n, dtype=np.int32)
-        for i, p in enumerate(parents):
-            key = None if p is None else p.holder.vkey
-            j = index.get(key)
+        # a resampled swarm lists the same Particle object many times: resolve each object once
+        dists, index, by_obj, dist_l = [], {}, {}, []
+        for p in parents:
+            j = by_obj.get(id(p))
             if j is None:
-                d = kernel.get_proposal_distribution(data_point, p)
-                if not getattr(d, "fast_draws", False):
-                    return [self._propose_particle(q) for q in parents]
-                j = index[key] = len(dists)
-                dists.append(d)
-            dist_of[i] = j
+                key = None if p is None else p.holder.vkey
+                j = index.get(key)
+                if j is None:
+                    d = kernel.get_proposal_distribution(data_point, p)
+                    if not getattr(d, "fast_draws", False):
+                        return [self._propose_particle(q) for q in parents]
+                    j = index[key] = len(dists)
+                    dists.append(d)
+                by_obj[id(p)] = j
+            dist_l.append(j)
+        dist_of = np.array(dist_l, dtype=np.int32)
         for d in dists:
             if d._q_dist is None:
                 d._finish()  # the first one resolves the scores of every proposal of the step: one flush
@@ -98,7 +103,7 @@ class AbstractSMCSampler(object):
         if rc != 0:
             raise RuntimeError("pcb_smc_draws failed (rc=%d)" % rc)
         out = []
-        kind_l, pick_l, koff_l, dist_l = kind.tolist(), pick.tolist(), koff.tolist(), dist_of.tolist()
+        kind_l, pick_l, koff_l = kind.tolist(), pick.tolist(), koff.tolist()
         create = kernel.create_particle
         memo = {}  # particles that drew the same thing from the same proposal share holder and log_q
         for i, p in enumerate(parents):
