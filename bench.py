@@ -168,6 +168,16 @@ def run_ours(args):
         raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
     if args.gpus > 1 and world == 1:
         raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    # one host thread drives each chain: give every rank its own block of cores so that the ranks of a box do not
+    # migrate over each other (PCB_NO_PIN=1 turns it off)
+    pinned = None
+    if world > 1 and not os.environ.get("PCB_NO_PIN") and hasattr(os, "sched_setaffinity"):
+        cores = sorted(os.sched_getaffinity(0))
+        block = len(cores) // world
+        if block >= 1:
+            mine = cores[local * block:(local + 1) * block]
+            os.sched_setaffinity(0, mine)
+            pinned = "%d cores per rank (contiguous blocks of the %d available)" % (block, len(cores))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -196,6 +206,8 @@ def run_ours(args):
 
     stream = torch.cuda.current_stream(dev)
 
+    per_rank_ms = []
+
     def timed(n_steps, before_step=None, after_step=None):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
@@ -210,7 +222,12 @@ def run_ours(args):
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
+            every = [torch.zeros_like(ms) for _ in range(world)]
+            dist.all_gather(every, ms)
+            per_rank_ms[:] = [float(t.item()) / n_steps for t in every]
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        else:
+            per_rank_ms[:] = [float(ms.item()) / n_steps]
         return float(ms.item())
 
     # ---- timed region 1: inputs resident in HBM
@@ -220,6 +237,7 @@ def run_ours(args):
     staged0 = store.arena.staged_bytes
     with ClockSampler(local) as clocks:
         ms = timed(args.steps)
+    value_per_rank_ms = list(per_rank_ms)
     launches = ops.launch_count() - launches0
     s1 = dict(chain.stats)
     job_timing = store.arena.stop_timing()
@@ -284,6 +302,8 @@ def run_ours(args):
             "particle_extensions_per_sec": ext / (ms * 1e-3),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
+            "per_rank_ms_per_step": [round(x, 2) for x in value_per_rank_ms],
+            "cpu_pinning": pinned,
             "roofline": {"bound": "fp64", "kernel": "node_jobs_kernel", "achieved": achieved / 1e12,
                          "peak": fp64_peak / 1e12, "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": traffic, "traffic_source": traffic_src,
                          "launches": len(job_timing), "avg_launch_us": 1e3 * kernel_ms / n_launch,
