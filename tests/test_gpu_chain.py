@@ -123,3 +123,33 @@ def test_arena_grows_on_demand():
                              np.random.default_rng(1), ["s"], 1, 0, 0.0)
     for a, b in zip(res["trace"], ref["trace"]):
         assert a["log_p_one"] == b["log_p_one"] and a["alpha"] == b["alpha"]
+
+
+@pytest.mark.parametrize("depth", [200, 2000])
+def test_replayed_chain_at_bench_config(depth):
+    """BASELINE configs[1] at full size (50 clusters x 8 samples, grid 101, 100 particles; depth 2000 is the
+    floor-exercising variant of SURVEY.md 8d): one burn-in sweep and one PG iteration of the CPU port, its
+    draws replayed into the GPU sampler, which must ask for the same draws from the same distributions (1e-9)
+    and produce the same topologies, alpha and log_p_one."""
+    from oracle.synthetic import make_synthetic
+    from phyclone_b200.data.base import make_data_points
+    from phyclone_b200.run import run_phyclone_chain
+    from tests.chain_utils import signature
+    from tests.tape import RecordingRNG, ReplayRNG
+
+    syn = make_synthetic(50, 8, 101, 10, depth, seed=0, density="beta-binomial", precision=400)
+    vals = syn["values"]
+    rec = RecordingRNG(np.random.default_rng(1))
+    want = osm.run_chain([osm.Datum(i, v) for i, v in enumerate(vals)], rec, 1, burnin=1, num_particles=100)
+    rep = ReplayRNG(rec.tape)
+    res = run_phyclone_chain(1, True, 1.0, make_data_points(vals), float("inf"), 1, 100, 1, 1, 0, 10**9, "semi-adapted",
+                             0.5, rep, ["s"], 1, 0, 0.0)
+    assert rep.done()
+    assert len(res["trace"]) == len(want["trace"])
+    for got, ref in zip(res["trace"], want["trace"]):
+        assert got["alpha"] == pytest.approx(ref["alpha"], rel=1e-9)
+        assert got["log_p_one"] == pytest.approx(ref["log_p_one"], rel=1e-9)
+        a = signature(got["tree"], len(vals))
+        b = signature(ref["tree"], len(vals), name_of=lambda dp: dp.idx)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    print("depth %d: %d draws replayed, max relative probability error %.2e" % (depth, len(rec.tape), rep.max_p_err))
