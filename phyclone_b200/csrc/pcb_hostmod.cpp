@@ -564,6 +564,9 @@ PyObject* mod_forest_state(PyObject*, PyObject* args) {
 }
 
 // extend(book, kind, dp, arg) -> thawed successor state, or None if the arena is full
+// status: 0 = ok, 1 = arena full (nothing allocated; grow and call again), -1 = Python error set
+FState* fstate_extend(FState* self, Book* book, int kind, const DataPt& dp, PyObject* arg, int* status);
+
 PyObject* FState_extend(FState* self, PyObject* args) {
   Book* book;
   int kind;
@@ -571,6 +574,14 @@ PyObject* FState_extend(FState* self, PyObject* args) {
   if (!PyArg_ParseTuple(args, "O!iOO", &BookType, &book, &kind, &dpo, &arg)) return nullptr;
   DataPt dp;
   if (!parse_dp(dpo, dp)) return nullptr;
+  int status = 0;
+  FState* s = fstate_extend(self, book, kind, dp, arg, &status);
+  if (status == 1) Py_RETURN_NONE;
+  return (PyObject*)s;
+}
+
+FState* fstate_extend(FState* self, Book* book, int kind, const DataPt& dp, PyObject* arg, int* status) {
+  *status = -1;
   const size_t R = self->roots->size();
   long node = 0;
   std::vector<long> taken_names;
@@ -586,9 +597,15 @@ PyObject* FState_extend(FState* self, PyObject* args) {
       return nullptr;
     }
     lp_new = (*self->lp)[j_at] == book->prior_id ? dp.single_id : book_add(book, (*self->lp)[j_at], dp.value_id, false);
-    if (lp_new < 0) Py_RETURN_NONE;
+    if (lp_new < 0) {
+      *status = 1;
+      return nullptr;
+    }
     lr_new = (*self->kids)[j_at].empty() ? lp_new : book_node(book, lp_new, (*self->kids)[j_at]);
-    if (lr_new < 0) Py_RETURN_NONE;
+    if (lr_new < 0) {
+      *status = 1;
+      return nullptr;
+    }
   } else if (kind == K_NEW) {
     if (!longs_of(arg, taken_names)) return nullptr;
     for (size_t j = 0; j < R; ++j) {
@@ -599,7 +616,10 @@ PyObject* FState_extend(FState* self, PyObject* args) {
     for (int j : take) nk.push_back((*self->lr)[j]);  // descending slot order = thawed child order
     lp_new = dp.single_id;
     lr_new = nk.empty() ? lp_new : book_node(book, lp_new, nk);
-    if (lr_new < 0) Py_RETURN_NONE;
+    if (lr_new < 0) {
+      *status = 1;
+      return nullptr;
+    }
   }
   FState* s = fstate_alloc();
   if (!s) return nullptr;
@@ -626,7 +646,10 @@ PyObject* FState_extend(FState* self, PyObject* args) {
     s->omarg = self->omarg + dp.marg;
     if (dp.op != 0.0) s->oprior = self->oprior + dp.op;
     s->last_added = -1;
-    return (PyObject*)s;
+    {
+    *status = 0;
+    return s;
+  }
   }
   if (dp.op != 0.0) s->oprior = self->oprior + dp.opn;
   if (kind == K_ATTACH) {
@@ -649,7 +672,10 @@ PyObject* FState_extend(FState* self, PyObject* args) {
     s->crp = self->crp + (n >= 1 ? lf(n) - lf(n - 1) : 0.0);
     s->skey = self->skey ^ data_hash(node, n, dp.idx);
     s->last_added = node;
-    return (PyObject*)s;
+    {
+    *status = 0;
+    return s;
+  }
   }
   const long name = self->n_nodes, gi = self->n_slots, root_gi = 0;
   s->roots->push_back(name);
@@ -685,7 +711,10 @@ PyObject* FState_extend(FState* self, PyObject* args) {
   }
   s->skey = key;
   s->last_added = name;
-  return (PyObject*)s;
+  {
+    *status = 0;
+    return s;
+  }
 }
 
 // score_attach_all(book, dp, nodes, log_alpha) -> [(prior_p, prior_one, score id, n children of node)] | None
@@ -861,8 +890,375 @@ PyObject* mod_data_hash(PyObject*, PyObject* args) {
   return PyLong_FromUnsignedLongLong(data_hash(node, pos, idx));
 }
 
+// =====================================================================================================
+// Holder: one SMC candidate = thawed(parent) + one edit, scored from root-level states (smc/swarm.py adds the
+// tree replay on top as a Python subclass).  Mirrors the read interface of the reference's TreeHolder
+// (smc/swarm/tree_holder.py:6-110): log_p, log_p_one, tree_roots, node last added to, ...
+// =====================================================================================================
+#include <structmember.h>
+
+struct Holder {
+  PyObject_HEAD
+  long uid;
+  int kind;
+  PyObject* dp;
+  PyObject* arg;
+  PyObject* parent_holder;
+  PyObject* store;         // TileStore: flush() / _grow() / .book
+  Book* book;              // strong reference
+  FState* parent_state;    // thawed state of the parent particle
+  FState* tstate;          // thawed state of this candidate, built on demand
+  PyObject* roots_tuple;   // as-built root order
+  PyObject* roots_arr;     // the same as an array (made by the Python side on first use, or shared)
+  PyObject* vkey;
+  PyObject* thawed;        // cache slot of the Python subclass (replayed tree)
+  PyObject* grid_size;
+  long node_last_added_to, nkids;
+  double prior_p, prior_one, log_p, log_p_one, log_pdf;
+  int sid, resolved;
+  DataPt dpt;
+};
+
+long g_next_uid = -1;  // negative: never collides with the Python-side holder counter
+
+Holder* holder_new(PyTypeObject* cls) {
+  Holder* h = (Holder*)cls->tp_alloc(cls, 0);
+  if (!h) return nullptr;
+  h->uid = g_next_uid--;
+  h->kind = 0;
+  h->dp = h->arg = h->parent_holder = h->store = nullptr;
+  h->book = nullptr;
+  h->parent_state = h->tstate = nullptr;
+  h->roots_tuple = h->roots_arr = h->vkey = h->thawed = h->grid_size = nullptr;
+  h->node_last_added_to = h->nkids = 0;
+  h->prior_p = h->prior_one = h->log_p = h->log_p_one = h->log_pdf = 0.0;
+  h->sid = -1;
+  h->resolved = 0;
+  return h;
+}
+
+void Holder_dealloc(Holder* h) {
+  Py_XDECREF(h->dp);
+  Py_XDECREF(h->arg);
+  Py_XDECREF(h->parent_holder);
+  Py_XDECREF(h->store);
+  Py_XDECREF((PyObject*)h->book);
+  Py_XDECREF((PyObject*)h->parent_state);
+  Py_XDECREF((PyObject*)h->tstate);
+  Py_XDECREF(h->roots_tuple);
+  Py_XDECREF(h->roots_arr);
+  Py_XDECREF(h->vkey);
+  Py_XDECREF(h->thawed);
+  Py_XDECREF(h->grid_size);
+  Py_TYPE(h)->tp_free((PyObject*)h);
+}
+
+inline void set_ref(PyObject** slot, PyObject* v) {
+  Py_XINCREF(v);
+  Py_XDECREF(*slot);
+  *slot = v;
+}
+
+// common fields of a freshly scored candidate
+void holder_fill(Holder* h, int kind, PyObject* dp, const DataPt& dpt, PyObject* arg, PyObject* parent_holder,
+                 PyObject* store, Book* book, FState* parent_state, PyObject* grid_size) {
+  h->kind = kind;
+  h->dpt = dpt;
+  set_ref(&h->dp, dp);
+  set_ref(&h->arg, arg);
+  set_ref(&h->parent_holder, parent_holder);
+  set_ref(&h->store, store);
+  Py_INCREF((PyObject*)book);
+  h->book = book;
+  Py_INCREF((PyObject*)parent_state);
+  h->parent_state = parent_state;
+  set_ref(&h->grid_size, grid_size);
+}
+
+bool holder_resolve(Holder* h) {
+  if (h->resolved) return true;
+  double lp = h->prior_p, lp1 = h->prior_one;
+  if (h->sid >= 0) {
+    Book* b = h->book;
+    if ((size_t)h->sid >= b->sc_ready->size()) {
+      PyErr_SetString(PyExc_IndexError, "bad score id");
+      return false;
+    }
+    if (!(*b->sc_ready)[h->sid]) {  // first score read of a batch: run everything that is pending
+      PyObject* r = PyObject_CallMethod(h->store, "flush", nullptr);
+      if (!r) return false;
+      Py_DECREF(r);
+      if (!(*b->sc_ready)[h->sid]) {
+        PyErr_SetString(PyExc_RuntimeError, "score still pending after flush");
+        return false;
+      }
+    }
+    lp += (*b->sc_lse)[h->sid];
+    lp1 += (*b->sc_last)[h->sid];
+  }
+  h->log_p = lp;
+  h->log_p_one = lp1;
+  h->resolved = 1;
+  return true;
+}
+
+PyObject* Holder_get_log_p(Holder* h, void*) {
+  if (!holder_resolve(h)) return nullptr;
+  return PyFloat_FromDouble(h->log_p);
+}
+PyObject* Holder_get_log_p_one(Holder* h, void*) {
+  if (!holder_resolve(h)) return nullptr;
+  return PyFloat_FromDouble(h->log_p_one);
+}
+
+// thawed_state(): state of from_dict(to_dict(parent + edit)), built on first use
+PyObject* Holder_thawed_state(Holder* h, PyObject*) {
+  if (!h->tstate) {
+    for (int attempt = 0; attempt < 2 && !h->tstate; ++attempt) {
+      int status = 0;
+      PyObject* arg = h->arg;
+      PyObject* tmp = nullptr;
+      if (h->kind == K_NEW) {  // the thawed child order is the slot order: any iteration order of the set will do
+        tmp = PySequence_Tuple(arg);
+        if (!tmp) return nullptr;
+        arg = tmp;
+      }
+      FState* s = fstate_extend(h->parent_state, h->book, h->kind, h->dpt, arg, &status);
+      Py_XDECREF(tmp);
+      if (status == -1) return nullptr;
+      if (status == 1) {
+        PyObject* r = PyObject_CallMethod(h->store, "_grow", nullptr);
+        if (!r) return nullptr;
+        Py_DECREF(r);
+        continue;
+      }
+      h->tstate = s;
+    }
+    if (!h->tstate) {
+      PyErr_SetString(PyExc_MemoryError, "tile arena exhausted");
+      return nullptr;
+    }
+  }
+  Py_INCREF((PyObject*)h->tstate);
+  return (PyObject*)h->tstate;
+}
+
+PyObject* Holder_get_vkey(Holder* h, void*) {
+  if (!h->vkey) {
+    PyObject* st = Holder_thawed_state(h, nullptr);
+    if (!st) return nullptr;
+    FState* s = (FState*)st;
+    PyObject* last = s->has_last ? PyLong_FromLong(s->last_added) : (Py_INCREF(Py_None), Py_None);
+    h->vkey = Py_BuildValue("(KNl)", (unsigned long long)s->skey, last, s->n_nodes + 1);
+    Py_DECREF(st);
+    if (!h->vkey) return nullptr;
+  }
+  Py_INCREF(h->vkey);
+  return h->vkey;
+}
+
+PyObject* Holder_get_outlier_name(Holder*, void*) { return PyLong_FromLong(-1); }
+
+PyMemberDef Holder_members[] = {
+    {"uid", T_LONG, offsetof(Holder, uid), READONLY, ""},
+    {"kind", T_INT, offsetof(Holder, kind), READONLY, ""},
+    {"dp", T_OBJECT, offsetof(Holder, dp), READONLY, ""},
+    {"arg", T_OBJECT, offsetof(Holder, arg), READONLY, ""},
+    {"_parent_holder", T_OBJECT, offsetof(Holder, parent_holder), READONLY, ""},
+    {"_store", T_OBJECT, offsetof(Holder, store), READONLY, ""},
+    {"_grid_size", T_OBJECT, offsetof(Holder, grid_size), READONLY, ""},
+    {"_roots_tuple", T_OBJECT, offsetof(Holder, roots_tuple), READONLY, ""},
+    {"_roots_arr", T_OBJECT, offsetof(Holder, roots_arr), 0, ""},
+    {"_thawed", T_OBJECT, offsetof(Holder, thawed), 0, ""},
+    {"node_last_added_to", T_LONG, offsetof(Holder, node_last_added_to), READONLY, ""},
+    {"num_children_on_node_that_matters", T_LONG, offsetof(Holder, nkids), READONLY, ""},
+    {"log_pdf", T_DOUBLE, offsetof(Holder, log_pdf), 0, ""},
+    {nullptr, 0, 0, 0, nullptr}};
+
+PyGetSetDef Holder_getset[] = {{"log_p", (getter)Holder_get_log_p, nullptr, "", nullptr},
+                               {"log_p_one", (getter)Holder_get_log_p_one, nullptr, "", nullptr},
+                               {"vkey", (getter)Holder_get_vkey, nullptr, "value key of the thawed candidate", nullptr},
+                               {"outlier_node_name", (getter)Holder_get_outlier_name, nullptr, "", nullptr},
+                               {nullptr, nullptr, nullptr, nullptr, nullptr}};
+
+PyMethodDef Holder_methods[] = {
+    {"thawed_state", (PyCFunction)Holder_thawed_state, METH_NOARGS, "root-level state of this candidate's own round trip"},
+    {nullptr, nullptr, 0, nullptr}};
+
+PyTypeObject HolderType = {PyVarObject_HEAD_INIT(nullptr, 0)};
+
+// shared prior terms of all attach candidates of one base state (same operation order as score_attach_all)
+struct AttachTerms {
+  double head, tail_p, tail_one;
+};
+inline AttachTerms attach_terms(FState* base, const DataPt& dp, double log_alpha) {
+  double oprior = base->oprior;
+  if (dp.op != 0.0) oprior = oprior + dp.opn;
+  const long n = base->n_nodes;
+  AttachTerms t;
+  t.head = (double)n * log_alpha;
+  double ways = 0.0;
+  for (int z : *base->size) ways += (double)(z - 1) * tlog(z);
+  t.tail_p = -(double)(n - 1) * tlog(n + 1) - base->mult + (oprior + base->omarg);
+  t.tail_one = (-ways + g_rterm[base->size->size()]) - base->mult + (oprior + base->omarg);
+  return t;
+}
+
+// attach_holders(cls, store, base_state, parent_state, parent_holder, dp, dp_tuple, nodes, log_alpha, roots_arr)
+//   -> [holder per node] | None (arena full)
+PyObject* mod_attach_holders(PyObject*, PyObject* args) {
+  PyTypeObject* cls;
+  PyObject *store, *parent_holder, *dp, *dpo, *nodes_o, *roots_arr;
+  FState *base, *pstate;
+  double log_alpha;
+  if (!PyArg_ParseTuple(args, "O!OO!O!OOOOdO", &PyType_Type, &cls, &store, &FStateType, &base, &FStateType, &pstate,
+                        &parent_holder, &dp, &dpo, &nodes_o, &log_alpha, &roots_arr))
+    return nullptr;
+  DataPt dpt;
+  if (!parse_dp(dpo, dpt)) return nullptr;
+  std::vector<long> nodes;
+  if (!longs_of(nodes_o, nodes)) return nullptr;
+  PyObject* book_o = PyObject_GetAttrString(store, "book");
+  if (!book_o) return nullptr;
+  if (!PyObject_TypeCheck(book_o, &BookType)) {
+    Py_DECREF(book_o);
+    PyErr_SetString(PyExc_TypeError, "store.book is not a TileBook");
+    return nullptr;
+  }
+  Book* book = (Book*)book_o;
+  PyObject* grid = PyObject_GetAttrString(dp, "grid_size");
+  if (!grid) {
+    Py_DECREF(book_o);
+    return nullptr;
+  }
+  const AttachTerms t = attach_terms(base, dpt, log_alpha);
+  PyObject* roots_t = roots_tuple_of(base);
+  PyObject* out = PyList_New(0);
+  std::vector<int> kids_t;
+  bool ok = roots_t && out;
+  bool full = false;
+  for (size_t q = 0; ok && q < nodes.size(); ++q) {
+    const long node = nodes[q];
+    const int j = index_of(base, node);
+    if (j < 0) {
+      PyErr_SetString(PyExc_KeyError, "node is not a root of the base state");
+      ok = false;
+      break;
+    }
+    const int m = (*base->ndata)[j];
+    const double crp = t.head + (base->crp + (m >= 1 ? lf(m) - lf(m - 1) : 0.0));
+    const int lr = book_add(book, (*base->lr)[j], dpt.value_id, false);  // log_r += value (tree/tree_node.py:47-52)
+    if (lr < 0) {
+      full = true;
+      break;
+    }
+    kids_t = *base->lr;
+    kids_t[j] = lr;
+    Holder* h = holder_new(cls);
+    if (!h) {
+      ok = false;
+      break;
+    }
+    PyObject* node_o = PyLong_FromLong(node);
+    holder_fill(h, K_ATTACH, dp, dpt, node_o, parent_holder, store, book, pstate, grid);
+    Py_DECREF(node_o);
+    h->prior_p = crp + t.tail_p;
+    h->prior_one = crp + t.tail_one;
+    h->sid = book_score(book, kids_t);
+    h->node_last_added_to = node;
+    h->nkids = (long)(*base->kids)[j].size();
+    set_ref(&h->roots_tuple, roots_t);
+    if (roots_arr != Py_None) set_ref(&h->roots_arr, roots_arr);
+    PyList_Append(out, (PyObject*)h);
+    Py_DECREF((PyObject*)h);
+  }
+  Py_XDECREF(roots_t);
+  Py_DECREF(grid);
+  Py_DECREF(book_o);
+  if (!ok || full) {
+    Py_XDECREF(out);
+    if (!ok) return nullptr;
+    Py_RETURN_NONE;
+  }
+  return out;
+}
+
+// edit_holder(cls, store, base_state, parent_state, parent_holder, kind, dp, dp_tuple, arg, log_alpha)
+//   -> holder of base + (NEW root adopting `arg` | OUTLIER) | None (arena full)
+PyObject* mod_edit_holder(PyObject*, PyObject* args) {
+  PyTypeObject* cls;
+  PyObject *store, *parent_holder, *dp, *dpo, *arg;
+  FState *base, *pstate;
+  int kind;
+  double log_alpha;
+  if (!PyArg_ParseTuple(args, "O!OO!O!OiOOOd", &PyType_Type, &cls, &store, &FStateType, &base, &FStateType, &pstate,
+                        &parent_holder, &kind, &dp, &dpo, &arg, &log_alpha))
+    return nullptr;
+  if (kind != K_NEW && kind != K_OUTLIER) {
+    PyErr_SetString(PyExc_ValueError, "edit_holder: kind must be NEW or OUTLIER");
+    return nullptr;
+  }
+  DataPt dpt;
+  if (!parse_dp(dpo, dpt)) return nullptr;
+  PyObject* book_o = PyObject_GetAttrString(store, "book");
+  if (!book_o) return nullptr;
+  if (!PyObject_TypeCheck(book_o, &BookType)) {
+    Py_DECREF(book_o);
+    PyErr_SetString(PyExc_TypeError, "store.book is not a TileBook");
+    return nullptr;
+  }
+  Book* book = (Book*)book_o;
+  // the scoring itself is the ForestState method: (prior_p, prior_one, sid, roots[, k])
+  PyObject* rec;
+  if (kind == K_NEW) {
+    PyObject* children = PySequence_Tuple(arg);  // adoption order = the set's iteration order
+    if (!children) {
+      Py_DECREF(book_o);
+      return nullptr;
+    }
+    PyObject* a = Py_BuildValue("(OOOd)", book_o, dpo, children, log_alpha);
+    Py_DECREF(children);
+    rec = a ? FState_score_new(base, a) : nullptr;
+    Py_XDECREF(a);
+  } else {
+    PyObject* a = Py_BuildValue("(OOd)", book_o, dpo, log_alpha);
+    rec = a ? FState_score_outlier(base, a) : nullptr;
+    Py_XDECREF(a);
+  }
+  if (!rec || rec == Py_None) {
+    Py_DECREF(book_o);
+    return rec;  // error, or None: arena full
+  }
+  PyObject* grid = PyObject_GetAttrString(dp, "grid_size");
+  Holder* h = grid ? holder_new(cls) : nullptr;
+  if (!h) {
+    Py_XDECREF(grid);
+    Py_DECREF(rec);
+    Py_DECREF(book_o);
+    return nullptr;
+  }
+  holder_fill(h, kind, dp, dpt, arg, parent_holder, store, book, pstate, grid);
+  Py_DECREF(grid);
+  Py_DECREF(book_o);
+  h->prior_p = PyFloat_AsDouble(PyTuple_GET_ITEM(rec, 0));
+  h->prior_one = PyFloat_AsDouble(PyTuple_GET_ITEM(rec, 1));
+  h->sid = (int)PyLong_AsLong(PyTuple_GET_ITEM(rec, 2));
+  set_ref(&h->roots_tuple, PyTuple_GET_ITEM(rec, 3));
+  if (kind == K_NEW) {
+    h->nkids = PyLong_AsLong(PyTuple_GET_ITEM(rec, 4));
+    h->node_last_added_to = base->n_nodes;
+  } else {
+    h->nkids = 0;
+    h->node_last_added_to = -1;
+  }
+  Py_DECREF(rec);
+  return (PyObject*)h;
+}
+
 PyMethodDef mod_methods[] = {
     {"forest_state", mod_forest_state, METH_VARARGS, "build a ForestState from Python sequences"},
+    {"attach_holders", mod_attach_holders, METH_VARARGS, "scored candidates: the data point joins each given root"},
+    {"edit_holder", mod_edit_holder, METH_VARARGS, "scored candidate: new root adopting some roots, or outlier"},
     {"set_tables", mod_set_tables, METH_VARARGS, "log(n) and r_term(n) tables"},
     {"edge_hash", mod_edge_hash, METH_VARARGS, "structure-hash contribution of an edge (slot, src, dst)"},
     {"data_hash", mod_data_hash, METH_VARARGS, "structure-hash contribution of a data point (node, position, idx)"},
@@ -896,5 +1292,15 @@ PyMODINIT_FUNC PyInit__pcbhost(void) {
   if (PyType_Ready(&FStateType) < 0) return nullptr;
   Py_INCREF(&FStateType);
   PyModule_AddObject(m, "ForestState", (PyObject*)&FStateType);
+  HolderType.tp_name = "_pcbhost.Holder";
+  HolderType.tp_basicsize = sizeof(Holder);
+  HolderType.tp_flags = Py_TPFLAGS_DEFAULT | Py_TPFLAGS_BASETYPE;
+  HolderType.tp_dealloc = (destructor)Holder_dealloc;
+  HolderType.tp_members = Holder_members;
+  HolderType.tp_getset = Holder_getset;
+  HolderType.tp_methods = Holder_methods;
+  if (PyType_Ready(&HolderType) < 0) return nullptr;
+  Py_INCREF(&HolderType);
+  PyModule_AddObject(m, "Holder", (PyObject*)&HolderType);
   return m;
 }

@@ -13,7 +13,7 @@ import numpy as np
 
 from ..tree.tree import Tree
 from ..utils.math import cached_log_binomial_coefficient, discrete_rvs, log_binomial_coefficient, log_normalize
-from .forest_state import ATTACH, NEW, OUTLIER, ForestState, ensure_tables, score_attach_all
+from .forest_state import NEW, OUTLIER, ForestState, ensure_tables
 from .swarm import Particle, StateHolder, TreeHolder
 
 
@@ -255,14 +255,12 @@ class StateSemiAdaptedProposalDistribution(object):
         if parent_particle is not None and len(parent_particle.tree_roots):
             nodes = parent_particle.tree_roots.tolist()
             shared_roots = np.asarray(base_state.roots)  # attaching does not change the as-built root order
-            for node, (score, nkids) in zip(nodes, score_attach_all(base_state, st, data_point, nodes, td)):
-                trees.append(StateHolder(st, ph, parent_state, base_state, ATTACH, data_point, node, td,
-                                         prescored=(score, nkids, shared_roots)))
+            trees = StateHolder.attach_all(st, ph, parent_state, base_state, data_point, nodes, td, shared_roots)
         if kernel.outlier_proposal_prob > 0:
-            trees.append(StateHolder(st, ph, parent_state, base_state, OUTLIER, data_point, None, td))
+            trees.append(StateHolder.edit(st, ph, parent_state, base_state, OUTLIER, data_point, None, td))
         self.parent_is_empty_tree = parent_particle is None or len(parent_particle.tree_roots) == 0
         if self.parent_is_empty_tree:
-            trees.append(StateHolder(st, ph, parent_state, base_state, NEW, data_point, frozenset(), td))
+            trees.append(StateHolder.edit(st, ph, parent_state, base_state, NEW, data_point, frozenset(), td))
         else:
             self._cached_log_old_num_roots = np.log(len(parent_particle.tree_roots) + 1)
         self._curr_trees = trees
@@ -290,8 +288,8 @@ class StateSemiAdaptedProposalDistribution(object):
         from_dict; one holder per (parent value, data point, child set)."""
         key = (self._pholder.vkey, self.data_point.idx, children)
         return self.kernel._new_tree_cache.get(
-            key, lambda: StateHolder(self._store, self._pholder, self._pstate, self._pstate, NEW, self.data_point,
-                                     children, self.tree_dist))
+            key, lambda: StateHolder.edit(self._store, self._pholder, self._pstate, self._pstate, NEW, self.data_point,
+                                          children, self.tree_dist))
 
 
 class SemiAdaptedKernel(Kernel):

@@ -9,9 +9,12 @@ import itertools
 
 import numpy as np
 
+from .._hostmod import load as _load_hostmod
 from ..utils.math import log_sum_exp
+from .forest_state import host_tuple
 
-_uid = itertools.count()
+_hm = _load_hostmod()
+_uid = itertools.count()  # holders made by the extension count downwards from -1: the two never collide
 
 
 class TreeHolder(object):
@@ -77,63 +80,44 @@ class TreeHolder(object):
         return self._tstate
 
 
-class StateHolder(object):
+class StateHolder(_load_hostmod().Holder):
     """Holder of `thawed(parent) + one SMC edit`, evaluated from root-level `ForestState`s instead of a copied
-    `Tree` (see forest_state.py).  Same read interface as `TreeHolder`; the actual tree is only rebuilt, by
-    replaying the edits, when `.tree` is asked for."""
+    `Tree` (see forest_state.py).  Same read interface as `TreeHolder`.  The object itself -- score, lazy
+    `log_p` / `log_p_one` (the first read flushes the tile store), `thawed_state()`, `vkey` -- is the `_pcbhost.Holder`
+    C++ type and is created by the factories below; this subclass adds what needs a real `Tree`: it is only
+    rebuilt, by replaying the edits, when `.tree` is asked for."""
 
-    __slots__ = ("uid", "kind", "dp", "arg", "_parent_holder", "_parent_state", "_score", "tree_roots",
-                 "node_last_added_to", "num_children_on_node_that_matters", "outlier_node_name", "log_pdf", "_tstate",
-                 "_thawed", "_store", "_grid_size", "_vkey")
+    __slots__ = ()
 
-    def __init__(self, store, parent_holder, parent_state, base_state, kind, dp, arg, tree_dist, prescored=None):
-        from .forest_state import NEW, OUTLIER, score_edit
+    @staticmethod
+    def attach_all(store, parent_holder, parent_state, base_state, dp, nodes, tree_dist, shared_roots):
+        """One candidate per root in `nodes` (the data point joins that root), scored with shared prior terms."""
+        t = host_tuple(store, dp)
+        la = tree_dist.prior.log_alpha
+        hs = _hm.attach_holders(StateHolder, store, base_state, parent_state, parent_holder, dp, t, nodes, la, shared_roots)
+        if hs is None:  # arena full: grow and record again (ops already recorded are memoised)
+            store._grow()
+            hs = _hm.attach_holders(StateHolder, store, base_state, parent_state, parent_holder, dp, t, nodes, la,
+                                    shared_roots)
+        return hs
 
-        self.uid = next(_uid)
-        self.kind, self.dp, self.arg = kind, dp, arg
-        self._parent_holder = parent_holder
-        self._parent_state = parent_state
-        self._store, self._grid_size = store, dp.grid_size
-        if prescored is None:
-            self._score, roots, nkids = score_edit(base_state, store, kind, dp, arg, tree_dist)
-            self.tree_roots = np.asarray(roots)
-        else:  # (StateScore, children of the node, shared as-built roots array) from score_attach_all
-            self._score, nkids, self.tree_roots = prescored
-        self._vkey = None
-        self.outlier_node_name = -1
-        self.log_pdf = 0.0
-        if kind == OUTLIER:
-            self.node_last_added_to = -1
-        elif kind == NEW:
-            self.node_last_added_to = base_state.n_nodes
-        else:
-            self.node_last_added_to = arg
-        self.num_children_on_node_that_matters = nkids
-        self._tstate = None
-        self._thawed = None
+    @staticmethod
+    def edit(store, parent_holder, parent_state, base_state, kind, dp, arg, tree_dist):
+        """Candidate `base + (NEW root adopting the roots in arg | OUTLIER)`."""
+        t = host_tuple(store, dp)
+        la = tree_dist.prior.log_alpha
+        h = _hm.edit_holder(StateHolder, store, base_state, parent_state, parent_holder, kind, dp, t, arg, la)
+        if h is None:
+            store._grow()
+            h = _hm.edit_holder(StateHolder, store, base_state, parent_state, parent_holder, kind, dp, t, arg, la)
+        return h
 
     @property
-    def log_p(self):
-        return self._score.resolve()[0]
-
-    @property
-    def log_p_one(self):
-        return self._score.resolve()[1]
-
-    def thawed_state(self):
-        if self._tstate is None:
-            from .forest_state import extend
-
-            self._tstate = extend(self._parent_state, self._store, self.kind, self.dp, self.arg)
-        return self._tstate
-
-    @property
-    def vkey(self):
-        k = self._vkey
-        if k is None:
-            st = self.thawed_state()
-            k = self._vkey = (st.skey, st.last_added, st.n_nodes + 1)
-        return k
+    def tree_roots(self):
+        r = self._roots_arr
+        if r is None:
+            r = self._roots_arr = np.asarray(self._roots_tuple)
+        return r
 
     @property
     def labels(self):
