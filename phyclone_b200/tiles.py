@@ -31,7 +31,7 @@ class TileStore:
     packing) lives in the `_pcbhost.TileBook` C++ extension (csrc/pcb_hostmod.cpp); the arithmetic is executed
     by `arena` (an `engine.DeviceArena`; the CPU tests plug in a NumPy executor with the same interface)."""
 
-    LATENCY_LAYOUT = -2  # narrow strips: shorter single launches (27 vs 37 us at config #2), no gain per step measured
+    LATENCY_LAYOUT = -2  # narrow strips: shorter single launches (27 vs 33 us at config #2); what a chain uses
     THROUGHPUT_LAYOUT = -1  # wide strips: best FP64 pipe use on saturated batches
 
     def __init__(self, values, device=None, capacity=None, variant=-1, arena_factory=None):
