@@ -1255,8 +1255,144 @@ PyObject* mod_edit_holder(PyObject*, PyObject* args) {
   return (PyObject*)h;
 }
 
+// =====================================================================================================
+// Data-point Gibbs move: scores of re-attaching one data point to every node (and the outlier set), recorded from
+// the ONE current tree (mcmc/gibbs_mh.py:35-70 in the reference copies the tree once per candidate).
+// gibbs_scores(book, parent, kids, lp, lr, root, cand, cand_ndata, oi, n_old, n_nodes, crp, mult, sizes, oprior, omarg,
+//              dp_tuple, log_alpha, with_outlier) -> [(prior_p, prior_one, sid)] | None (arena full)
+//   parent / kids / lp / lr are indexed by graph slot; cand lists the candidate nodes in `tree.nodes` order;
+//   oi = slot of the node the point sits in now (-1: it is an outlier), n_old = points in that node.
+// Floating-point operations in the order of DataPointSampler._score_candidates / forest_state._priors.
+// =====================================================================================================
+PyObject* mod_gibbs_scores(PyObject*, PyObject* args) {
+  Book* book;
+  PyObject *parent_o, *kids_o, *lp_o, *lr_o, *cand_o, *cand_n_o, *sizes_o, *dpo;
+  long root, oi, n_old, n_nodes;
+  double crp, mult, oprior, omarg, log_alpha;
+  int with_outlier;
+  if (!PyArg_ParseTuple(args, "O!OOOOlOOlllddOddOdp", &BookType, &book, &parent_o, &kids_o, &lp_o,
+                        &lr_o, &root, &cand_o, &cand_n_o, &oi, &n_old, &n_nodes, &crp, &mult, &sizes_o, &oprior, &omarg,
+                        &dpo, &log_alpha, &with_outlier))
+    return nullptr;
+  DataPt dp;
+  if (!parse_dp(dpo, dp)) return nullptr;
+  std::vector<int> parent, lp, lr, cand, cand_n, sizes;
+  if (!ints_of(parent_o, parent) || !ints_of(lp_o, lp) || !ints_of(lr_o, lr) || !ints_of(cand_o, cand) ||
+      !ints_of(cand_n_o, cand_n) || !ints_of(sizes_o, sizes))
+    return nullptr;
+  std::vector<std::vector<int>> kids;
+  {
+    PyObject* it = PyObject_GetIter(kids_o);
+    if (!it) return nullptr;
+    while (PyObject* item = PyIter_Next(it)) {
+      std::vector<int> k;
+      const bool good = ints_of(item, k);
+      Py_DECREF(item);
+      if (!good) {
+        Py_DECREF(it);
+        return nullptr;
+      }
+      kids.push_back(std::move(k));
+    }
+    Py_DECREF(it);
+    if (PyErr_Occurred()) return nullptr;
+  }
+  const size_t n_slots = parent.size();
+  if (kids.size() != n_slots || lp.size() != n_slots || lr.size() != n_slots || cand.size() != cand_n.size() ||
+      root < 0 || (size_t)root >= n_slots || oi >= (long)n_slots) {
+    PyErr_SetString(PyExc_ValueError, "gibbs_scores: inconsistent tree arrays");
+    return nullptr;
+  }
+  const int NONE = -0x7fffffff;
+  std::vector<int> over(n_slots, NONE), over2(n_slots, NONE);
+  std::vector<int> touched2, kt;
+  int lp_old = -1;
+  double crp_removed = crp;
+  if (oi < 0) {  // currently an outlier: removing it touches no tile (tree/tree.py:446-454)
+    if (dp.op != 0.0) oprior = oprior - dp.op + dp.opn;
+    omarg = omarg - dp.marg;
+  } else {
+    // removal: new log_p of the old node, refreshed log_r along old node .. root
+    lp_old = book_add(book, lp[(size_t)oi], dp.value_id, true);
+    if (lp_old < 0) Py_RETURN_NONE;
+    long i = oi;
+    bool first = true;
+    while (i != root) {
+      kt.clear();
+      for (int c : kids[(size_t)i]) kt.push_back(over[(size_t)c] != NONE ? over[(size_t)c] : lr[(size_t)c]);
+      const int base = first ? lp_old : lp[(size_t)i];
+      const int t = kt.empty() ? base : book_node(book, base, kt);
+      if (t < 0) Py_RETURN_NONE;
+      over[(size_t)i] = t;
+      first = false;
+      i = parent[(size_t)i];
+      if (i < 0) {
+        PyErr_SetString(PyExc_ValueError, "gibbs_scores: node without a path to the root");
+        return nullptr;
+      }
+    }
+    crp_removed = crp - (lf(n_old - 1) - lf(n_old - 2));
+  }
+  auto cur = [&](int c) { return over[(size_t)c] != NONE ? over[(size_t)c] : lr[(size_t)c]; };
+  PyObject* out = PyList_New(0);
+  if (!out) return nullptr;
+  const std::vector<int>& roots = kids[(size_t)root];
+  for (size_t q = 0; q < cand.size(); ++q) {
+    const int ni = cand[q];
+    const int m = cand_n[q] - (ni == oi ? 1 : 0);  // points in the node once the point is removed
+    for (int t : touched2) over2[(size_t)t] = NONE;
+    touched2.clear();
+    int t0 = book_add(book, cur(ni), dp.value_id, false);
+    if (t0 < 0) {
+      Py_DECREF(out);
+      Py_RETURN_NONE;
+    }
+    over2[(size_t)ni] = t0;
+    touched2.push_back(ni);
+    long i = parent[(size_t)ni];
+    while (i != root) {
+      if (i < 0) {
+        Py_DECREF(out);
+        PyErr_SetString(PyExc_ValueError, "gibbs_scores: node without a path to the root");
+        return nullptr;
+      }
+      kt.clear();
+      for (int c : kids[(size_t)i]) kt.push_back(over2[(size_t)c] != NONE ? over2[(size_t)c] : cur(c));
+      const int t = book_node(book, i == oi ? lp_old : lp[(size_t)i], kt);
+      if (t < 0) {
+        Py_DECREF(out);
+        Py_RETURN_NONE;
+      }
+      over2[(size_t)i] = t;
+      touched2.push_back((int)i);
+      i = parent[(size_t)i];
+    }
+    kt.clear();
+    for (int c : roots) kt.push_back(over2[(size_t)c] != NONE ? over2[(size_t)c] : cur(c));
+    const double c2 = crp_removed + (m >= 1 ? lf(m) - lf(m - 1) : 0.0);
+    double p, p1;
+    priors(log_alpha, n_nodes, c2, mult, sizes.data(), sizes.size(), oprior, omarg, p, p1);
+    PyObject* rec = Py_BuildValue("(ddi)", p, p1, book_score(book, kt));
+    PyList_Append(out, rec);
+    Py_DECREF(rec);
+  }
+  if (with_outlier) {
+    kt.clear();
+    for (int c : roots) kt.push_back(cur(c));
+    double op = oprior;
+    if (dp.op != 0.0) op = oprior - dp.opn + dp.op;
+    double p, p1;
+    priors(log_alpha, n_nodes, crp_removed, mult, sizes.data(), sizes.size(), op, omarg + dp.marg, p, p1);
+    PyObject* rec = Py_BuildValue("(ddi)", p, p1, kt.empty() ? -1 : book_score(book, kt));
+    PyList_Append(out, rec);
+    Py_DECREF(rec);
+  }
+  return out;
+}
+
 PyMethodDef mod_methods[] = {
     {"forest_state", mod_forest_state, METH_VARARGS, "build a ForestState from Python sequences"},
+    {"gibbs_scores", mod_gibbs_scores, METH_VARARGS, "scores of moving one data point to every node / the outliers"},
     {"attach_holders", mod_attach_holders, METH_VARARGS, "scored candidates: the data point joins each given root"},
     {"edit_holder", mod_edit_holder, METH_VARARGS, "scored candidate: new root adopting some roots, or outlier"},
     {"set_tables", mod_set_tables, METH_VARARGS, "log(n) and r_term(n) tables"},

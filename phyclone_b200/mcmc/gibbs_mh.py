@@ -6,8 +6,10 @@ candidate scores are read afterwards, so one Gibbs step is one batched device ev
 
 import numpy as np
 
-from ..utils.math import cached_log_factorial as lf
+from .._hostmod import load as _load_hostmod
 from ..utils.math import exp_normalize, log_normalize
+
+_hm = _load_hostmod()
 
 
 class DataPointSampler(object):
@@ -50,69 +52,44 @@ class DataPointSampler(object):
         return new_tree
 
     def _score_candidates(self, tree, data_point, old_node):
-        from ..smc.forest_state import StateScore, _priors
+        """Scores of `tree` with `data_point` moved to every node (in `tree.nodes` order) and, with outlier
+        modelling on, to the outlier set.  The tree is flattened into per-slot arrays and `_pcbhost.gibbs_scores`
+        records the tile ops of the two path refreshes of every candidate (removal from `old_node`, `log_r += value`
+        on the new node, parents up to the root) and computes the prior terms from the running statistics."""
+        from ..smc.forest_state import StateScore, ensure_tables, host_tuple
 
         st = tree.store
         g, lp, lr, idx = tree._graph, tree._lp, tree._lr, tree._node_indices
-        root = idx[tree._ROOT_NODE_NAME]
-        v = st.value_id[data_point.idx]
-        succ_cache = {}
-
-        def succ(i, _get=succ_cache.get, _raw=g.successor_indices):  # the same node is asked for by every candidate below it
-            r = _get(i)
-            if r is None:
-                r = succ_cache[i] = _raw(i)
-            return r
-
-        pred = g.predecessor_indices
-        crp, mult, size, oprior, omarg = tree.prior_terms()
-        n_nodes = tree.get_number_of_nodes()
-        roots = succ(root)
-        sizes = [size[i] for i in roots]
         prior = self.tree_dist.prior
-        over = {}
+        ensure_tables(prior, st.T + 2)
+        n_slots = len(g.payload)
+        parent, kids = [-1] * n_slots, [()] * n_slots
+        lp_l, lr_l = [-1] * n_slots, [-1] * n_slots
+        succ, pred = g.successor_indices, g.predecessor_indices
+        for i in g.node_indices():
+            kids[i] = succ(i)
+            p = pred(i)
+            if p:
+                parent[i] = p[0]
+            lp_l[i], lr_l[i] = lp[i], lr[i]
+        root = idx[tree._ROOT_NODE_NAME]
+        crp, mult, size, oprior, omarg = tree.prior_terms()
+        sizes = [size[i] for i in kids[root]]
+        nodes = tree.nodes
+        data = tree._data
+        cand = [idx[n] for n in nodes]
+        cand_n = [len(data[n]) for n in nodes]
         if old_node == tree._OUTLIER_NODE_NAME:
-            # the point is currently an outlier: removing it touches no tile (tree/tree.py:446-454)
-            oi, lp_old = -1, None
-            crp_removed = crp
-            if data_point.outlier_prob != 0:
-                oprior = oprior - data_point.outlier_prob + data_point.outlier_prob_not
-            omarg = omarg - data_point.outlier_marginal_prob
+            oi, n_old = -1, 0
         else:
-            # ---- removal: new log_p of old_node, refreshed log_r along old_node..root
-            oi = idx[old_node]
-            lp_old = st.sub(lp[oi], v)
-            i, first = oi, True
-            while i != root:
-                kids = tuple(over.get(c, lr[c]) for c in succ(i))
-                base = lp_old if first else lp[i]
-                over[i] = st.node(base, kids) if kids else base
-                first = False
-                i = pred(i)[0]
-            n_old = len(tree._data[old_node])
-            crp_removed = crp - (lf(n_old - 1) - lf(n_old - 2))
-        out = []
-        for new_node in tree.nodes:
-            ni = idx[new_node]
-            m = len(tree._data[new_node]) - (1 if ni == oi else 0)  # points in the node once the point is removed
-            over2 = {ni: st.add(over.get(ni, lr[ni]), v)}
-            i = pred(ni)[0]
-            while i != root:
-                kids = tuple(over2.get(c, over.get(c, lr[c])) for c in succ(i))
-                over2[i] = st.node(lp_old if i == oi else lp[i], kids)
-                i = pred(i)[0]
-            kids = tuple(over2.get(c, over.get(c, lr[c])) for c in roots)
-            c2 = crp_removed + (lf(m) - lf(m - 1) if m >= 1 else 0.0)
-            p, p1 = _priors(prior, n_nodes, c2, mult, sizes, oprior, omarg)
-            out.append(StateScore(p, p1, st.score(kids), st))
-        if self.outliers:
-            kids = tuple(over.get(c, lr[c]) for c in roots)
-            op = oprior
-            if data_point.outlier_prob != 0:
-                op = oprior - data_point.outlier_prob_not + data_point.outlier_prob
-            p, p1 = _priors(prior, n_nodes, crp_removed, mult, sizes, op, omarg + data_point.outlier_marginal_prob)
-            out.append(StateScore(p, p1, st.score(kids) if kids else None, st))
-        return out
+            oi, n_old = idx[old_node], len(data[old_node])
+        args = (st.book, parent, kids, lp_l, lr_l, root, cand, cand_n, oi, n_old, tree.get_number_of_nodes(), crp, mult,
+                sizes, oprior, omarg, host_tuple(st, data_point), prior.log_alpha, bool(self.outliers))
+        recs = _hm.gibbs_scores(*args)
+        if recs is None:  # arena full: grow and record again (ops already recorded are memoised)
+            st._grow()
+            recs = _hm.gibbs_scores(*args)
+        return [StateScore(p, p1, None if sid < 0 else sid, st) for p, p1, sid in recs]
 
 
 class PruneRegraphSampler(object):
