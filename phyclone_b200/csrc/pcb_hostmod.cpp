@@ -11,6 +11,7 @@
 #include <cstring>
 #include <string>
 #include <unordered_map>
+#include <map>
 #include <vector>
 
 namespace {
@@ -1256,6 +1257,312 @@ PyObject* mod_edit_holder(PyObject*, PyObject* args) {
 }
 
 // =====================================================================================================
+// Particle (smc/swarm/particle.py): log_q, parent particle, holder; the incremental weight
+// log_w = log_p - parent.log_p - log_q (smc/kernels/base.py:38-57) is evaluated on first read, so that every new
+// candidate of an SMC step is scored by one batched flush.
+// =====================================================================================================
+struct Particle {
+  PyObject_HEAD
+  PyObject* log_q;
+  PyObject* parent;
+  PyObject* holder;
+  double log_w;
+  int has_w;
+};
+
+extern PyTypeObject ParticleType;
+
+bool holder_scores(PyObject* holder, double* lp, double* lp1) {
+  if (PyObject_TypeCheck(holder, &HolderType)) {
+    Holder* h = (Holder*)holder;
+    if (!holder_resolve(h)) return false;
+    *lp = h->log_p;
+    *lp1 = h->log_p_one;
+    return true;
+  }
+  PyObject* a = PyObject_GetAttrString(holder, "log_p");
+  if (!a) return false;
+  *lp = PyFloat_AsDouble(a);
+  Py_DECREF(a);
+  if (lp1) {
+    PyObject* b = PyObject_GetAttrString(holder, "log_p_one");
+    if (!b) return false;
+    *lp1 = PyFloat_AsDouble(b);
+    Py_DECREF(b);
+  }
+  return !PyErr_Occurred();
+}
+
+Particle* particle_make(PyObject* log_q, PyObject* parent, PyObject* holder) {
+  Particle* p = PyObject_New(Particle, &ParticleType);
+  if (!p) return nullptr;
+  Py_INCREF(log_q);
+  Py_INCREF(parent);
+  Py_INCREF(holder);
+  p->log_q = log_q;
+  p->parent = parent;
+  p->holder = holder;
+  p->log_w = 0.0;
+  p->has_w = 0;
+  return p;
+}
+
+PyObject* Particle_new(PyTypeObject*, PyObject* args, PyObject*) {
+  PyObject *log_q, *parent, *holder;
+  if (!PyArg_ParseTuple(args, "OOO", &log_q, &parent, &holder)) return nullptr;
+  return (PyObject*)particle_make(log_q, parent, holder);
+}
+
+void Particle_dealloc(Particle* p) {
+  // genealogies are as long as the data set: release the parent chain iteratively, not recursively
+  PyObject* parent = p->parent;
+  Py_XDECREF(p->log_q);
+  Py_XDECREF(p->holder);
+  PyObject_Del(p);
+  while (parent && Py_TYPE(parent) == &ParticleType && Py_REFCNT(parent) == 1) {
+    Particle* q = (Particle*)parent;
+    PyObject* next = q->parent;
+    Py_XDECREF(q->log_q);
+    Py_XDECREF(q->holder);
+    PyObject_Del(q);
+    parent = next;
+  }
+  Py_XDECREF(parent);
+}
+
+bool particle_log_w(Particle* p, double* out) {
+  if (!p->has_w) {
+    double lp, unused;
+    if (!holder_scores(p->holder, &lp, &unused)) return false;
+    const double lq = PyFloat_AsDouble(p->log_q);
+    if (lq == -1.0 && PyErr_Occurred()) return false;
+    double w = lp;
+    if (p->parent != Py_None) {
+      double plp;
+      if (Py_TYPE(p->parent) == &ParticleType) {
+        if (!holder_scores(((Particle*)p->parent)->holder, &plp, &unused)) return false;
+      } else {
+        PyObject* a = PyObject_GetAttrString(p->parent, "log_p");
+        if (!a) return false;
+        plp = PyFloat_AsDouble(a);
+        Py_DECREF(a);
+      }
+      w = w - plp;
+    }
+    p->log_w = w - lq;
+    p->has_w = 1;
+  }
+  *out = p->log_w;
+  return true;
+}
+
+PyObject* Particle_get_log_w(Particle* p, void*) {
+  double w;
+  if (!particle_log_w(p, &w)) return nullptr;
+  return PyFloat_FromDouble(w);
+}
+PyObject* Particle_get_log_p(Particle* p, void*) {
+  double lp, lp1;
+  if (!holder_scores(p->holder, &lp, &lp1)) return nullptr;
+  return PyFloat_FromDouble(lp);
+}
+PyObject* Particle_get_log_p_one(Particle* p, void*) {
+  double lp, lp1;
+  if (!holder_scores(p->holder, &lp, &lp1)) return nullptr;
+  return PyFloat_FromDouble(lp1);
+}
+PyObject* Particle_get_log_pdf(Particle*, void*) { return PyFloat_FromDouble(0.0); }
+PyObject* Particle_get_holder(Particle* p, void*) {
+  Py_INCREF(p->holder);
+  return p->holder;
+}
+PyObject* Particle_get_tree_roots(Particle* p, void*) { return PyObject_GetAttrString(p->holder, "tree_roots"); }
+PyObject* Particle_get_tree_nodes(Particle* p, void*) { return PyObject_GetAttrString(p->holder, "tree_nodes"); }
+PyObject* Particle_get_tree(Particle* p, void*) { return PyObject_GetAttrString(p->holder, "tree"); }
+
+PyMemberDef Particle_members[] = {{"_log_q", T_OBJECT, offsetof(Particle, log_q), 0, ""},
+                                  {"parent_particle", T_OBJECT, offsetof(Particle, parent), READONLY, ""},
+                                  {"_holder", T_OBJECT, offsetof(Particle, holder), READONLY, ""},
+                                  {nullptr, 0, 0, 0, nullptr}};
+
+PyGetSetDef Particle_getset[] = {{"log_w", (getter)Particle_get_log_w, nullptr, "", nullptr},
+                                 {"log_p", (getter)Particle_get_log_p, nullptr, "", nullptr},
+                                 {"log_p_one", (getter)Particle_get_log_p_one, nullptr, "", nullptr},
+                                 {"log_pdf", (getter)Particle_get_log_pdf, nullptr, "", nullptr},
+                                 {"holder", (getter)Particle_get_holder, nullptr, "", nullptr},
+                                 {"tree_roots", (getter)Particle_get_tree_roots, nullptr, "", nullptr},
+                                 {"tree_nodes", (getter)Particle_get_tree_nodes, nullptr, "", nullptr},
+                                 {"tree", (getter)Particle_get_tree, nullptr, "", nullptr},
+                                 {nullptr, nullptr, nullptr, nullptr, nullptr}};
+
+PyTypeObject ParticleType = {PyVarObject_HEAD_INIT(nullptr, 0)};
+
+// particle_log_ws(particles, last_step) -> [log_w] (+ log_p_one - log_p on the last SMC step, samplers/base.py:52-58)
+PyObject* mod_particle_log_ws(PyObject*, PyObject* args) {
+  PyObject* seq;
+  int last;
+  if (!PyArg_ParseTuple(args, "Op", &seq, &last)) return nullptr;
+  PyObject* fast = PySequence_Fast(seq, "expected a sequence of particles");
+  if (!fast) return nullptr;
+  const Py_ssize_t n = PySequence_Fast_GET_SIZE(fast);
+  PyObject* out = PyList_New(n);
+  for (Py_ssize_t i = 0; out && i < n; ++i) {
+    PyObject* o = PySequence_Fast_GET_ITEM(fast, i);
+    double w;
+    if (Py_TYPE(o) == &ParticleType) {
+      Particle* p = (Particle*)o;
+      if (!particle_log_w(p, &w)) {
+        Py_CLEAR(out);
+        break;
+      }
+      if (last) {
+        double lp, lp1;
+        if (!holder_scores(p->holder, &lp, &lp1)) {
+          Py_CLEAR(out);
+          break;
+        }
+        w = w - lp + lp1;
+      }
+    } else {
+      PyErr_SetString(PyExc_TypeError, "particle_log_ws: not a Particle");
+      Py_CLEAR(out);
+      break;
+    }
+    PyList_SET_ITEM(out, i, PyFloat_FromDouble(w));
+  }
+  Py_DECREF(fast);
+  return out;
+}
+
+// finish_particles(parents, dist_of, kind, pick, kids, koff, cands, log_qs, meta, new_holder) -> [Particle]
+//   Turns the draws of one SMC step (csrc/pcb_host.cpp) into particles: particle i extends parents[i] with the
+//   candidate it drew from proposal dist_of[i] -- an enumerated one (kind 0: cands[j][pick]) or a new root adopting
+//   kids[koff[i]:koff[i+1]] (made by the Python callback new_holder(j, frozenset), which owns the value-keyed LRU) --
+//   and carries the proposal log-probability of semi_adapted.py:36-61.
+//   meta[j] = (parent is empty, log 1/2, log(R + 1), R); log_qs[j]: float64 buffer of the normalised candidate scores.
+PyObject* mod_finish_particles(PyObject*, PyObject* args) {
+  PyObject *parents_o, *dist_o, *kind_o, *pick_o, *kids_o, *koff_o, *cands_o, *logq_o, *meta_o, *cb;
+  if (!PyArg_ParseTuple(args, "OOOOOOOOOO", &parents_o, &dist_o, &kind_o, &pick_o, &kids_o, &koff_o, &cands_o, &logq_o,
+                        &meta_o, &cb))
+    return nullptr;
+  std::vector<long> dist, kind, pick, kids, koff;
+  if (!longs_of(dist_o, dist) || !longs_of(kind_o, kind) || !longs_of(pick_o, pick) || !longs_of(kids_o, kids) ||
+      !longs_of(koff_o, koff))
+    return nullptr;
+  PyObject* parents = PySequence_Fast(parents_o, "parents must be a sequence");
+  if (!parents) return nullptr;
+  const Py_ssize_t n = PySequence_Fast_GET_SIZE(parents);
+  if ((size_t)n != dist.size() || (size_t)n != kind.size() || (size_t)n != pick.size() || koff.size() != (size_t)n + 1) {
+    Py_DECREF(parents);
+    PyErr_SetString(PyExc_ValueError, "finish_particles: array lengths differ");
+    return nullptr;
+  }
+  struct Made {
+    PyObject* holder;
+    double log_q;
+  };
+  std::map<std::pair<long, std::vector<long>>, Made> memo;  // same proposal, same children: same holder and log_q
+  PyObject* out = PyList_New(n);
+  bool ok = out != nullptr;
+  for (Py_ssize_t i = 0; ok && i < n; ++i) {
+    const long j = dist[(size_t)i];
+    PyObject* meta = PySequence_GetItem(meta_o, j);
+    if (!meta) {
+      ok = false;
+      break;
+    }
+    int empty;
+    double log_half, log_r1;
+    long R;
+    ok = PyArg_ParseTuple(meta, "pddl", &empty, &log_half, &log_r1, &R) != 0;
+    Py_DECREF(meta);
+    if (!ok) break;
+    PyObject* holder = nullptr;
+    double lq = 0.0;
+    if (kind[(size_t)i] == 0) {
+      PyObject* cl = PySequence_GetItem(cands_o, j);
+      holder = cl ? PySequence_GetItem(cl, pick[(size_t)i]) : nullptr;
+      Py_XDECREF(cl);
+      PyObject* arr = holder ? PySequence_GetItem(logq_o, j) : nullptr;
+      Py_buffer view;
+      if (!arr || PyObject_GetBuffer(arr, &view, PyBUF_C_CONTIGUOUS) != 0) {
+        Py_XDECREF(arr);
+        Py_XDECREF(holder);
+        ok = false;
+        break;
+      }
+      if ((size_t)view.len < (size_t)(pick[(size_t)i] + 1) * sizeof(double)) {
+        PyErr_SetString(PyExc_IndexError, "finish_particles: pick outside the candidate scores");
+        ok = false;
+      } else {
+        const double q = ((const double*)view.buf)[pick[(size_t)i]];
+        lq = empty ? q : log_half + q;
+      }
+      PyBuffer_Release(&view);
+      Py_DECREF(arr);
+      if (!ok) {
+        Py_XDECREF(holder);
+        break;
+      }
+    } else {
+      std::pair<long, std::vector<long>> key(j, std::vector<long>(kids.begin() + koff[(size_t)i], kids.begin() + koff[(size_t)i + 1]));
+      auto it = memo.find(key);
+      if (it == memo.end()) {
+        PyObject* lst = PyList_New(0);
+        for (long c : key.second) {
+          PyObject* v = PyLong_FromLong(c);
+          PyList_Append(lst, v);
+          Py_DECREF(v);
+        }
+        PyObject* fs = PyFrozenSet_New(lst);
+        Py_DECREF(lst);
+        PyObject* h = fs ? PyObject_CallFunction(cb, "lO", j, fs) : nullptr;
+        Py_XDECREF(fs);
+        if (!h) {
+          ok = false;
+          break;
+        }
+        long nk;
+        if (PyObject_TypeCheck(h, &HolderType)) {
+          nk = ((Holder*)h)->nkids;
+        } else {
+          PyObject* a = PyObject_GetAttrString(h, "num_children_on_node_that_matters");
+          nk = a ? PyLong_AsLong(a) : -1;
+          Py_XDECREF(a);
+          if (PyErr_Occurred()) {
+            Py_DECREF(h);
+            ok = false;
+            break;
+          }
+        }
+        const double lbc = lf(R) - lf(nk) - lf(R - nk);  // utils/math.py:180-182
+        Made m{h, log_half - (log_r1 + lbc)};
+        it = memo.emplace(std::move(key), m).first;  // the map keeps the reference
+      }
+      holder = it->second.holder;
+      Py_INCREF(holder);
+      lq = it->second.log_q;
+    }
+    PyObject* lqo = PyFloat_FromDouble(lq);
+    Particle* p = lqo ? particle_make(lqo, PySequence_Fast_GET_ITEM(parents, i), holder) : nullptr;
+    Py_XDECREF(lqo);
+    Py_DECREF(holder);
+    if (!p) {
+      ok = false;
+      break;
+    }
+    PyList_SET_ITEM(out, i, (PyObject*)p);
+  }
+  for (auto& kv : memo) Py_DECREF(kv.second.holder);
+  Py_DECREF(parents);
+  if (!ok) {
+    Py_XDECREF(out);
+    return nullptr;
+  }
+  return out;
+}
+
+// =====================================================================================================
 // Data-point Gibbs move: scores of re-attaching one data point to every node (and the outlier set), recorded from
 // the ONE current tree (mcmc/gibbs_mh.py:35-70 in the reference copies the tree once per candidate).
 // gibbs_scores(book, parent, kids, lp, lr, root, cand, cand_ndata, oi, n_old, n_nodes, crp, mult, sizes, oprior, omarg,
@@ -1392,6 +1699,8 @@ PyObject* mod_gibbs_scores(PyObject*, PyObject* args) {
 
 PyMethodDef mod_methods[] = {
     {"forest_state", mod_forest_state, METH_VARARGS, "build a ForestState from Python sequences"},
+    {"particle_log_ws", mod_particle_log_ws, METH_VARARGS, "incremental weights of a list of particles"},
+    {"finish_particles", mod_finish_particles, METH_VARARGS, "particles of one SMC step from its draws"},
     {"gibbs_scores", mod_gibbs_scores, METH_VARARGS, "scores of moving one data point to every node / the outliers"},
     {"attach_holders", mod_attach_holders, METH_VARARGS, "scored candidates: the data point joins each given root"},
     {"edit_holder", mod_edit_holder, METH_VARARGS, "scored candidate: new root adopting some roots, or outlier"},
@@ -1438,5 +1747,15 @@ PyMODINIT_FUNC PyInit__pcbhost(void) {
   if (PyType_Ready(&HolderType) < 0) return nullptr;
   Py_INCREF(&HolderType);
   PyModule_AddObject(m, "Holder", (PyObject*)&HolderType);
+  ParticleType.tp_name = "_pcbhost.Particle";
+  ParticleType.tp_basicsize = sizeof(Particle);
+  ParticleType.tp_flags = Py_TPFLAGS_DEFAULT;
+  ParticleType.tp_new = Particle_new;
+  ParticleType.tp_dealloc = (destructor)Particle_dealloc;
+  ParticleType.tp_members = Particle_members;
+  ParticleType.tp_getset = Particle_getset;
+  if (PyType_Ready(&ParticleType) < 0) return nullptr;
+  Py_INCREF(&ParticleType);
+  PyModule_AddObject(m, "Particle", (PyObject*)&ParticleType);
   return m;
 }

@@ -12,10 +12,13 @@ import ctypes as C
 import numpy as np
 
 from .. import _hostlib
+from .._hostmod import load as _load_hostmod
 from ..tree.tree import Tree
 from ..utils.math import discrete_rvs
 from .swarm import ParticleSwarm, TreeHolder
 from .utils import RootPermutationDistribution
+
+_hm = _load_hostmod()
 
 
 class AbstractSMCSampler(object):
@@ -102,24 +105,17 @@ class AbstractSMCSampler(object):
                                            ptr(r_off), ptr(empty), ptr(kind), ptr(pick), ptr(kids), ptr(koff))
         if rc != 0:
             raise RuntimeError("pcb_smc_draws failed (rc=%d)" % rc)
-        out = []
-        kind_l, pick_l, koff_l = kind.tolist(), pick.tolist(), koff.tolist()
-        create = kernel.create_particle
-        memo = {}  # particles that drew the same thing from the same proposal share holder and log_q
-        for i, p in enumerate(parents):
-            j = dist_l[i]
-            key = (j, pick_l[i]) if kind_l[i] == 0 else (j, -1, kids[koff_l[i]:koff_l[i + 1]].tobytes())
-            hit = memo.get(key)
-            if hit is None:
-                d = dists[j]
-                if kind_l[i] == 0:
-                    holder = d._curr_trees[pick_l[i]]
-                else:
-                    holder = d.new_node_holder(frozenset(kids[koff_l[i]:koff_l[i + 1]]))
-                hit = memo[key] = (d.log_p(holder), holder)
-            out.append(create(hit[0], p, hit[1]))
+        meta = [(d.parent_is_empty_tree, float(d.log_half),
+                 0.0 if d.parent_is_empty_tree else float(d._cached_log_old_num_roots), len(d.roots_array)) for d in dists]
+        out = _hm.finish_particles(parents, dist_l, kind.tolist(), pick.tolist(), kids.tolist(), koff.tolist(),
+                                   [d._curr_trees for d in dists],
+                                   [d._log_q for d in dists], meta, lambda j, children: dists[j].new_node_holder(children))
         kernel.num_extensions += n
         return out
+
+    def _get_log_ws(self, particles):
+        """`_get_log_w` for a list of particles in one call into the host extension."""
+        return _hm.particle_log_ws(particles, self.iteration >= self.num_iterations - 1)
 
     def _get_log_w(self, particle):
         """base.py:52-58"""
@@ -151,8 +147,8 @@ class SMCSampler(AbstractSMCSampler):
         log_W = self.swarm.log_weights
         particles = self._propose_all(self.swarm.particles)
         new_swarm = ParticleSwarm()
-        for parent_log_W, particle in zip(log_W, particles):
-            new_swarm.add_particle(parent_log_W + self._get_log_w(particle), particle)
+        for parent_log_W, particle, log_w in zip(log_W, particles, self._get_log_ws(particles)):
+            new_swarm.add_particle(parent_log_W + log_w, particle)
         self.swarm = new_swarm
 
 
@@ -223,8 +219,8 @@ class ConditionalSMCSampler(AbstractSMCSampler):
         retained = self.constrained_path[self.iteration + 1]
         particles = [retained] + self._propose_all(self.swarm.particles[1:])
         new_swarm = ParticleSwarm()
-        for parent_log_W, particle in zip(log_W, particles):
-            new_swarm.add_particle(parent_log_W + self._get_log_w(particle), particle)
+        for parent_log_W, particle, log_w in zip(log_W, particles, self._get_log_ws(particles)):
+            new_swarm.add_particle(parent_log_W + log_w, particle)
         self.swarm = new_swarm
 
 

@@ -154,37 +154,9 @@ class StateHolder(_load_hostmod().Holder):
         return self._thawed.copy()
 
 
-class Particle(object):
-    """smc/swarm/particle.py; the incremental weight (kernels/base.py:38-57) is evaluated on first read so
-    that every new tree of an SMC step is scored by one batched flush."""
-
-    __slots__ = ("_log_w", "_log_q", "parent_particle", "_holder")
-
-    def __init__(self, log_q, parent_particle, tree_holder):
-        self._log_w = None
-        self._log_q = log_q
-        self.parent_particle = parent_particle
-        self._holder = tree_holder
-
-    @property
-    def log_w(self):
-        if self._log_w is None:
-            if self.parent_particle is None:
-                self._log_w = self._holder.log_p - self._log_q
-            else:
-                self._log_w = self._holder.log_p - self.parent_particle.log_p - self._log_q
-        return self._log_w
-
-    log_p = property(lambda self: self._holder.log_p)
-    log_p_one = property(lambda self: self._holder.log_p_one)
-    log_pdf = property(lambda self: 0.0)
-    tree_roots = property(lambda self: self._holder.tree_roots)
-    tree_nodes = property(lambda self: self._holder.tree_nodes)
-    holder = property(lambda self: self._holder)
-
-    @property
-    def tree(self):
-        return self._holder.tree
+# smc/swarm/particle.py: (log_q, parent_particle, holder) with the incremental weight (kernels/base.py:38-57) evaluated on
+# first read, so that every new tree of an SMC step is scored by one batched flush.  Native type: csrc/pcb_hostmod.cpp.
+Particle = _hm.Particle
 
 
 class ParticleSwarm(object):
