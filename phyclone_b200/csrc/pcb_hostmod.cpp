@@ -1697,8 +1697,45 @@ PyObject* mod_gibbs_scores(PyObject*, PyObject* args) {
   return out;
 }
 
+// log_sum_exp(float64 buffer) (utils/math.py:102-118): max shift, terms summed left to right with libm exp / log
+PyObject* mod_log_sum_exp(PyObject*, PyObject* arg) {
+  Py_buffer view;
+  if (PyObject_GetBuffer(arg, &view, PyBUF_C_CONTIGUOUS | PyBUF_FORMAT) != 0) return nullptr;
+  if (view.itemsize != 8 || !view.format || view.format[0] != 'd') {
+    PyBuffer_Release(&view);
+    PyErr_SetString(PyExc_TypeError, "log_sum_exp: expected a contiguous float64 buffer");
+    return nullptr;
+  }
+  const double* x = (const double*)view.buf;
+  const Py_ssize_t n = view.len / 8;
+  if (n == 0) {
+    PyBuffer_Release(&view);
+    PyErr_SetString(PyExc_ValueError, "log_sum_exp of an empty array");
+    return nullptr;
+  }
+  double m = x[0];
+  bool nan = std::isnan(m);
+  for (Py_ssize_t i = 1; i < n; ++i) {
+    nan |= std::isnan(x[i]);
+    if (x[i] > m) m = x[i];
+  }
+  double out;
+  if (nan) {
+    out = std::nan("");
+  } else if (std::isinf(m)) {
+    out = m;
+  } else {
+    double total = 0.0;
+    for (Py_ssize_t i = 0; i < n; ++i) total += std::exp(x[i] - m);
+    out = std::log(total) + m;
+  }
+  PyBuffer_Release(&view);
+  return PyFloat_FromDouble(out);
+}
+
 PyMethodDef mod_methods[] = {
     {"forest_state", mod_forest_state, METH_VARARGS, "build a ForestState from Python sequences"},
+    {"log_sum_exp", mod_log_sum_exp, METH_O, "log sum exp of a float64 buffer, reference summation order"},
     {"particle_log_ws", mod_particle_log_ws, METH_VARARGS, "incremental weights of a list of particles"},
     {"finish_particles", mod_finish_particles, METH_VARARGS, "particles of one SMC step from its draws"},
     {"gibbs_scores", mod_gibbs_scores, METH_VARARGS, "scores of moving one data point to every node / the outliers"},

@@ -135,21 +135,15 @@ class SMCSampler(AbstractSMCSampler):
 
     def _resample_swarm(self):
         if self.swarm.relative_ess <= self.resample_threshold:
-            new_swarm = ParticleSwarm()
             log_uniform_weight = -np.log(self.num_particles)
             multiplicities = self._rng.multinomial(self.num_particles, self.swarm.weights)
-            for particle, multiplicity in zip(self.swarm.particles, multiplicities):
-                for _ in range(multiplicity):
-                    new_swarm.add_particle(log_uniform_weight, particle)
-            self.swarm = new_swarm
+            particles = [p for p, m in zip(self.swarm.particles, multiplicities.tolist()) for _ in range(m)]
+            self.swarm = ParticleSwarm.of(particles, [log_uniform_weight] * len(particles))
 
     def _update_swarm(self):
         log_W = self.swarm.log_weights
         particles = self._propose_all(self.swarm.particles)
-        new_swarm = ParticleSwarm()
-        for parent_log_W, particle, log_w in zip(log_W, particles, self._get_log_ws(particles)):
-            new_swarm.add_particle(parent_log_W + log_w, particle)
-        self.swarm = new_swarm
+        self.swarm = ParticleSwarm.of(particles, [a + b for a, b in zip(log_W, self._get_log_ws(particles))])
 
 
 class ConditionalSMCSampler(AbstractSMCSampler):
@@ -205,23 +199,17 @@ class ConditionalSMCSampler(AbstractSMCSampler):
 
     def _resample_swarm(self):
         if self.swarm.relative_ess <= self.resample_threshold:
-            new_swarm = ParticleSwarm()
             log_uniform_weight = -np.log(self.num_particles)
             multiplicities = self._rng.multinomial(self.num_particles - 1, self.swarm.weights)
-            new_swarm.add_particle(log_uniform_weight, self.constrained_path[self.iteration + 1])
-            for particle, multiplicity in zip(self.swarm.particles, multiplicities):
-                for _ in range(multiplicity):
-                    new_swarm.add_particle(log_uniform_weight, particle)
-            self.swarm = new_swarm
+            particles = [self.constrained_path[self.iteration + 1]]
+            particles += [p for p, m in zip(self.swarm.particles, multiplicities.tolist()) for _ in range(m)]
+            self.swarm = ParticleSwarm.of(particles, [log_uniform_weight] * len(particles))
 
     def _update_swarm(self):
         log_W = self.swarm.log_weights
         retained = self.constrained_path[self.iteration + 1]
         particles = [retained] + self._propose_all(self.swarm.particles[1:])
-        new_swarm = ParticleSwarm()
-        for parent_log_W, particle, log_w in zip(log_W, particles, self._get_log_ws(particles)):
-            new_swarm.add_particle(parent_log_W + log_w, particle)
-        self.swarm = new_swarm
+        self.swarm = ParticleSwarm.of(particles, [a + b for a, b in zip(log_W, self._get_log_ws(particles))])
 
 
 class UnconditionalSMCSampler(object):

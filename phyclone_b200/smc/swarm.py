@@ -201,6 +201,14 @@ class ParticleSwarm(object):
         weights /= weights.sum()
         return weights
 
+    @staticmethod
+    def of(particles, log_weights):
+        """Swarm holding the given particles / unnormalised log weights (lists; taken over, not copied)."""
+        sw = ParticleSwarm()
+        sw.particles = particles
+        sw._unnormalized_log_weights = log_weights
+        return sw
+
     def add_particle(self, log_weight, particle):
         self.particles.append(particle)
         self._unnormalized_log_weights.append(log_weight)

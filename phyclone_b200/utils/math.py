@@ -12,6 +12,9 @@ from functools import lru_cache
 
 import numpy as np
 
+from .._hostmod import load as _load_hostmod
+
+_hm = _load_hostmod()
 _libm = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
 _libm.lgamma.restype = ctypes.c_double
 _libm.lgamma.argtypes = [ctypes.c_double]
@@ -40,15 +43,8 @@ def cached_log_binomial_coefficient(n, x):
 
 
 def log_sum_exp(log_X):
-    """utils/math.py:102-118"""
-    log_X = np.asarray(log_X, dtype=np.float64)
-    max_exp = float(np.max(log_X))
-    if math.isinf(max_exp):
-        return max_exp
-    total = 0.0
-    for x in log_X.tolist():
-        total += math.exp(x - max_exp)
-    return math.log(total) + max_exp
+    """utils/math.py:102-118 (max shift, terms summed left to right with libm exp / log): host extension."""
+    return _hm.log_sum_exp(np.ascontiguousarray(log_X, dtype=np.float64))
 
 
 def log_normalize(log_p):
