@@ -171,6 +171,12 @@ int pcb_run_plan_dev(const pcb_arena* arena, const int32_t* packed_host, int64_t
                      const int32_t* plan, int32_t n_rec, double prior, double* rows_lse, double* rows_last,
                      int64_t n_slots, double* sums_dev, double* sums_host, void* const* events, void* stream);
 
+/* Kernel timing for roofline figures: between begin and end every pcb_node_jobs_dev launch (also inside
+ * pcb_run_plan_dev) is bracketed by a CUDA event pair on its stream; end synchronises the device and returns the summed
+ * durations and the number of launches recorded (at most max_launches). */
+int pcb_timing_begin(int32_t max_launches);
+int pcb_timing_end(double* total_ms, int64_t* n_launches);
+
 /* MAP cellular prevalences of B trees: the max-plus twin of the node fold with back-pointers.
  *   process_trace/map.py:48-64 compute_max_likelihood, :67-93 compute_log_S (prefix max, ties to the earliest
  *   index), :96-134 compute_log_D / _compute_log_D_n (max_j child[j] + D[i-j], ties to the largest j; D starts at 0),

@@ -373,8 +373,61 @@ int pcb_tile_add_dev(const pcb_arena* a, const int32_t* a_ids, const int32_t* b_
   return PCB_OK;
 }
 
+// ---- kernel timing for the roofline figure: CUDA event pairs around every node-jobs launch, owned by the library
+// so that the instrumented region pays two cudaEventRecord calls per launch and nothing on the Python side
+struct JobTiming {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;  // 2 per recorded launch
+  size_t used = 0, cap = 0;
+};
+JobTiming g_timing;
+
+int pcb_timing_begin(int32_t max_launches) {
+  if (max_launches < 1) return fail(PCB_ERR_ARG, "timing: max_launches must be positive");
+  const size_t want = 2 * (size_t)max_launches;
+  while (g_timing.ev.size() < want) {
+    cudaEvent_t e;
+    PCB_CUDA(cudaEventCreate(&e));
+    g_timing.ev.push_back(e);
+  }
+  g_timing.cap = want;
+  g_timing.used = 0;
+  g_timing.on = true;
+  return PCB_OK;
+}
+
+int pcb_timing_end(double* total_ms, int64_t* n_launches) {
+  g_timing.on = false;
+  PCB_CUDA(cudaDeviceSynchronize());
+  double total = 0.0;
+  for (size_t i = 0; i + 1 < g_timing.used; i += 2) {
+    float ms = 0.f;
+    PCB_CUDA(cudaEventElapsedTime(&ms, g_timing.ev[i], g_timing.ev[i + 1]));
+    total += ms;
+  }
+  if (total_ms) *total_ms = total;
+  if (n_launches) *n_launches = (int64_t)(g_timing.used / 2);
+  g_timing.used = 0;
+  return PCB_OK;
+}
+
+static int node_jobs_launch(const pcb_arena* a, const int32_t* jobs_dev, const int32_t* children_dev, int64_t n_jobs,
+                            double prior, double* rows_lse, double* rows_last, void* stream);
+
 int pcb_node_jobs_dev(const pcb_arena* a, const int32_t* jobs_dev, const int32_t* children_dev, int64_t n_jobs,
                       double prior, double* rows_lse, double* rows_last, void* stream) {
+  const bool timed = g_timing.on && n_jobs > 0 && g_timing.used + 2 <= g_timing.cap;
+  if (timed) PCB_CUDA(cudaEventRecord(g_timing.ev[g_timing.used], (cudaStream_t)stream));
+  const int rc = node_jobs_launch(a, jobs_dev, children_dev, n_jobs, prior, rows_lse, rows_last, stream);
+  if (timed && rc == PCB_OK) {
+    PCB_CUDA(cudaEventRecord(g_timing.ev[g_timing.used + 1], (cudaStream_t)stream));
+    g_timing.used += 2;
+  }
+  return rc;
+}
+
+static int node_jobs_launch(const pcb_arena* a, const int32_t* jobs_dev, const int32_t* children_dev, int64_t n_jobs,
+                            double prior, double* rows_lse, double* rows_last, void* stream) {
   int rc = check_arena(a);
   if (rc) return rc;
   if (n_jobs <= 0) return PCB_OK;

@@ -65,34 +65,8 @@ class DeviceArena:
         self._rows = self._sums = self._sums_host = None
         self._pinned_vals = self._staged_vals = None
         self.staged_bytes = 0  # host->device bytes of job tables / id lists so far
-        self.job_timing = None  # set to a list to record (start_event, end_event, n_jobs, conv_pairs) per launch
-        self._event_pool = []
         self._plan_synced = True
         self._plan_np = self._sums_np = None
-
-    def start_timing(self, n_events=8192):
-        """Time every node-jobs launch with a CUDA event pair from a pre-created pool (creating events inside the
-        measured region would cost more than the launches they time)."""
-        stream = torch.cuda.current_stream(self.device)
-        while len(self._event_pool) < n_events:
-            e = torch.cuda.Event(enable_timing=True)
-            e.record(stream)  # forces creation
-            self._event_pool.append(e)
-        self.job_timing = []
-
-    def stop_timing(self):
-        timing, self.job_timing = self.job_timing, None
-        return timing
-
-    def _event_pair(self):
-        pool = self._event_pool
-        if len(pool) >= 2:
-            return pool.pop(), pool.pop()
-        stream = torch.cuda.current_stream(self.device)
-        pair = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        for e in pair:
-            e.record(stream)  # forces creation: the raw handle is handed to the C library
-        return pair
 
     def grow(self, new_capacity):
         """Enlarge the arena in place (tile ids stay valid): new zero-filled tensors, old content copied over."""
@@ -224,16 +198,9 @@ class DeviceArena:
         pl = pt = None
         if rows is not None:
             pl, pt = rows[0].data_ptr(), rows[1].data_ptr()
-        timing = self.job_timing
-        if timing is not None:
-            e0, e1 = self._event_pair()
-            e0.record(torch.cuda.current_stream(self.device))
         _lib.check(
             self.lib.pcb_node_jobs_dev(C.byref(self.c), base, base + 4 * n * JOB_INTS, n, self.prior, pl, pt, self._stream())
         )
-        if timing is not None:
-            e1.record(torch.cuda.current_stream(self.device))
-            timing.append((e0, e1, n, int(tab[:, 1].sum()) - n))
 
     def run_plan(self, packed, plan, n_slots, plan_raw=None):
         """Execute one flush: `packed` (int32) holds every id list / job table of the batch and is sent to the
@@ -273,21 +240,10 @@ class DeviceArena:
                 self._sums_np = self._sums_host.numpy()
             pl, pt = self._rows[0].data_ptr(), self._rows[1].data_ptr()
             sd, sh = self._sums.data_ptr(), self._sums_host.data_ptr()
-        timing = self.job_timing
-        events = None
-        if timing is not None:
-            pairs = [self._event_pair() for _ in range(n_rec)]
-            events = (C.c_void_p * (2 * n_rec))(*[e.cuda_event for pr in pairs for e in pr])
         _lib.check(self.lib.pcb_run_plan_dev(C.byref(self.c), st[0].data_ptr(), n_ints, st[1].data_ptr(), plan_raw, n_rec,
-                                             self.prior, pl, pt, n_slots, sd, sh, events,
+                                             self.prior, pl, pt, n_slots, sd, sh, None,
                                              C.c_void_p(stream_obj.cuda_stream)))
         self._plan_synced = bool(n_slots)
-        if timing is not None:
-            for (e0, e1), rec in zip(pairs, plan):
-                if rec[0] != "add":
-                    timing.append((e0, e1, rec[2], rec[4]))
-                else:
-                    self._event_pool.extend((e0, e1))
         if not n_slots:
             return None
         return self._sums_np[: 2 * n_slots].reshape(2, n_slots)

@@ -220,3 +220,15 @@ def fp64_peak(iters=4096):
 
 def launch_count():
     return int(_lib.load().pcb_launch_count())
+
+
+def timing_begin(max_launches=1 << 16):
+    """Bracket every node-jobs launch with a CUDA event pair (library-owned) until `timing_end`."""
+    _lib.check(_lib.require_device().pcb_timing_begin(int(max_launches)))
+
+
+def timing_end():
+    """(summed kernel milliseconds, number of launches recorded) since `timing_begin`; synchronises the device."""
+    ms, n = C.c_double(0.0), C.c_int64(0)
+    _lib.check(_lib.require_device().pcb_timing_end(C.byref(ms), C.byref(n)))
+    return ms.value, n.value

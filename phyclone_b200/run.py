@@ -99,6 +99,17 @@ class Chain(object):
                                                                   sum(node_sizes))
         self.iteration += 1
 
+    def snapshot(self):
+        """State needed to repeat the coming iterations exactly (the carried tree is never mutated by a step)."""
+        return {"tree": self.tree, "rng": self.rng.bit_generator.state, "alpha": self.tree_dist.prior.alpha,
+                "iteration": self.iteration}
+
+    def restore(self, snap):
+        self.tree = snap["tree"]
+        self.rng.bit_generator.state = snap["rng"]
+        self.tree_dist.prior.alpha = snap["alpha"]
+        self.iteration = snap["iteration"]
+
     def log_p_one(self):
         return self.tree_dist.log_p_one(self.tree)
 

@@ -19,7 +19,6 @@ class FakeArena:
         self.prior = -float(np.log(G))
         self.tiles = {}
         self.staged_bytes = 0
-        self.job_timing = None
 
     def grow(self, new_capacity):
         self.capacity = self.alloc.capacity = int(new_capacity)

@@ -14,7 +14,6 @@ class NullArena:
         self.alloc = TileAllocator(self.capacity)
         self.prior = -float(np.log(G))
         self.staged_bytes = 0
-        self.job_timing = None
         self._n = 0
 
     def grow(self, new_capacity):
