@@ -48,27 +48,74 @@ def chain_rng(rank, world):
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock, power and throttle reasons sampled DURING the timed region.  NVML in-process (a few microseconds per
+    sample); spawning `nvidia-smi` five times a second measurably slowed the launch-bound step it was watching, so
+    that is only the fallback."""
+
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index = index
-        self.rows = []
+        self.rows = []  # [sm_mhz, sm_max_mhz, power_w, hw_slowdown, hw_thermal, sw_thermal, sw_power_cap]
         self._stop = threading.Event()
         self._thr = threading.Thread(target=self._run, daemon=True)
+        self._nvml = self._handle = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            uuid = None
+            try:
+                import torch
+
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+            except Exception:  # noqa: BLE001
+                pass
+            handle = None
+            if uuid:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    u = pynvml.nvmlDeviceGetUUID(h)
+                    u = u.decode() if isinstance(u, bytes) else u
+                    if uuid in u:
+                        handle = h
+                        break
+            self._handle = handle if handle is not None else pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._nvml = pynvml
+        except Exception:  # noqa: BLE001
+            self._nvml = None
+
+    def _sample_nvml(self):
+        n, h = self._nvml, self._handle
+        sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+        sm_max = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+        power = n.nvmlDeviceGetPowerUsage(h) / 1000.0
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:  # noqa: BLE001
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        flag = lambda bit: "Active" if r & bit else "Not Active"  # noqa: E731
+        self.rows.append([str(sm), str(sm_max), str(power), flag(0x8), flag(0x40), flag(0x20), flag(0x4)])
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        parts = [x.strip() for x in out.strip().split(",")]
+        if len(parts) >= 7:
+            self.rows.append(parts)
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [x.strip() for x in out.strip().split(",")]
-                if len(parts) >= 7:
-                    self.rows.append(parts)
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:  # noqa: BLE001
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.1 if self._nvml is not None else 1.0)
 
     def __enter__(self):
         self._thr.start()
@@ -80,14 +127,15 @@ class ClockSampler:
 
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples"]}
         sm = sorted(float(r[0]) for r in self.rows)
         reasons = []
         for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
             if any(r[col].lower().startswith("active") for r in self.rows):
                 reasons.append(name)
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows), "power_w_max": max(float(r[2]) for r in self.rows)}
+                "samples": len(self.rows), "power_w_max": max(float(r[2]) for r in self.rows),
+                "source": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
 # ----------------------------------------------------------------------------- CPU arms
