@@ -171,6 +171,10 @@ int pcb_run_plan_dev(const pcb_arena* arena, const int32_t* packed_host, int64_t
                      const int32_t* plan, int32_t n_rec, double prior, double* rows_lse, double* rows_last,
                      int64_t n_slots, double* sums_dev, double* sums_host, void* const* events, void* stream);
 
+/* Host-side split of all synchronising pcb_run_plan_dev calls so far: seconds spent enqueueing (copies + launches) and
+ * seconds spent waiting for the stream. */
+int pcb_plan_stats(double* enqueue_s, double* sync_s, int64_t* flushes);
+
 /* Kernel timing for roofline figures: between begin and end every pcb_node_jobs_dev launch (also inside
  * pcb_run_plan_dev) is bracketed by a CUDA event pair on its stream; end synchronises the device and returns the summed
  * durations and the number of launches recorded (at most max_launches). */

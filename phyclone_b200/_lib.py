@@ -53,6 +53,7 @@ SIGNATURES = {
     "pcb_tile_add_dev": (C.c_int, [C.POINTER(Arena), _P, _P, _P, _i64, _f64, _f64, _P]),
     "pcb_node_jobs_dev": (C.c_int, [C.POINTER(Arena), _P, _P, _i64, _f64, _P, _P, _P]),
     "pcb_run_plan_dev": (C.c_int, [C.POINTER(Arena), _P, _i64, _P, _P, _i32, _f64, _P, _P, _i64, _P, _P, _P, _P]),
+    "pcb_plan_stats": (C.c_int, [C.POINTER(_f64), C.POINTER(_f64), C.POINTER(_i64)]),
     "pcb_timing_begin": (C.c_int, [_i32]),
     "pcb_timing_end": (C.c_int, [C.POINTER(_f64), C.POINTER(_i64)]),
     "pcb_reduce_rows_dev": (C.c_int, [_P, _i64, _i32, _P, _P]),

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <chrono>
 #include <vector>
 
 #include "../../include/phyclone_b200.h"
@@ -36,7 +37,7 @@ int fail(int code, const std::string& msg) {
   } while (0)
 
 // ---- layout -------------------------------------------------------------------
-const int kStrips[] = {5, 7, 9, 13, 17};
+const int kStrips[] = {3, 5, 7, 9, 13, 17};
 
 int jobs_double_b() {
   static int v = -1;
@@ -471,6 +472,8 @@ static int node_jobs_launch(const pcb_arena* a, const int32_t* jobs_dev, const i
   const size_t smem = jobs_smem_bytes(l.rows_per_cta, l.pitch);
   cudaStream_t st = (cudaStream_t)stream;
   switch (l.strip) {
+    case 3:
+      return launch_jobs_L<3>(kp, n_jobs, threads, smem, st);
     case 5:
       return launch_jobs_L<5>(kp, n_jobs, threads, smem, st);
     case 7:
@@ -493,6 +496,9 @@ int pcb_reduce_rows_dev(const double* rows_dev, int64_t n_slots, int32_t S, doub
   return PCB_OK;
 }
 
+double g_plan_enqueue_s = 0.0, g_plan_sync_s = 0.0;
+int64_t g_plan_flushes = 0;
+
 // One flush of the host's tile store in ONE call: stage the packed id lists / job tables (pinned host -> device),
 // run every launch of the plan in dependency order, reduce the score rows and copy the sums back.
 // plan: n_rec records of 6 int32: {kind (0 = tile add, 1 = node jobs), offset into packed, n, n_kids, negate, 0}.
@@ -507,6 +513,7 @@ int pcb_run_plan_dev(const pcb_arena* a, const int32_t* packed_host, int64_t n_i
   if (n_slots > 0 && (!rows_lse || !rows_last || !sums_dev || !sums_host))
     return fail(PCB_ERR_ARG, "run_plan: score buffers missing");
   cudaStream_t st = (cudaStream_t)stream;
+  const auto t_begin = std::chrono::steady_clock::now();
   PCB_CUDA(cudaMemcpyAsync(packed_dev, packed_host, (size_t)n_ints * 4, cudaMemcpyHostToDevice, st));
   for (int r = 0; r < n_rec; ++r) {
     const int32_t* rec = plan + 6 * r;
@@ -526,8 +533,21 @@ int pcb_run_plan_dev(const pcb_arena* a, const int32_t* packed_host, int64_t n_i
     if ((rc = pcb_reduce_rows_dev(rows_lse, n_slots, a->layout.S, sums_dev, stream))) return rc;
     if ((rc = pcb_reduce_rows_dev(rows_last, n_slots, a->layout.S, sums_dev + n_slots, stream))) return rc;
     PCB_CUDA(cudaMemcpyAsync(sums_host, sums_dev, (size_t)n_slots * 16, cudaMemcpyDeviceToHost, st));
+    const auto t_enq = std::chrono::steady_clock::now();
     PCB_CUDA(cudaStreamSynchronize(st));
+    const auto t_end = std::chrono::steady_clock::now();
+    g_plan_enqueue_s += std::chrono::duration<double>(t_enq - t_begin).count();
+    g_plan_sync_s += std::chrono::duration<double>(t_end - t_enq).count();
+    ++g_plan_flushes;
   }
+  return PCB_OK;
+}
+
+// where a synchronising flush spends its time on the host: enqueueing (copies + launches) vs waiting for the stream
+int pcb_plan_stats(double* enqueue_s, double* sync_s, int64_t* flushes) {
+  if (enqueue_s) *enqueue_s = g_plan_enqueue_s;
+  if (sync_s) *sync_s = g_plan_sync_s;
+  if (flushes) *flushes = g_plan_flushes;
   return PCB_OK;
 }
 

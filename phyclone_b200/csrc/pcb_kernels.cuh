@@ -91,28 +91,26 @@ __device__ __forceinline__ void conv_step(ConvLane<L>& st, double (&X)[L], doubl
   st.bn += L;
   st.an -= L;
   --st.left;
-  if (st.second) {
-    // The strip switch happens at a different body for every lane of a row, so the warp runs this block once per
-    // lane: keep it small.  One body before the switch the refill pointers are redirected (predicated, no branch)
-    // so that the regular in-body refills already fetch the second strip's entering elements and b[0..L);
-    // at the switch only the new window is loaded.
-    const bool redirect = st.left == 1;
-    st.an = redirect ? st.a + st.k2 - 1 : st.an;
-    st.bn = redirect ? st.b : st.bn;
-    if (st.left == 0) {  // Y is the window of the next step, X already holds its entering elements
-      st.second = false;
-      st.left = st.k2 / L + 1;
+  // The strip switch happens at a different body for every lane of a row, so the warp runs the switch block once per
+  // lane: keep it small, and keep everything around it branch-free (a lone warp pays ~15 cycles per taken branch).
+  // One body before the switch the refill pointers are redirected (predicated) so that the regular in-body refills
+  // already fetch the second strip's entering elements and b[0..L); at the switch only the new window is loaded.
+  const bool redirect = st.second && st.left == 1;
+  const bool sw = st.second && st.left == 0;
+  st.an = redirect ? st.a + st.k2 - 1 : st.an;
+  st.bn = redirect ? st.b : st.bn;
+  st.active = st.second || st.left != 0;  // a strip without a successor has run out
+  if (sw) {  // Y is the window of the next step, X already holds its entering elements
+    st.second = false;
+    st.left = st.k2 / L + 1;
 #pragma unroll
-      for (int i = 0; i < L; ++i) {
-        y1[i] = y2[i];
-        y2[i] = 0.0;
-        Y[i] = st.a[st.k2 + i];
-      }
-      st.an = st.a + st.k2 - 1 - L;
-      st.bn = st.b + L;
+    for (int i = 0; i < L; ++i) {
+      y1[i] = y2[i];
+      y2[i] = 0.0;
+      Y[i] = st.a[st.k2 + i];
     }
-  } else if (st.left == 0) {
-    st.active = false;
+    st.an = st.a + st.k2 - 1 - L;
+    st.bn = st.b + L;
   }
 }
 
@@ -218,6 +216,7 @@ __device__ __forceinline__ void row_prefix_lse(const double* x, double* out, int
   run.s = __shfl_up_sync(0xffffffffu, inc.s, 1);
   if (lir == 0) run = LsePair{-INFINITY, 0.0};
   if (row_ok)
+#pragma unroll 4
     for (int k = kbeg; k < kend; ++k) {
       run = lse_combine(run, LsePair{x[k], 1.0});
       out[k] = (run.m == -INFINITY) ? -INFINITY : run.m + log(run.s);
@@ -239,7 +238,7 @@ constexpr int kSmemHead = 256;
 constexpr int kSmemTail = 256;
 
 template <int L>
-__global__ void __launch_bounds__(32) node_jobs_kernel(const JobKernelParams p) {
+__global__ void __launch_bounds__(32, (L == 13) ? 12 : 1) node_jobs_kernel(const JobKernelParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
   const int rows_elems = p.RB * p.pitch;
@@ -272,12 +271,17 @@ __global__ void __launch_bounds__(32) node_jobs_kernel(const JobKernelParams p) 
   }
   __syncwarp();
 
-  const int c0 = p.children[coff];
+  // child tile ids: one coalesced load per 32 children, handed out by shuffles.  (Reading children[coff + j] when
+  // step j needs it put two dependent global loads -- id, then row maximum / TMA source -- on the serial path of
+  // every fold step: ~1 us of the ~3.3 us a lone warp spends per step.)
+  int my_child = (tid < C) ? p.children[coff + tid] : 0;
+  const int c0 = __shfl_sync(0xffffffffu, my_child, 0);
+  const int c1_id = __shfl_sync(0xffffffffu, my_child, 1);
   if (tid == 0) {
     mbar_expect_tx(&bars[0], bytes);
     tma_load_1d(bufA, p.lin + (size_t)c0 * p.tile_elems + (size_t)r0 * pitch, bytes, &bars[0]);
     if (C >= 2) {
-      const int c1 = p.children[coff + 1];
+      const int c1 = c1_id;
       mbar_expect_tx(&bars[1], bytes);
       tma_load_1d(bufB0, p.lin + (size_t)c1 * p.tile_elems + (size_t)r0 * pitch, bytes, &bars[1]);
     } else if (!shortcut) {
@@ -298,15 +302,21 @@ __global__ void __launch_bounds__(32) node_jobs_kernel(const JobKernelParams p) 
   // ---- left fold over the children (tree/utils.py:33-47) --------------------------
   const bool db = p.double_b;
   for (int j = 1; j < C; ++j) {
+    if ((j & 31) == 0) my_child = (j + tid < C) ? p.children[coff + j + tid] : 0;  // next 32 ids
+    const int cj = __shfl_sync(0xffffffffu, my_child, j & 31);
+    // id of the child after this one (the refill issued during this step) and this child's row maximum: both are
+    // requested here, a whole convolution before they are needed
+    int cnext = 0;
+    if (j + 1 < C) cnext = ((j + 1) & 31) ? __shfl_sync(0xffffffffu, my_child, (j + 1) & 31) : p.children[coff + j + 1];
+    const double mB = row_ok ? p.rmax[(size_t)cj * p.S + row] : 0.0;
     double* Bcur = (!db || (j & 1)) ? bufB0 : bufB1;
     uint64_t* bbar = (!db || (j & 1)) ? &bars[1] : &bars[2];
     mbar_wait(bbar, db ? (((j - 1) >> 1) & 1) : ((j - 1) & 1));
     if (db && j + 1 < C && tid == 0) {  // prefetch the next operand into the buffer step j-1 released
       double* Bnext = (j & 1) ? bufB1 : bufB0;
       uint64_t* nbar = (j & 1) ? &bars[2] : &bars[1];
-      const int cn = p.children[coff + j + 1];
       mbar_expect_tx(nbar, bytes);
-      tma_load_1d(Bnext, p.lin + (size_t)cn * p.tile_elems + (size_t)r0 * pitch, bytes, nbar);
+      tma_load_1d(Bnext, p.lin + (size_t)cnext * p.tile_elems + (size_t)r0 * pitch, bytes, nbar);
     }
     const double* b_row = Bcur + lrow * pitch + lead;
     double y1[L], y2[L];
@@ -315,9 +325,8 @@ __global__ void __launch_bounds__(32) node_jobs_kernel(const JobKernelParams p) 
       __syncwarp();
       if (tid == 0) {
         fence_proxy_async();
-        const int cn = p.children[coff + j + 1];
         mbar_expect_tx(&bars[1], bytes);
-        tma_load_1d(bufB0, p.lin + (size_t)cn * p.tile_elems + (size_t)r0 * pitch, bytes, &bars[1]);
+        tma_load_1d(bufB0, p.lin + (size_t)cnext * p.tile_elems + (size_t)r0 * pitch, bytes, &bars[1]);
       }
     }
     // floor (tree/utils.py:77) and row maximum, all in registers.  Outputs past G (only the last
@@ -339,7 +348,6 @@ __global__ void __launch_bounds__(32) node_jobs_kernel(const JobKernelParams p) 
 #pragma unroll
       for (int i = 0; i + w < L; i += 2 * w) mx[i] = (mx[i] > mx[i + w]) ? mx[i] : mx[i + w];
     const double ymax = group_max(mx[0], P);
-    const double mB = row_ok ? p.rmax[(size_t)p.children[coff + j] * p.S + row] : 0.0;
     double scale = 1.0;
     bool tiny = false;
     if (j < C - 1) {
@@ -401,11 +409,13 @@ __global__ void __launch_bounds__(32) node_jobs_kernel(const JobKernelParams p) 
         for (int k = kbeg; k < kend; ++k) loc += yrow[k];
       double run = group_excl_scan(loc, P, lir);
       if (row_ok)
+    #pragma unroll 4
         for (int k = kbeg; k < kend; ++k) {
           run += yrow[k];
           yrow[k] = log(run) + M;
         }
     } else if (row_ok) {
+  #pragma unroll 4
       for (int k = lir; k < G; k += P) yrow[k] = log(yrow[k]) + M;
     }
   } else {
@@ -422,12 +432,24 @@ __global__ void __launch_bounds__(32) node_jobs_kernel(const JobKernelParams p) 
   double vmax = -INFINITY;
   if (row_ok) {
     const double* bptr = (base >= 0) ? p.lg + (size_t)base * p.tile_elems + (size_t)row * pitch + lead : nullptr;
-    for (int k = lir; k < G; k += P) {
-      double v = yrow[k];
-      if (bptr) v = bptr[k] + v;
-      v += addc;
-      yrow[k] = v;
-      vmax = fmax(vmax, v);
+    // the log_p tile comes from global memory: four loads in flight per lane instead of one load-use round trip per
+    // element (a third of the stall samples of a live launch sat on this line)
+    for (int k = lir; k < G; k += 4 * P) {
+      double bb[4] = {0.0, 0.0, 0.0, 0.0};
+      if (bptr) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          if (k + t * P < G) bb[t] = bptr[k + t * P];
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (k + t * P < G) {
+          double v = yrow[k + t * P];
+          if (bptr) v = bb[t] + v;
+          v += addc;
+          yrow[k + t * P] = v;
+          vmax = fmax(vmax, v);
+        }
     }
   }
   vmax = group_max(vmax, P);
@@ -435,6 +457,7 @@ __global__ void __launch_bounds__(32) node_jobs_kernel(const JobKernelParams p) 
   if (row_ok) {
     double* olg = (outt >= 0) ? p.lg + (size_t)outt * p.tile_elems + (size_t)row * pitch + lead : nullptr;
     double* olin = (outt >= 0) ? p.lin + (size_t)outt * p.tile_elems + (size_t)row * pitch + lead : nullptr;
+#pragma unroll 4
     for (int k = lir; k < G; k += P) {
       const double v = yrow[k];
       const double e = (v == -INFINITY) ? 0.0 : exp(v - vmax);
@@ -654,11 +677,13 @@ __global__ void __launch_bounds__(128) node_jobs_wide_kernel(const JobKernelPara
       for (int k = kbeg; k < kend; ++k) loc += yrow[k];
     double run = group_excl_scan(loc, P, lir);
     if (cs)
+  #pragma unroll 4
       for (int k = kbeg; k < kend; ++k) {
         run += yrow[k];
         yrow[k] = log(run) + Me;
       }
     if (full && eC >= 2 && !scan)
+  #pragma unroll 4
       for (int k = lir; k < G; k += P) yrow[k] = log(yrow[k]) + Me;
     row_prefix_lse(brow, yrow, G, P, lir, full && eC == 1 && scan);
     if (full && eC == 1 && !scan)
@@ -668,12 +693,24 @@ __global__ void __launch_bounds__(128) node_jobs_wide_kernel(const JobKernelPara
   double vmax = -INFINITY;
   if (full) {
     const double* bptr = (base >= 0) ? p.lg + (size_t)base * p.tile_elems + (size_t)er * pitch + lead : nullptr;
-    for (int k = lir; k < G; k += P) {
-      double v = yrow[k];
-      if (bptr) v = bptr[k] + v;
-      v += addc;
-      yrow[k] = v;
-      vmax = fmax(vmax, v);
+    // the log_p tile comes from global memory: four loads in flight per lane instead of one load-use round trip per
+    // element (a third of the stall samples of a live launch sat on this line)
+    for (int k = lir; k < G; k += 4 * P) {
+      double bb[4] = {0.0, 0.0, 0.0, 0.0};
+      if (bptr) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          if (k + t * P < G) bb[t] = bptr[k + t * P];
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (k + t * P < G) {
+          double v = yrow[k + t * P];
+          if (bptr) v = bb[t] + v;
+          v += addc;
+          yrow[k + t * P] = v;
+          vmax = fmax(vmax, v);
+        }
     }
   }
   vmax = group_max(vmax, P);
@@ -681,6 +718,7 @@ __global__ void __launch_bounds__(128) node_jobs_wide_kernel(const JobKernelPara
   if (full) {
     double* olg = (outt >= 0) ? p.lg + (size_t)outt * p.tile_elems + (size_t)er * pitch + lead : nullptr;
     double* olin = (outt >= 0) ? p.lin + (size_t)outt * p.tile_elems + (size_t)er * pitch + lead : nullptr;
+#pragma unroll 4
     for (int k = lir; k < G; k += P) {
       const double v = yrow[k];
       const double e = (v == -INFINITY) ? 0.0 : exp(v - vmax);

@@ -232,3 +232,10 @@ def timing_end():
     ms, n = C.c_double(0.0), C.c_int64(0)
     _lib.check(_lib.require_device().pcb_timing_end(C.byref(ms), C.byref(n)))
     return ms.value, n.value
+
+
+def plan_stats():
+    """(seconds enqueueing, seconds waiting for the stream, flushes) over all synchronising flushes of this process."""
+    a, b, n = C.c_double(0.0), C.c_double(0.0), C.c_int64(0)
+    _lib.check(_lib.require_device().pcb_plan_stats(C.byref(a), C.byref(b), C.byref(n)))
+    return a.value, b.value, n.value

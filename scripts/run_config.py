@@ -70,6 +70,8 @@ def main():
            "it_per_s": float(1.0 / per_it.mean()), "stats": res["stats"],
            "final_log_p_one": res["trace"][-1]["log_p_one"],
            "n_nodes": len([k for k in res["trace"][-1]["tree"]["node_data"] if k not in ("root", -1)])}
+    enq, syn, nfl = ops.plan_stats()
+    out["flush_split"] = {"enqueue_s": enq, "sync_s": syn, "flushes": nfl}
     print(json.dumps(out))
 
 
