@@ -7,6 +7,7 @@
 #define PY_SSIZE_T_CLEAN
 #include <Python.h>
 
+#include <chrono>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -44,6 +45,8 @@ struct Book {
   std::vector<char>* sc_ready;
   std::vector<int>* pending_scores;   // score ids in slot order of the pending batch
   int64_t n_adds, n_jobs, n_scores, n_hits, n_pairs;
+  int64_t n_flushes, n_launches, d2h_bytes, staged_ints;  // of the in-extension flush path (run)
+  double run_s;
 };
 
 inline int level_of(Book* b, int id) { return (size_t)id < b->level->size() ? (*b->level)[id] : 0; }
@@ -104,6 +107,8 @@ int Book_init(Book* self, PyObject* args, PyObject*) {
   self->sc_ready = new std::vector<char>();
   self->pending_scores = new std::vector<int>();
   self->n_adds = self->n_jobs = self->n_scores = self->n_hits = self->n_pairs = 0;
+  self->n_flushes = self->n_launches = self->d2h_bytes = self->staged_ints = 0;
+  self->run_s = 0.0;
   return 0;
 }
 
@@ -268,15 +273,15 @@ PyObject* Book_has_pending(Book* self, PyObject*) {
 // pack() -> (packed int32 bytes, plan list, n_slots)
 //   plan entries: ("add", offset, n, sign) | ("jobs", offset, n, n_kids, conv_pairs); same layout as
 //   engine.DeviceArena.run_plan expects: adds [a | b | out], jobs [n x 8 table | kids]
-PyObject* Book_pack(Book* self, PyObject*) {
+// packs the pending batch: `packed` = every id list / job table, `raw` = the launch plan as 6 int32 per record
+// (what pcb_run_plan_dev reads), `plan` (may be NULL) = the same plan as a Python list for engine.run_plan
+bool pack_core(Book* self, std::vector<int32_t>& packed, std::vector<int32_t>& raw, PyObject* plan) {
   int max_level = 0;
   for (const PendAdd& a : *self->adds) max_level = std::max(max_level, a.level);
   for (const PendJob& j : *self->jobs) max_level = std::max(max_level, j.level);
-  std::vector<int32_t> packed;
+  packed.clear();
+  raw.clear();
   packed.reserve(self->adds->size() * 3 + self->jobs->size() * 8 + self->kids->size());
-  PyObject* plan = PyList_New(0);
-  if (!plan) return nullptr;
-  std::vector<int32_t> raw;  // the same plan as 6 int32 per record, for pcb_run_plan_dev
   std::vector<const PendAdd*> sel;
   std::vector<const PendJob*> selj;
   for (int lv = 1; lv <= max_level; ++lv) {
@@ -289,11 +294,14 @@ PyObject* Book_pack(Book* self, PyObject*) {
       for (const PendAdd* a : sel) packed.push_back(a->a);
       for (const PendAdd* a : sel) packed.push_back(a->b);
       for (const PendAdd* a : sel) packed.push_back(a->out);
-      PyObject* rec = Py_BuildValue("(snnd)", "add", (Py_ssize_t)off, (Py_ssize_t)n, neg ? -1.0 : 1.0);
       const int32_t rr[6] = {0, (int32_t)off, (int32_t)n, 0, neg, 0};
       raw.insert(raw.end(), rr, rr + 6);
-      PyList_Append(plan, rec);
-      Py_DECREF(rec);
+      if (plan) {
+        PyObject* rec = Py_BuildValue("(snnd)", "add", (Py_ssize_t)off, (Py_ssize_t)n, neg ? -1.0 : 1.0);
+        if (!rec) return false;
+        PyList_Append(plan, rec);
+        Py_DECREF(rec);
+      }
       self->n_adds += (int64_t)n;
     }
     selj.clear();
@@ -310,19 +318,92 @@ PyObject* Book_pack(Book* self, PyObject*) {
     }
     for (const PendJob* j : selj)
       packed.insert(packed.end(), self->kids->begin() + j->kid_off, self->kids->begin() + j->kid_off + j->n_kids);
-    PyObject* rec = Py_BuildValue("(snnnn)", "jobs", (Py_ssize_t)off, (Py_ssize_t)n, (Py_ssize_t)koff,
-                                  (Py_ssize_t)(koff - (int32_t)n));
     const int32_t rr[6] = {1, (int32_t)off, (int32_t)n, koff, 0, 0};
     raw.insert(raw.end(), rr, rr + 6);
-    PyList_Append(plan, rec);
-    Py_DECREF(rec);
+    if (plan) {
+      PyObject* rec = Py_BuildValue("(snnnn)", "jobs", (Py_ssize_t)off, (Py_ssize_t)n, (Py_ssize_t)koff,
+                                    (Py_ssize_t)(koff - (int32_t)n));
+      if (!rec) return false;
+      PyList_Append(plan, rec);
+      Py_DECREF(rec);
+    }
     self->n_jobs += (int64_t)n;
     self->n_pairs += (int64_t)(koff - (int32_t)n);
+  }
+  return true;
+}
+
+PyObject* Book_pack(Book* self, PyObject*) {
+  std::vector<int32_t> packed, raw;
+  PyObject* plan = PyList_New(0);
+  if (!plan) return nullptr;
+  if (!pack_core(self, packed, raw, plan)) {
+    Py_DECREF(plan);
+    return nullptr;
   }
   PyObject* bytes = PyBytes_FromStringAndSize((const char*)packed.data(), (Py_ssize_t)(packed.size() * 4));
   PyObject* raw_bytes = PyBytes_FromStringAndSize((const char*)raw.data(), (Py_ssize_t)(raw.size() * 4));
   PyObject* out = Py_BuildValue("(NNnN)", bytes, plan, (Py_ssize_t)self->pending_scores->size(), raw_bytes);
   return out;
+}
+
+void take_scores(Book* self, const double* p) {
+  const size_t n = self->pending_scores->size();
+  for (size_t s = 0; s < n; ++s) {
+    const int sid = (*self->pending_scores)[s];
+    (*self->sc_lse)[sid] = p[s];
+    (*self->sc_last)[sid] = p[n + s];
+    (*self->sc_ready)[sid] = 1;
+  }
+  self->n_scores += (int64_t)n;
+}
+
+// run(run_plan_fn, last_error_fn, arena, host, host_cap_ints, dev, prior, rows_lse, rows_last, slot_cap, sums_dev,
+//     sums_host, stream) -> None | (ints needed, slots needed)
+//   The whole flush without leaving the extension: pack, copy into the pinned staging buffer, ONE call of
+//   pcb_run_plan_dev (through its address in libphyclone_b200.so), read the scores back.  Returns the sizes
+//   instead when a buffer is too small or the batch has no score to wait for; the caller then takes the generic
+//   path (TileStore.flush), which also (re)allocates.  All addresses are plain integers.
+typedef int (*run_plan_fn)(const void*, const int32_t*, int64_t, int32_t*, const int32_t*, int32_t, double, double*, double*,
+                           int64_t, double*, double*, void* const*, void*);
+typedef const char* (*last_error_fn)(void);
+
+PyObject* Book_run(Book* self, PyObject* args) {
+  unsigned long long fn_a, err_a, arena_a, host_a, dev_a, rows_l_a, rows_t_a, sums_dev_a, sums_host_a, stream_a;
+  long long host_cap, slot_cap;
+  double prior;
+  if (!PyArg_ParseTuple(args, "KKKKLKdKKLKKK", &fn_a, &err_a, &arena_a, &host_a, &host_cap, &dev_a, &prior, &rows_l_a,
+                        &rows_t_a, &slot_cap, &sums_dev_a, &sums_host_a, &stream_a))
+    return nullptr;
+  const long long n_ints = (long long)(self->adds->size() * 3 + self->jobs->size() * 8 + self->kids->size());
+  const long long n_slots = (long long)self->pending_scores->size();
+  if (n_slots == 0 || n_ints > host_cap || n_slots > slot_cap || n_ints == 0)
+    return Py_BuildValue("(LL)", n_ints, n_slots);
+  std::vector<int32_t> packed, raw;
+  if (!pack_core(self, packed, raw, nullptr)) return nullptr;
+  std::memcpy((void*)(uintptr_t)host_a, packed.data(), packed.size() * 4);
+  const auto t0 = std::chrono::steady_clock::now();
+  int rc;
+  Py_BEGIN_ALLOW_THREADS
+  rc = ((run_plan_fn)(uintptr_t)fn_a)((const void*)(uintptr_t)arena_a, (const int32_t*)(uintptr_t)host_a,
+                                      (int64_t)packed.size(), (int32_t*)(uintptr_t)dev_a, raw.data(),
+                                      (int32_t)(raw.size() / 6), prior, (double*)(uintptr_t)rows_l_a,
+                                      (double*)(uintptr_t)rows_t_a, (int64_t)n_slots, (double*)(uintptr_t)sums_dev_a,
+                                      (double*)(uintptr_t)sums_host_a, nullptr, (void*)(uintptr_t)stream_a);
+  Py_END_ALLOW_THREADS
+  self->run_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (rc != 0) {
+    const char* msg = ((last_error_fn)(uintptr_t)err_a)();
+    PyErr_Format(PyExc_RuntimeError, "pcb_run_plan_dev failed (%d): %s", rc, msg ? msg : "?");
+    return nullptr;
+  }
+  take_scores(self, (const double*)(uintptr_t)sums_host_a);
+  ++self->n_flushes;
+  self->n_launches += (int64_t)(raw.size() / 6) + 2;
+  self->d2h_bytes += 16 * n_slots;
+  self->staged_ints += (int64_t)packed.size();
+  clear_pending(self);
+  Py_RETURN_NONE;
 }
 
 // done(scores or None): scores = contiguous float64 buffer [2, n_slots]; marks the batch as executed
@@ -336,15 +417,8 @@ PyObject* Book_done(Book* self, PyObject* arg) {
       PyErr_SetString(PyExc_ValueError, "score buffer too small");
       return nullptr;
     }
-    const double* p = (const double*)view.buf;
-    for (size_t s = 0; s < n; ++s) {
-      const int sid = (*self->pending_scores)[s];
-      (*self->sc_lse)[sid] = p[s];
-      (*self->sc_last)[sid] = p[n + s];
-      (*self->sc_ready)[sid] = 1;
-    }
+    take_scores(self, (const double*)view.buf);
     PyBuffer_Release(&view);
-    self->n_scores += (int64_t)n;
   }
   clear_pending(self);
   Py_RETURN_NONE;
@@ -358,9 +432,12 @@ PyObject* Book_set_capacity(Book* self, PyObject* arg) {
 }
 
 PyObject* Book_counters(Book* self, PyObject*) {
-  return Py_BuildValue("{s:L,s:L,s:L,s:L,s:L,s:L}", "adds", (long long)self->n_adds, "node_jobs",
+  return Py_BuildValue("{s:L,s:L,s:L,s:L,s:L,s:L,s:L,s:L,s:L,s:L,s:d}", "adds", (long long)self->n_adds, "node_jobs",
                        (long long)self->n_jobs, "scores", (long long)self->n_scores, "memo_hits",
-                       (long long)self->n_hits, "conv_pairs", (long long)self->n_pairs, "top", (long long)self->top);
+                       (long long)self->n_hits, "conv_pairs", (long long)self->n_pairs, "top", (long long)self->top,
+                       "fast_flushes", (long long)self->n_flushes, "fast_launches", (long long)self->n_launches,
+                       "fast_d2h_bytes", (long long)self->d2h_bytes, "fast_staged_ints", (long long)self->staged_ints,
+                       "fast_run_s", self->run_s);
 }
 
 PyMethodDef Book_methods[] = {
@@ -371,6 +448,7 @@ PyMethodDef Book_methods[] = {
     {"score", (PyCFunction)Book_score, METH_O, "score handle of a dummy root folding kids"},
     {"value", (PyCFunction)Book_value, METH_O, "(lse_sum, last_sum) or None while pending"},
     {"has_pending", (PyCFunction)Book_has_pending, METH_NOARGS, ""},
+    {"run", (PyCFunction)Book_run, METH_VARARGS, "flush the pending batch through pcb_run_plan_dev without leaving the extension"},
     {"pack", (PyCFunction)Book_pack, METH_NOARGS, "(packed bytes, plan, n_slots, plan as int32 x 6 records) of the pending batch"},
     {"done", (PyCFunction)Book_done, METH_O, "hand back the [2, n_slots] scores of the packed batch"},
     {"set_capacity", (PyCFunction)Book_set_capacity, METH_O, ""},

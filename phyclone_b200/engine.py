@@ -202,6 +202,24 @@ class DeviceArena:
             self.lib.pcb_node_jobs_dev(C.byref(self.c), base, base + 4 * n * JOB_INTS, n, self.prior, pl, pt, self._stream())
         )
 
+    def flush_context(self):
+        """Addresses `TileBook.run` needs to execute a flush without coming back to Python: the library entry points,
+        the arena descriptor, the pinned staging buffer and its device twin, the score buffers, the stream.  Buffers
+        are (re)allocated by `run_plan`; call again after it has run."""
+        st = self._staging.get("plan")
+        if st is None or self._rows is None:
+            return None
+        if not self._plan_synced:  # the in-extension path overwrites the pinned buffer without asking
+            torch.cuda.current_stream(self.device).synchronize()
+            self._plan_synced = True
+        lib = self.lib
+        fn = C.cast(lib.pcb_run_plan_dev, C.c_void_p).value
+        err = C.cast(lib.pcb_last_error, C.c_void_p).value
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        return (fn, err, C.addressof(self.c), st[0].data_ptr(), st[0].shape[0], st[1].data_ptr(), float(self.prior),
+                self._rows[0].data_ptr(), self._rows[1].data_ptr(), self._rows.shape[1], self._sums.data_ptr(),
+                self._sums_host.data_ptr(), stream)
+
     def run_plan(self, packed, plan, n_slots, plan_raw=None):
         """Execute one flush: `packed` (int32) holds every id list / job table of the batch and is sent to the
         device in ONE pinned copy; `plan` is a list of launches over it:
