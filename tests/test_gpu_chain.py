@@ -153,3 +153,28 @@ def test_replayed_chain_at_bench_config(depth):
         b = signature(ref["tree"], len(vals), name_of=lambda dp: dp.idx)
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
     print("depth %d: %d draws replayed, max relative probability error %.2e" % (depth, len(rec.tape), rep.max_p_err))
+
+
+def test_in_extension_flush_equals_generic_flush(monkeypatch):
+    """`TileBook.run` (pack + stage + pcb_run_plan_dev inside the host extension) and the step-by-step Python flush
+    must be the same computation: identical traces and identical launch / job counts on the same seed."""
+    from phyclone_b200.tiles import TileStore
+
+    g = load_chain("syn12")
+    seed = int(g["meta"][0])
+    fast = _run(g, np.random.default_rng(seed))
+    assert fast["stats"]["staged_ints"] > 0  # the in-extension path did run
+
+    def generic_only(self):
+        if self.book.has_pending():
+            self._flush_generic()
+
+    monkeypatch.setattr(TileStore, "flush", generic_only)
+    slow = _run(g, np.random.default_rng(seed))
+    assert slow["stats"]["staged_ints"] == 0
+    assert len(fast["trace"]) == len(slow["trace"])
+    for a, b in zip(fast["trace"], slow["trace"]):
+        assert a["log_p_one"] == b["log_p_one"] and a["alpha"] == b["alpha"]
+        assert a["tree"]["graph"] == b["tree"]["graph"]
+    for k in ("flushes", "launches", "node_jobs", "adds", "scores", "conv_pairs", "d2h_bytes"):
+        assert fast["stats"][k] == slow["stats"][k], k
