@@ -1518,6 +1518,11 @@ PyObject* mod_particle_log_ws(PyObject*, PyObject* args) {
 //   kids[koff[i]:koff[i+1]] (made by the Python callback new_holder(j, frozenset), which owns the value-keyed LRU) --
 //   and carries the proposal log-probability of semi_adapted.py:36-61.
 //   meta[j] = (parent is empty, log 1/2, log(R + 1), R); log_qs[j]: float64 buffer of the normalised candidate scores.
+PyObject* finish_particles_core(PyObject* parents_o, const std::vector<long>& dist, const std::vector<long>& kind,
+                                const std::vector<long>& pick, const std::vector<long>& kids,
+                                const std::vector<long>& koff, PyObject* cands_o, PyObject* logq_o, PyObject* meta_o,
+                                PyObject* cb);
+
 PyObject* mod_finish_particles(PyObject*, PyObject* args) {
   PyObject *parents_o, *dist_o, *kind_o, *pick_o, *kids_o, *koff_o, *cands_o, *logq_o, *meta_o, *cb;
   if (!PyArg_ParseTuple(args, "OOOOOOOOOO", &parents_o, &dist_o, &kind_o, &pick_o, &kids_o, &koff_o, &cands_o, &logq_o,
@@ -1527,6 +1532,13 @@ PyObject* mod_finish_particles(PyObject*, PyObject* args) {
   if (!longs_of(dist_o, dist) || !longs_of(kind_o, kind) || !longs_of(pick_o, pick) || !longs_of(kids_o, kids) ||
       !longs_of(koff_o, koff))
     return nullptr;
+  return finish_particles_core(parents_o, dist, kind, pick, kids, koff, cands_o, logq_o, meta_o, cb);
+}
+
+PyObject* finish_particles_core(PyObject* parents_o, const std::vector<long>& dist, const std::vector<long>& kind,
+                                const std::vector<long>& pick, const std::vector<long>& kids,
+                                const std::vector<long>& koff, PyObject* cands_o, PyObject* logq_o, PyObject* meta_o,
+                                PyObject* cb) {
   PyObject* parents = PySequence_Fast(parents_o, "parents must be a sequence");
   if (!parents) return nullptr;
   const Py_ssize_t n = PySequence_Fast_GET_SIZE(parents);
@@ -1638,6 +1650,89 @@ PyObject* mod_finish_particles(PyObject*, PyObject* args) {
     return nullptr;
   }
   return out;
+}
+
+// propose_step(draws_fn, bitgen, parents, dist_of, q_list, roots_list, cands, log_qs, meta, new_holder) -> [Particle]
+//   One SMC step after the proposals exist: flattens the proposals' q vectors and root lists, makes every particle's
+//   draws with ONE call of pcb_smc_draws (csrc/pcb_host.cpp: numpy's own Generator code on the same bit generator, in
+//   swarm order; called through its address) and turns them into particles (finish_particles).
+typedef int (*smc_draws_fn)(void*, int64_t, const int32_t*, const double*, const int64_t*, const int64_t*, const int64_t*,
+                            const uint8_t*, int32_t*, int64_t*, int64_t*, int64_t*);
+
+PyObject* mod_propose_step(PyObject*, PyObject* args) {
+  unsigned long long fn_a, bitgen_a;
+  PyObject *parents_o, *dist_o, *q_list, *roots_list, *cands_o, *logq_o, *meta_o, *cb;
+  if (!PyArg_ParseTuple(args, "KKOOOOOOOO", &fn_a, &bitgen_a, &parents_o, &dist_o, &q_list, &roots_list, &cands_o, &logq_o,
+                        &meta_o, &cb))
+    return nullptr;
+  std::vector<long> dist;
+  if (!longs_of(dist_o, dist)) return nullptr;
+  const Py_ssize_t nd = PySequence_Size(q_list);
+  if (nd < 0 || PySequence_Size(roots_list) != nd || PySequence_Size(meta_o) != nd) {
+    PyErr_SetString(PyExc_ValueError, "propose_step: per-proposal lists differ in length");
+    return nullptr;
+  }
+  std::vector<double> q_flat;
+  std::vector<int64_t> q_off(1, 0), r_flat, r_off(1, 0);
+  std::vector<uint8_t> empty;
+  for (Py_ssize_t j = 0; j < nd; ++j) {
+    for (int which = 0; which < 2; ++which) {
+      PyObject* arr = PySequence_GetItem(which ? roots_list : q_list, j);
+      if (!arr) return nullptr;
+      Py_buffer view;
+      if (PyObject_GetBuffer(arr, &view, PyBUF_C_CONTIGUOUS | PyBUF_FORMAT) != 0) {
+        Py_DECREF(arr);
+        return nullptr;
+      }
+      const bool ok = view.itemsize == 8 && view.format && (which ? (view.format[0] == 'l' || view.format[0] == 'q')
+                                                                  : view.format[0] == 'd');
+      if (ok) {
+        const Py_ssize_t m = view.len / 8;
+        if (which) {
+          r_flat.insert(r_flat.end(), (const int64_t*)view.buf, (const int64_t*)view.buf + m);
+          r_off.push_back((int64_t)r_flat.size());
+        } else {
+          q_flat.insert(q_flat.end(), (const double*)view.buf, (const double*)view.buf + m);
+          q_off.push_back((int64_t)q_flat.size());
+        }
+      }
+      PyBuffer_Release(&view);
+      Py_DECREF(arr);
+      if (!ok) {
+        PyErr_SetString(PyExc_TypeError, "propose_step: q must be float64 and roots int64 (contiguous)");
+        return nullptr;
+      }
+    }
+    PyObject* meta = PySequence_GetItem(meta_o, j);
+    if (!meta) return nullptr;
+    const int is_empty = PyObject_IsTrue(PyTuple_Check(meta) && PyTuple_GET_SIZE(meta) > 0 ? PyTuple_GET_ITEM(meta, 0) : Py_False);
+    Py_DECREF(meta);
+    empty.push_back(is_empty ? 1 : 0);
+  }
+  const size_t n = dist.size();
+  std::vector<int32_t> dist32(n), kind32(n);
+  size_t kid_cap = 1;
+  for (size_t i = 0; i < n; ++i) {
+    if (dist[i] < 0 || dist[i] >= nd) {
+      PyErr_SetString(PyExc_IndexError, "propose_step: proposal index out of range");
+      return nullptr;
+    }
+    dist32[i] = (int32_t)dist[i];
+    kid_cap += (size_t)(r_off[(size_t)dist[i] + 1] - r_off[(size_t)dist[i]]);
+  }
+  std::vector<int64_t> pick64(n), kids64(kid_cap), koff64(n + 1);
+  if (q_flat.empty()) q_flat.push_back(0.0);
+  if (r_flat.empty()) r_flat.push_back(0);
+  const int rc = ((smc_draws_fn)(uintptr_t)fn_a)((void*)(uintptr_t)bitgen_a, (int64_t)n, dist32.data(), q_flat.data(),
+                                                 q_off.data(), r_flat.data(), r_off.data(), empty.data(), kind32.data(),
+                                                 pick64.data(), kids64.data(), koff64.data());
+  if (rc != 0) {
+    PyErr_Format(PyExc_RuntimeError, "pcb_smc_draws failed (rc=%d)", rc);
+    return nullptr;
+  }
+  std::vector<long> kind(kind32.begin(), kind32.end()), pick(pick64.begin(), pick64.end()),
+      koff(koff64.begin(), koff64.end()), kids(kids64.begin(), kids64.begin() + (n ? koff64[n] : 0));
+  return finish_particles_core(parents_o, dist, kind, pick, kids, koff, cands_o, logq_o, meta_o, cb);
 }
 
 // =====================================================================================================
@@ -1815,6 +1910,7 @@ PyMethodDef mod_methods[] = {
     {"forest_state", mod_forest_state, METH_VARARGS, "build a ForestState from Python sequences"},
     {"log_sum_exp", mod_log_sum_exp, METH_O, "log sum exp of a float64 buffer, reference summation order"},
     {"particle_log_ws", mod_particle_log_ws, METH_VARARGS, "incremental weights of a list of particles"},
+    {"propose_step", mod_propose_step, METH_VARARGS, "draws of one SMC step (pcb_smc_draws) and the particles they make"},
     {"finish_particles", mod_finish_particles, METH_VARARGS, "particles of one SMC step from its draws"},
     {"gibbs_scores", mod_gibbs_scores, METH_VARARGS, "scores of moving one data point to every node / the outliers"},
     {"attach_holders", mod_attach_holders, METH_VARARGS, "scored candidates: the data point joins each given root"},

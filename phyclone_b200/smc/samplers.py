@@ -19,6 +19,14 @@ from .swarm import ParticleSwarm, TreeHolder
 from .utils import RootPermutationDistribution
 
 _hm = _load_hostmod()
+_draws = []
+
+
+def _draws_address():
+    """Address of pcb_smc_draws (csrc/pcb_host.cpp) for the host extension to call."""
+    if not _draws:
+        _draws.append(C.cast(_hostlib.load().pcb_smc_draws, C.c_void_p).value)
+    return _draws[0]
 
 
 class AbstractSMCSampler(object):
@@ -84,32 +92,14 @@ class AbstractSMCSampler(object):
                     dists.append(d)
                 by_obj[id(p)] = j
             dist_l.append(j)
-        dist_of = np.array(dist_l, dtype=np.int32)
         for d in dists:
             if d._q_dist is None:
                 d._finish()  # the first one resolves the scores of every proposal of the step: one flush
-        q_off = np.zeros(len(dists) + 1, dtype=np.int64)
-        r_off = np.zeros(len(dists) + 1, dtype=np.int64)
-        for j, d in enumerate(dists):
-            q_off[j + 1] = q_off[j] + len(d._q_dist)
-            r_off[j + 1] = r_off[j] + len(d.roots_array)
-        q_flat = np.concatenate([d._q_dist for d in dists])
-        r_flat = np.concatenate([d.roots_array for d in dists] + [np.zeros(0, dtype=np.int64)]).astype(np.int64, copy=False)
-        empty = np.array([1 if d.parent_is_empty_tree else 0 for d in dists], dtype=np.uint8)
-        kind = np.empty(n, dtype=np.int32)
-        pick = np.empty(n, dtype=np.int64)
-        kids = np.empty(max(1, int((r_off[dist_of + 1] - r_off[dist_of]).sum())), dtype=np.int64)
-        koff = np.empty(n + 1, dtype=np.int64)
-        ptr = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
-        rc = _hostlib.load().pcb_smc_draws(C.c_void_p(addr), n, ptr(dist_of), ptr(q_flat), ptr(q_off), ptr(r_flat),
-                                           ptr(r_off), ptr(empty), ptr(kind), ptr(pick), ptr(kids), ptr(koff))
-        if rc != 0:
-            raise RuntimeError("pcb_smc_draws failed (rc=%d)" % rc)
         meta = [(d.parent_is_empty_tree, float(d.log_half),
                  0.0 if d.parent_is_empty_tree else float(d._cached_log_old_num_roots), len(d.roots_array)) for d in dists]
-        out = _hm.finish_particles(parents, dist_l, kind.tolist(), pick.tolist(), kids.tolist(), koff.tolist(),
-                                   [d._curr_trees for d in dists],
-                                   [d._log_q for d in dists], meta, lambda j, children: dists[j].new_node_holder(children))
+        out = _hm.propose_step(_draws_address(), addr, parents, dist_l, [d._q_dist for d in dists],
+                               [d.roots_array for d in dists], [d._curr_trees for d in dists],
+                               [d._log_q for d in dists], meta, lambda j, children: dists[j].new_node_holder(children))
         kernel.num_extensions += n
         return out
 
