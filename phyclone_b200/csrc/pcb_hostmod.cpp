@@ -1606,7 +1606,35 @@ PyObject* finish_particles_core(PyObject* parents_o, const std::vector<long>& di
         }
         PyObject* fs = PyFrozenSet_New(lst);
         Py_DECREF(lst);
-        PyObject* h = fs ? PyObject_CallFunction(cb, "lO", j, fs) : nullptr;
+        PyObject* h = nullptr;
+        if (fs && PyTuple_Check(cb)) {
+          // (holder class, data point, its host tuple, log alpha, [(store, parent state, parent holder) per proposal]):
+          // the new-root candidate is made right here; within a step (proposal, child set) is unique in `memo`, which
+          // is all the reference's value-keyed cache (semi_adapted.py:186-194) can ever hit on
+          PyObject *cls, *dp, *dpo, *per;
+          double la;
+          if (PyArg_ParseTuple(cb, "OOOdO", &cls, &dp, &dpo, &la, &per)) {
+            PyObject* ctx = PySequence_GetItem(per, j);
+            PyObject *store, *pstate, *pholder;
+            if (ctx && PyArg_ParseTuple(ctx, "OOO", &store, &pstate, &pholder)) {
+              for (int attempt = 0; attempt < 2; ++attempt) {
+                PyObject* a = Py_BuildValue("(OOOOOiOOOd)", cls, store, pstate, pstate, pholder, (int)K_NEW, dp, dpo, fs, la);
+                h = a ? mod_edit_holder(nullptr, a) : nullptr;
+                Py_XDECREF(a);
+                if (h != Py_None) break;
+                Py_DECREF(h);  // arena full: grow it and record again
+                h = nullptr;
+                PyObject* r = PyObject_CallMethod(store, "_grow", nullptr);
+                if (!r) break;
+                Py_DECREF(r);
+              }
+              if (!h && !PyErr_Occurred()) PyErr_SetString(PyExc_MemoryError, "tile arena exhausted");
+            }
+            Py_XDECREF(ctx);
+          }
+        } else if (fs) {
+          h = PyObject_CallFunction(cb, "lO", j, fs);
+        }
         Py_XDECREF(fs);
         if (!h) {
           ok = false;

@@ -15,7 +15,8 @@ from .. import _hostlib
 from .._hostmod import load as _load_hostmod
 from ..tree.tree import Tree
 from ..utils.math import discrete_rvs
-from .swarm import ParticleSwarm, TreeHolder
+from .forest_state import host_tuple
+from .swarm import ParticleSwarm, StateHolder, TreeHolder
 from .utils import RootPermutationDistribution
 
 _hm = _load_hostmod()
@@ -97,9 +98,12 @@ class AbstractSMCSampler(object):
                 d._finish()  # the first one resolves the scores of every proposal of the step: one flush
         meta = [(d.parent_is_empty_tree, float(d.log_half),
                  0.0 if d.parent_is_empty_tree else float(d._cached_log_old_num_roots), len(d.roots_array)) for d in dists]
+        store = kernel.store
+        make_new = (StateHolder, data_point, host_tuple(store, data_point), float(kernel.tree_dist.prior.log_alpha),
+                    [(store, d._pstate, d._pholder) for d in dists])
         out = _hm.propose_step(_draws_address(), addr, parents, dist_l, [d._q_dist for d in dists],
                                [d.roots_array for d in dists], [d._curr_trees for d in dists],
-                               [d._log_q for d in dists], meta, lambda j, children: dists[j].new_node_holder(children))
+                               [d._log_q for d in dists], meta, make_new)
         kernel.num_extensions += n
         return out
 
