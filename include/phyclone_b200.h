@@ -163,7 +163,8 @@ int pcb_outlier_marginal_host(const double* values, int64_t K, int32_t S, int32_
 /* One flush of the lazily recorded tile algebra (phyclone_b200/tiles.py) in a single call: copies the packed id lists /
  * job tables from pinned host memory, runs the plan's launches in dependency order on `stream` -- tile adds
  * (tree/tree_node.py:42-59) and node jobs (tree/tree_node.py:61-71, tree/distributions.py:197-200) -- reduces the score
- * rows over samples and copies [2][n_slots] sums to `sums_host`; synchronises the stream only if n_slots > 0.
+ * rows over samples straight into `sums_host` ([2][n_slots]; must be pinned, device-accessible host memory; `sums_dev` is
+ * unused); synchronises the stream only if n_slots > 0.
  * plan: n_rec x 6 int32 {kind 0=add | 1=jobs, offset into packed, n, n_kids, negate, 0}; add ids are laid out
  * [a | b | out], a job table (n x 8 int32) is followed by its n_kids child ids.  events: NULL or 2 CUDA events per
  * record, recorded around the node-jobs launches. */

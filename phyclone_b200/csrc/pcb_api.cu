@@ -530,9 +530,12 @@ int pcb_run_plan_dev(const pcb_arena* a, const int32_t* packed_host, int64_t n_i
     }
   }
   if (n_slots > 0) {
-    if ((rc = pcb_reduce_rows_dev(rows_lse, n_slots, a->layout.S, sums_dev, stream))) return rc;
-    if ((rc = pcb_reduce_rows_dev(rows_last, n_slots, a->layout.S, sums_dev + n_slots, stream))) return rc;
-    PCB_CUDA(cudaMemcpyAsync(sums_host, sums_dev, (size_t)n_slots * 16, cudaMemcpyDeviceToHost, st));
+    // one launch reduces both score kinds over the samples and writes the sums straight into the caller's pinned
+    // (device-accessible) host buffer: no separate device-to-host copy; the synchronise below makes them visible
+    (void)sums_dev;
+    pcb::reduce_rows2_kernel<<<(unsigned)((2 * n_slots + 127) / 128), 128, 0, st>>>(rows_lse, rows_last, n_slots,
+                                                                                  a->layout.S, sums_host);
+    PCB_LAUNCH_CHECK();
     const auto t_enq = std::chrono::steady_clock::now();
     PCB_CUDA(cudaStreamSynchronize(st));
     const auto t_end = std::chrono::steady_clock::now();

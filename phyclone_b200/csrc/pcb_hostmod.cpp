@@ -399,7 +399,7 @@ PyObject* Book_run(Book* self, PyObject* args) {
   }
   take_scores(self, (const double*)(uintptr_t)sums_host_a);
   ++self->n_flushes;
-  self->n_launches += (int64_t)(raw.size() / 6) + 2;
+  self->n_launches += (int64_t)(raw.size() / 6) + 1;
   self->d2h_bytes += 16 * n_slots;
   self->staged_ints += (int64_t)packed.size();
   clear_pending(self);

@@ -821,6 +821,19 @@ __global__ void reduce_rows_kernel(const double* __restrict__ rows, long long n,
   out[i] = acc;
 }
 
+// both score kinds of a flush in one launch: out[slot] = sum_s lse_rows[slot][s], out[n + slot] = sum_s last_rows[slot][s].
+// `out` may be pinned host memory (device-accessible under unified addressing): the sums then land where the host
+// reads them and a flush needs no device-to-host copy.
+__global__ void reduce_rows2_kernel(const double* __restrict__ lse_rows, const double* __restrict__ last_rows,
+                                    long long n, int S, double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * n) return;
+  const double* rows = (i < n) ? lse_rows + i * S : last_rows + (i - n) * S;
+  double acc = 0.0;
+  for (int s = 0; s < S; ++s) acc += rows[s];
+  out[i] = acc;
+}
+
 // root data terms straight from dense tiles: one warp per (tile,row)   (tree/distributions.py:197-200)
 __global__ void root_terms_rows_kernel(const double* __restrict__ dense, long long n, int S, int G,
                                        double* __restrict__ lse_rows, double* __restrict__ last_rows) {

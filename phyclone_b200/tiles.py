@@ -158,7 +158,7 @@ class TileStore:
         t_begin = time.perf_counter()
         st["flushes"] += 1
         packed, plan, n_slots, plan_raw = book.pack()
-        st["launches"] += len(plan) + (2 if n_slots else 0)
+        st["launches"] += len(plan) + (1 if n_slots else 0)
         t_run = time.perf_counter()
         host = self.arena.run_plan(np.frombuffer(packed, dtype=np.int32), plan, n_slots, plan_raw)
         st["device_wait_s"] += time.perf_counter() - t_run
