@@ -37,7 +37,7 @@ def main():
     print("| kernel | launches | total us | share | avg us | avg grid |\n|---|---|---|---|---|---|", file=out)
     for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print("| %s | %d | %.0f | %.1f%% | %.1f | %d |" % (k, a[0], a[1], 100 * a[1] / tot, a[1] / a[0], a[2] // a[0]), file=out)
-    chain = {k: a for k, a in agg.items() if k in ("node_jobs_kernel", "node_jobs_wide_kernel", "tile_add_kernel", "reduce_rows_kernel")}
+    chain = {k: a for k, a in agg.items() if k in ("node_jobs_kernel", "node_jobs_wide_kernel", "tile_add_kernel", "reduce_rows_kernel", "reduce_rows2_kernel")}
     ct = sum(a[1] for a in chain.values())
     print("\ntotal device time %.1f ms; the chain's own kernels (node_jobs, tile_add, reduce_rows) %.1f ms: %s" % (
         tot / 1e3, ct / 1e3, ", ".join("%s %.1f %%" % (k, 100 * a[1] / ct) for k, a in sorted(chain.items(), key=lambda kv: -kv[1][1]))),
