@@ -998,6 +998,7 @@ struct Holder {
   DataPt dpt;
 };
 
+extern PyTypeObject HolderType;
 long g_next_uid = -1;  // negative: never collides with the Python-side holder counter
 
 Holder* holder_new(PyTypeObject* cls) {
@@ -1017,9 +1018,20 @@ Holder* holder_new(PyTypeObject* cls) {
 }
 
 void Holder_dealloc(Holder* h) {
+  // a genealogy is as long as the data set (2000 at config #5, more for unclustered WGS): hand the parent chain down
+  // iteratively -- each ancestor is released with its own parent link already taken, so no call nests deeper than one
+  PyObject* parent = h->parent_holder;
+  h->parent_holder = nullptr;
+  while (parent && parent != Py_None && PyObject_TypeCheck(parent, &HolderType) && Py_REFCNT(parent) == 1) {
+    Holder* q = (Holder*)parent;
+    PyObject* next = q->parent_holder;
+    q->parent_holder = nullptr;
+    Py_DECREF(parent);
+    parent = next;
+  }
+  Py_XDECREF(parent);
   Py_XDECREF(h->dp);
   Py_XDECREF(h->arg);
-  Py_XDECREF(h->parent_holder);
   Py_XDECREF(h->store);
   Py_XDECREF((PyObject*)h->book);
   Py_XDECREF((PyObject*)h->parent_state);

@@ -92,3 +92,28 @@ def test_no_cpu_fallback_without_a_device():
         ops.np_conv_dims(np.zeros((2, 5)), np.zeros((2, 5)))
     with pytest.raises(RuntimeError):
         ops.map_trees(np.zeros((1, 2, 5)), [0, 1], [0], [0, 0], [])
+
+
+def test_long_holder_and_particle_chains_are_released_iteratively():
+    """Genealogies are as long as the data set; dropping the last reference to a 100 000-long chain of native holders /
+    particles must not recurse on the C stack."""
+    from phyclone_b200._hostmod import load
+    from phyclone_b200.data.base import DataPoint
+    from phyclone_b200.smc.forest_state import OUTLIER, ForestState, ensure_tables
+    from phyclone_b200.smc.swarm import StateHolder
+    from phyclone_b200.tree.distributions import FSCRPDistribution, TreeJointDistribution
+    from tests.null_store import NullTileStore
+
+    hm = load()
+    vals = np.zeros((2, 2, 8))
+    store = NullTileStore(vals)
+    tree_dist = TreeJointDistribution(FSCRPDistribution(1.0))
+    ensure_tables(tree_dist.prior, 10)
+    dp = DataPoint(0, vals[0], outlier_prob=-1.0, outlier_prob_not=-0.1, outlier_marginal_prob=-3.0)
+    empty = ForestState.empty(store)
+    holder, particle = None, None
+    for _ in range(100000):
+        holder = StateHolder.edit(store, holder, empty, empty, OUTLIER, dp, None, tree_dist)
+        particle = hm.Particle(0.0, particle, holder)
+    assert particle.parent_particle is not None and holder.kind == OUTLIER
+    del holder, particle
