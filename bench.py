@@ -308,6 +308,12 @@ def run_ours(args):
     h2d = values.nbytes + (staged() - st0) / args.steps
     d2h = (chain.stats["d2h_bytes"] - d2h0) / args.steps
 
+    # ---- the same iterations once more with nothing attached (no kernel events, no transfers): what the event pairs
+    # of region 1 cost
+    chain.restore(snap)
+    ms_plain = timed(args.steps)
+    value_plain = world * args.steps / (ms_plain * 1e-3)
+
     # ---- saturated-batch figure for the same kernel (how far the kernel itself goes when a launch is big)
     sat = None
     if rank == 0:
@@ -358,6 +364,7 @@ def run_ours(args):
                                                  (s1["adds"] + s1["node_jobs"] - s0["adds"] - s0["node_jobs"]) // args.steps
                                                  * store.arena.layout.tile_elems * 16 // (1 << 20))),
             "particle_extensions_per_sec": ext / (ms * 1e-3),
+            "value_without_kernel_timing": value_plain,  # same iterations, no CUDA events around the kernel launches
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "per_rank_ms_per_step": [round(x, 2) for x in value_per_rank_ms],
