@@ -19,23 +19,36 @@ class DataPointSampler(object):
         self._rng = rng
 
     def sample_tree(self, tree):
+        """gibbs_mh.py:17-33: one Gibbs move per data point whose node holds more than one point, in shuffled order.
+        The reference copies the tree for every move; here the input is copied ONCE and the moves edit that copy in
+        place (nothing else holds it), the label map is updated instead of rebuilt, and data points are looked up in
+        a map built once -- at 2000 unclustered mutations the per-move rebuilds were O(T) each."""
         tree_labels = tree.labels
         data_idxs = list(tree_labels.keys())
         self._rng.shuffle(data_idxs)
+        by_idx = None
         for data_idx in data_idxs:
             old_node = tree_labels[data_idx]
             if tree.get_data_len(old_node) > 1:
-                tree = self._sample_tree(data_idx, tree, old_node)
-                tree_labels = tree.labels
+                if by_idx is None:
+                    tree = tree.copy()
+                    by_idx = {dp.idx: dp for lst in tree._data.values() for dp in lst}
+                tree_labels[data_idx] = self._move(by_idx[data_idx], tree, old_node)
         return tree
 
     def _sample_tree(self, data_idx, tree, old_node):
-        """gibbs_mh.py:35-70.  The reference copies the tree once per candidate node; here every candidate is
-        scored from the ONE tree by recording the tile ops its two path refreshes would perform (remove from
-        `old_node`: refresh old_node..root; add to `new_node`: log_r += value, refresh parent(new_node)..root),
-        and only the candidate that is drawn gets built."""
+        """gibbs_mh.py:35-70 with the reference's signature: returns a new tree, the input is left alone."""
         data_point = tree.data[data_idx]
         assert data_point.idx == data_idx
+        new_tree = tree.copy()
+        self._move(data_point, new_tree, old_node)
+        return new_tree
+
+    def _move(self, data_point, tree, old_node):
+        """Draw the node `data_point` moves to and apply the move to `tree` IN PLACE; returns the node's name.
+        Every candidate is scored from the one tree by recording the tile ops its two path refreshes would perform
+        (remove from `old_node`: refresh old_node..root; add to the new node: log_r += value, refresh its parents up
+        to the root); only the candidate that is drawn gets built."""
         pending = self._score_candidates(tree, data_point, old_node)
         log_q = np.array([p.resolve()[1] for p in pending])
         log_q = log_normalize(log_q)
@@ -43,13 +56,14 @@ class DataPointSampler(object):
         q = q / sum(q)
         tree_idx = self._rng.multinomial(1, q).argmax()
         nodes = tree.nodes
-        new_tree = tree.copy()
-        new_tree.remove_data_point_from_node(data_point, old_node)
+        tree.remove_data_point_from_node(data_point, old_node)
         if tree_idx < len(nodes):
-            new_tree.add_data_point_to_node(data_point, nodes[tree_idx])
+            new_node = nodes[tree_idx]
+            tree.add_data_point_to_node(data_point, new_node)
         else:
-            new_tree.add_data_point_to_outliers(data_point)
-        return new_tree
+            new_node = tree.outlier_node_name
+            tree.add_data_point_to_outliers(data_point)
+        return new_node
 
     def _score_candidates(self, tree, data_point, old_node):
         """Scores of `tree` with `data_point` moved to every node (in `tree.nodes` order) and, with outlier
