@@ -25,4 +25,5 @@ def interleave_lists(lists, rng):
     for i, lst in enumerate(lists):
         sentinels.extend(repeat(i, len(lst)))
     rng.shuffle(sentinels)
-    return [lists[idx].pop(0) for idx in sentinels]
+    heads = [iter(lst) for lst in lists]  # the reference pops from the front of each list: O(n) per element
+    return [next(heads[idx]) for idx in sentinels]
