@@ -49,7 +49,16 @@ def main():
     ap.add_argument("--chains", default="1,2,4,8")
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--mps", action="store_true", help="share the GPU through an MPS daemon started for the run")
     args = ap.parse_args()
+    from phyclone_b200.run import MpsServer
+
+    with MpsServer(enable=args.mps) as server:
+        print(json.dumps({"mps": server.started}))
+        sweep(args)
+
+
+def sweep(args):
     ctx = mp.get_context("spawn")
     for n in [int(x) for x in args.chains.split(",")]:
         barrier = ctx.Barrier(n)

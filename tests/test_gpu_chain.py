@@ -178,3 +178,21 @@ def test_in_extension_flush_equals_generic_flush(monkeypatch):
         assert a["tree"]["graph"] == b["tree"]["graph"]
     for k in ("flushes", "launches", "node_jobs", "adds", "scores", "conv_pairs", "d2h_bytes"):
         assert fast["stats"][k] == slow["stats"][k], k
+
+
+def test_chains_in_worker_processes_match_in_process_chains():
+    """`run_chains_local` (one process per chain, sharing the GPU through MPS when the daemon can be started) must
+    give every chain the trace it has when the chains run one after the other in this process."""
+    from phyclone_b200.run import run_chains, run_chains_local
+
+    g = load_chain("syn12")
+    data = _data(g)
+    kw = dict(num_chains=3, seed=11, burnin=1, num_iters=3, num_particles=10, print_freq=10**9)
+    here = run_chains(data, ["s"], **kw)
+    there = run_chains_local(data, ["s"], devices=[0], mps=True, **kw)
+    assert sorted(there) == sorted(here) == [0, 1, 2]
+    for c in here:
+        assert len(there[c]["trace"]) == len(here[c]["trace"])
+        for a, b in zip(there[c]["trace"], here[c]["trace"]):
+            assert a["log_p_one"] == b["log_p_one"] and a["alpha"] == b["alpha"]
+            assert a["tree"]["graph"] == b["tree"]["graph"]
