@@ -334,6 +334,28 @@ def run_ours(args):
         except Exception as e:  # noqa: BLE001
             sat = {"error": str(e)}
 
+    # ---- BASELINE configs[2] on this one GPU: 8 chains in 8 host processes sharing the device through MPS (one chain
+    # leaves it ~70 % idle).  Reported beside the headline, never mixed into it; skipped under torchrun.
+    mps_chains = None
+    if rank == 0 and world == 1 and not args.no_mps_chains:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "scripts"))
+            from multi_chain_bench import run_chains_once
+
+            from phyclone_b200.run import MpsServer
+
+            n_chains = max(2, min(8, (os.cpu_count() or 2) // 2))
+            with MpsServer() as server:
+                if server.started:
+                    rate = run_chains_once(n_chains, args.steps, args.warmup, timeout=300)
+                    mps_chains = {"chains": n_chains, "value": rate, "unit": UNIT, "per_chain": rate / n_chains,
+                                  "how": "one host process per chain, all on GPU 0 through an MPS daemon started for this "
+                                         "leg (run.MpsServer / run.run_chains_local); same config, chain seeds spawned"}
+                else:
+                    mps_chains = {"unavailable": "nvidia-cuda-mps-control did not start"}
+        except Exception as e:  # noqa: BLE001
+            mps_chains = {"unavailable": "%s: %s" % (type(e).__name__, e)}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, elapsed, _ = oracle_chain_rate(2, 1)
@@ -377,6 +399,7 @@ def run_ours(args):
                                         "MEASURED_PEAKS.json has no FP64 figure (hbm_gbs=%s)" % peaks.get("hbm_gbs"),
                          "saturated_batch": sat},
             "cpu_baseline": cpu,
+            "chains_on_one_gpu_mps": mps_chains,
             "clocks": clocks.summary(),
             "per_step": {k: (s1[k] - s0[k]) / args.steps for k in ("flushes", "launches", "node_jobs", "adds", "scores",
                                                                     "conv_pairs", "memo_hits", "extensions")},
@@ -393,6 +416,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-mps-chains", action="store_true", help="skip the 8-chains-on-one-GPU (MPS) leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -34,13 +34,12 @@ def worker(rank, n, steps, warmup, barrier, q):
     for _ in range(warmup):
         chain.step()
     torch.cuda.synchronize()
-    barrier.wait()
+    barrier.wait(timeout=300)
     t0 = time.perf_counter()
     for _ in range(steps):
         chain.step()
     torch.cuda.synchronize()
     t1 = time.perf_counter()
-    barrier.wait()
     q.put((rank, t0, t1))
 
 
@@ -58,21 +57,31 @@ def main():
         sweep(args)
 
 
-def sweep(args):
+def run_chains_once(n, steps, warmup, timeout=600):
+    """n chains, one process each, same GPU; returns the aggregate PG iterations/s over the common timed window."""
     ctx = mp.get_context("spawn")
+    barrier = ctx.Barrier(n)
+    q = ctx.Queue()
+    procs = [ctx.Process(target=worker, args=(r, n, steps, warmup, barrier, q), daemon=True) for r in range(n)]
+    for p in procs:
+        p.start()
+    try:
+        res = [q.get(timeout=timeout) for _ in range(n)]
+    finally:
+        for p in procs:
+            p.join(timeout=30)
+            if p.is_alive():
+                p.terminate()
+    t0 = min(r[1] for r in res)
+    t1 = max(r[2] for r in res)
+    return n * steps / (t1 - t0)
+
+
+def sweep(args):
     for n in [int(x) for x in args.chains.split(",")]:
-        barrier = ctx.Barrier(n)
-        q = ctx.Queue()
-        procs = [ctx.Process(target=worker, args=(r, n, args.steps, args.warmup, barrier, q)) for r in range(n)]
-        for p in procs:
-            p.start()
-        res = [q.get() for _ in range(n)]
-        for p in procs:
-            p.join()
-        t0 = min(r[1] for r in res)
-        t1 = max(r[2] for r in res)
-        print(json.dumps({"chains_on_one_gpu": n, "steps": args.steps, "aggregate_pg_it_per_s": n * args.steps / (t1 - t0),
-                          "per_chain_it_per_s": args.steps / (t1 - t0), "host_cores": os.cpu_count()}))
+        rate = run_chains_once(n, args.steps, args.warmup)
+        print(json.dumps({"chains_on_one_gpu": n, "steps": args.steps, "aggregate_pg_it_per_s": rate,
+                          "per_chain_it_per_s": rate / n, "host_cores": os.cpu_count()}))
 
 
 if __name__ == "__main__":
