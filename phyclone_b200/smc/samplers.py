@@ -156,19 +156,35 @@ class ConditionalSMCSampler(AbstractSMCSampler):
         new_tree = Tree(tree.grid_size, kernel.store)
         outlier_node_name = tree.outlier_node_name
         holders = []
+        # `thawed` follows `new_tree` through the same edits but is re-read (from_dict round trip) after every one:
+        # it is what holder.tree must return, and building it incrementally keeps that O(touched nodes) per step --
+        # thawing each as-built tree from scratch re-derives every node touched so far, O(T) per step (1 s per
+        # iteration at 2000 data points).  Both start empty and have no vacancies, so the edits allocate the same
+        # node names and slots in both, and tile ids are a function of structure (memoised ops): same result.
+        thawed = new_tree.copy()
         for data_point in self.data_points:
             new_tree = new_tree.copy()
+            thawed = thawed.copy()
             old_node = data_to_node[data_point.idx]
             if old_node == outlier_node_name:
                 new_tree.add_data_point_to_outliers(data_point)
+                thawed.add_data_point_to_outliers(data_point)
             elif old_node in node_map:
                 new_tree.add_data_point_to_node(data_point, node_map[old_node])
+                thawed.add_data_point_to_node(data_point, node_map[old_node])
             else:
                 children = [node_map[child] for child in tree.get_children(old_node)]
                 new_node = new_tree.create_root_node(children)
                 node_map[old_node] = new_node
                 new_tree.add_data_point_to_node(data_point, new_node)
-            holders.append(TreeHolder(new_tree, kernel.tree_dist))
+                twin = thawed.create_root_node(children)
+                assert twin == new_node
+                thawed.add_data_point_to_node(data_point, new_node)
+            thawed.outliers  # noqa: B018 -- same key-creation side effect as scoring the as-built tree
+            thawed = thawed.thawed_copy()
+            holder = TreeHolder(new_tree, kernel.tree_dist)
+            holder._thawed = thawed
+            holders.append(holder)
         constrained_path = [None]
         parent_tree = None
         pending = []
