@@ -17,6 +17,7 @@ class DataPointSampler(object):
         self.tree_dist = tree_dist
         self.outliers = outliers
         self._rng = rng
+        self._flat = None  # (graph, flattened structure) of the tree the current sweep edits in place
 
     def sample_tree(self, tree):
         """gibbs_mh.py:17-33: one Gibbs move per data point whose node holds more than one point, in shuffled order.
@@ -26,6 +27,7 @@ class DataPointSampler(object):
         tree_labels = tree.labels
         data_idxs = list(tree_labels.keys())
         self._rng.shuffle(data_idxs)
+        self._flat = None
         by_idx = None
         for data_idx in data_idxs:
             old_node = tree_labels[data_idx]
@@ -76,22 +78,28 @@ class DataPointSampler(object):
         g, lp, lr, idx = tree._graph, tree._lp, tree._lr, tree._node_indices
         prior = self.tree_dist.prior
         ensure_tables(prior, st.T + 2)
-        n_slots = len(g.payload)
-        parent, kids = [-1] * n_slots, [()] * n_slots
+        # the shape of the tree does not change during a Gibbs sweep (points move, nodes stay): flatten it once
+        flat = self._flat
+        if flat is None or flat[0] is not g:
+            n_slots = len(g.payload)
+            parent, kids = [-1] * n_slots, [()] * n_slots
+            succ, pred = g.successor_indices, g.predecessor_indices
+            live = list(g.node_indices())
+            for i in live:
+                kids[i] = succ(i)
+                p = pred(i)
+                if p:
+                    parent[i] = p[0]
+            root = idx[tree._ROOT_NODE_NAME]
+            nodes = tree.nodes
+            flat = self._flat = (g, n_slots, parent, kids, live, root, nodes, [idx[n] for n in nodes])
+        _, n_slots, parent, kids, live, root, nodes, cand = flat
         lp_l, lr_l = [-1] * n_slots, [-1] * n_slots
-        succ, pred = g.successor_indices, g.predecessor_indices
-        for i in g.node_indices():
-            kids[i] = succ(i)
-            p = pred(i)
-            if p:
-                parent[i] = p[0]
+        for i in live:
             lp_l[i], lr_l[i] = lp[i], lr[i]
-        root = idx[tree._ROOT_NODE_NAME]
         crp, mult, size, oprior, omarg = tree.prior_terms()
         sizes = [size[i] for i in kids[root]]
-        nodes = tree.nodes
         data = tree._data
-        cand = [idx[n] for n in nodes]
         cand_n = [len(data[n]) for n in nodes]
         if old_node == tree._OUTLIER_NODE_NAME:
             oi, n_old = -1, 0

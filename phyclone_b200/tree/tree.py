@@ -154,6 +154,23 @@ class Tree(object):
             if node == out:
                 pt[4] += dp.outlier_marginal_prob
 
+    def _pt_detach(self, node, dp, old_len):
+        """Inverse of `_pt_attach` for one data point (the Gibbs move removes and re-adds a point thousands of times
+        per sweep at config #5; re-deriving the statistics is O(T) each time)."""
+        pt = self._pt
+        if pt is None:
+            return
+        out = self._OUTLIER_NODE_NAME
+        if node != out:
+            if old_len >= 2:  # a node going from n to n-1 points loses log(n-1)
+                pt[0] -= cached_log_factorial(old_len - 1) - cached_log_factorial(old_len - 2)
+            if dp.outlier_prob != 0:
+                pt[3] -= dp.outlier_prob_not
+        else:
+            if dp.outlier_prob != 0:
+                pt[3] -= dp.outlier_prob
+            pt[4] -= dp.outlier_marginal_prob
+
     # ------------------------------------------------------------------ queries
     @staticmethod
     def get_single_node_tree(data, store):
@@ -359,7 +376,7 @@ class Tree(object):
         lst.remove(data_point)
         self._data[node] = tuple(lst)
         self._skey = None
-        self._pt = None
+        self._pt_detach(node, data_point, len(lst) + 1)
         if node != self._OUTLIER_NODE_NAME:
             i = self._node_indices[node]
             self._lp[i] = self.store.sub(self._lp[i], self.store.value_id[data_point.idx])
