@@ -13,6 +13,8 @@ import pandas as pd
 
 from ..tiles import TileStore
 from ..tree.tree import Tree
+from ..utils.math import exp_normalize
+from .consensus import get_consensus_tree, tree_from_consensus
 from .map import map_trees
 from .trace_io import read_trace, write_trace
 
@@ -154,6 +156,31 @@ def create_topologies_archive(topology_df, results, top_trees, topologies_dict, 
                 nwk_path = os.path.join(tmp_dir, nwk_filename)
                 print_string_to_file(tree.to_newick_string(), nwk_path)
                 archive.add(nwk_path, arcname=str(os.path.join(topology_id, nwk_filename)))
+
+
+def write_consensus_results(in_file, out_table_file, out_tree_file, consensus_threshold=0.5,
+                            weight_type="joint-likelihood", device=None, store=None):
+    """process_trace.py:185-233: consensus tree of the trace (by counts, or weighted by each topology's best joint
+    likelihood times its count), its MAP prevalences and the clone table."""
+    results = read_trace(in_file)
+    data = results[0]["data"]
+    store = store_for(results, device, store)
+    trees, probs = [], None
+    if weight_type == "counts":
+        for chain_results in results.values():
+            trees.extend(Tree.from_dict(x["tree"], store) for x in chain_results["trace"])
+    else:
+        logs = []
+        for tree, info in create_topology_dict_from_trace(results, store).items():
+            trees.append(tree)
+            logs.append(info["log_p_joint_max"] + np.log(info["count"]))
+        probs, _ = exp_normalize(np.array(logs))
+    children, idxs, _ = get_consensus_tree(trees, data=data, threshold=consensus_threshold, weighted=probs is not None,
+                                           log_p_list=probs)
+    tree = tree_from_consensus(data, children, idxs, store)
+    table = get_clone_table(data, results[0]["samples"], tree, clusters=results[0].get("clusters", None))
+    _create_results_output_files(out_table_file, out_tree_file, table, tree)
+    return table
 
 
 def _create_results_output_files(out_table_file, out_tree_file, table, tree):

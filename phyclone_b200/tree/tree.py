@@ -370,6 +370,15 @@ class Tree(object):
     def add_data_point_to_outliers(self, data_point):
         self.add_data_point_to_node(data_point, self._OUTLIER_NODE_NAME)
 
+    def _attach_without_refresh(self, data_point, node):
+        """tree/tree.py:236-246 with build_add=True: the point joins the node's data and log_p, no path refresh (the
+        caller finishes with `update()`).  Used when a tree is assembled from a finished structure (consensus)."""
+        self._data[node] = self._data[node] + (data_point,)
+        self._last_node_added_to = node
+        self._skey = self._pt = self._dirty = None
+        if node != self._OUTLIER_NODE_NAME:
+            self._absorb(self._node_indices[node], (data_point,))
+
     def remove_data_point_from_node(self, data_point, node):
         """tree/tree.py:446-454"""
         lst = list(self._data[node])

@@ -4,7 +4,7 @@ Run:  python tests/golden/make_golden_trace.py
 mixing.tsv + mixing_clusters.tsv, one chain of 12 iterations with 20 particles, then the reference's own
 `create_main_run_output`, `write_map_results` (both map types) and `write_topology_report` with an archive.
 Outputs (committed): trace_mixing.pkl.gz, trace_mixing_map_{joint,freq}.tsv/.nwk, trace_mixing_topologies.tsv,
-trace_mixing_topologies.tar.gz.  Graph container = oracle/refshim/rustworkx (so tree["graph"] is a plain list).
+trace_mixing_topologies.tar.gz, trace_mixing_consensus_*.tsv/.nwk.  Graph container = oracle/refshim/rustworkx (so tree["graph"] is a plain list).
 """
 
 import io
@@ -19,8 +19,8 @@ sys.path[:0] = [REPO, os.path.join(REPO, "oracle", "refshim"), "/root/reference"
 import numpy as np  # noqa: E402
 
 from phyclone.data.pyclone import load_data  # noqa: E402
-from phyclone.process_trace.process_trace import (create_main_run_output, write_map_results,  # noqa: E402
-                                                  write_topology_report)
+from phyclone.process_trace.process_trace import (create_main_run_output, write_consensus_results,  # noqa: E402
+                                                  write_map_results, write_topology_report)
 from phyclone.run import run_phyclone_chain  # noqa: E402
 
 DATA = "/root/reference/examples/data/mixing.tsv"
@@ -41,6 +41,10 @@ def main():
         write_map_results(p(".pkl.gz"), p("_map_joint.tsv"), p("_map_joint.nwk"))
         write_map_results(p(".pkl.gz"), p("_map_freq.tsv"), p("_map_freq.nwk"), map_type="frequency")
         write_topology_report(p(".pkl.gz"), p("_topologies.tsv"), p("_topologies.tar.gz"), top_trees=3)
+        write_consensus_results(p(".pkl.gz"), p("_consensus_joint.tsv"), p("_consensus_joint.nwk"))
+        write_consensus_results(p(".pkl.gz"), p("_consensus_counts.tsv"), p("_consensus_counts.nwk"), weight_type="counts")
+        write_consensus_results(p(".pkl.gz"), p("_consensus_counts70.tsv"), p("_consensus_counts70.nwk"),
+                                consensus_threshold=0.7, weight_type="counts")
     for f in sorted(os.listdir(HERE)):
         if f.startswith("trace_mixing"):
             print(f, os.path.getsize(os.path.join(HERE, f)))
