@@ -41,29 +41,23 @@ def print_string_to_file(str_to_write, filename):
 
 
 def write_map_results(in_file, out_table_file, out_tree_file, map_type="joint-likelihood", device=None, store=None):
-    """process_trace.py:19-61"""
+    """process_trace.py:19-61: the table and Newick string of ONE sampled tree -- the one with the highest joint
+    likelihood, or (map_type "frequency") the best-scoring visit of the most frequently sampled topology."""
     results = read_trace(in_file)
-    data = results[0]["data"]
+    first = results[0]
     store = store_for(results, device, store)
-    chain_num = 0
     if map_type == "frequency":
-        topologies = create_topology_dict_from_trace(results, store)
-        df = create_topology_dataframe(topologies.values())
-        df = df.sort_values(by="count", ascending=False)
-        map_iter = df["iter"].iloc[0]
-        chain_num = df["chain_num"].iloc[0]
+        ranking = create_topology_dataframe(create_topology_dict_from_trace(results, store).values())
+        top = ranking.sort_values(by="count", ascending=False).iloc[0]
+        chain_num, map_iter = top["chain_num"], top["iter"]
     else:
-        map_iter = 0
-        map_val = float("-inf")
-        for curr_chain_num, chain_results in results.items():
-            for i, x in enumerate(chain_results["trace"]):
-                if x["log_p_one"] > map_val:
-                    map_iter = i
-                    map_val = x["log_p_one"]
-                    chain_num = curr_chain_num
+        chain_num, map_iter, best = 0, 0, float("-inf")
+        for c, chain_results in results.items():
+            for i, entry in enumerate(chain_results["trace"]):
+                if entry["log_p_one"] > best:  # strict: the first of equal maxima wins, as in the reference
+                    chain_num, map_iter, best = c, i, entry["log_p_one"]
     tree = Tree.from_dict(results[chain_num]["trace"][map_iter]["tree"], store)
-    clusters = results[0].get("clusters", None)
-    table = get_clone_table(data, results[0]["samples"], tree, clusters=clusters)
+    table = get_clone_table(first["data"], first["samples"], tree, clusters=first.get("clusters", None))
     _create_results_output_files(out_table_file, out_tree_file, table, tree)
     return table
 
@@ -80,22 +74,16 @@ def create_topology_dict_from_trace(trace, store):
 
 
 def count_topology(topologies, x, i, x_top, chain_num=0):
-    """process_trace.py:146-166"""
-    if x_top in topologies:
-        topology = topologies[x_top]
-        topology["count"] += 1
-        curr_log_p_one = x["log_p_one"]
-        if curr_log_p_one > topology["log_p_joint_max"]:
-            topology["log_p_joint_max"] = curr_log_p_one
-            topology["iter"] = i
-            topology["topology"] = x_top
-            topology["chain_num"] = chain_num
-    else:
+    """process_trace.py:146-166: one visit of topology `x_top` (trace entry `x`, position `i` in its chain)."""
+    seen = topologies.get(x_top)
+    if seen is None:
         log_mult = x_top.multiplicity
-        topologies[x_top] = {
-            "topology": x_top, "count": 1, "log_p_joint_max": x["log_p_one"], "iter": i, "chain_num": chain_num,
-            "multiplicity": np.exp(log_mult), "log_multiplicity": log_mult,
-        }
+        topologies[x_top] = dict(topology=x_top, count=1, log_p_joint_max=x["log_p_one"], iter=i, chain_num=chain_num,
+                                 multiplicity=np.exp(log_mult), log_multiplicity=log_mult)
+        return
+    seen["count"] += 1
+    if x["log_p_one"] > seen["log_p_joint_max"]:
+        seen.update(log_p_joint_max=x["log_p_one"], iter=i, topology=x_top, chain_num=chain_num)
 
 
 def create_topology_dataframe(topologies):
@@ -189,53 +177,47 @@ def _create_results_output_files(out_table_file, out_tree_file, table, tree):
 
 
 def get_clone_table(data, samples, tree, clusters=None, assignment=None):
-    """process_trace.py:294-320"""
+    """process_trace.py:294-320: one row per (mutation, sample) with the MAP cellular prevalence (`ccf`) and clonal
+    prevalence of the mutation's clone; -1 for mutations outside every clone.  Rows are ordered by clone, then sample,
+    then as in the labels table -- the order the reference's group-by loop produces."""
     labels = get_labels_table(data, tree, clusters=clusters)
-    ccfs, clonal_prev_dict = map_trees([tree])[0] if assignment is None else assignment
-    samples_idx_dict = {k: v for v, k in enumerate(samples)}
-    labels["sample_id"] = [samples] * len(labels)
-    labels = labels.explode("sample_id")
-    grouped = labels.groupby(["clone_id", "sample_id"])
-    df_list = []
-    for name, group in grouped:
-        clone_id, sample_id = name
-        group = group.copy()
-        if clone_id in ccfs:
-            group["ccf"] = ccfs[clone_id][samples_idx_dict[sample_id]]
-            group["clonal_prev"] = clonal_prev_dict[clone_id][samples_idx_dict[sample_id]]
-        else:
-            group["ccf"] = -1
-            group["clonal_prev"] = -1
-        df_list.append(group)
-    return pd.concat(df_list, ignore_index=True)
+    ccfs, clonal_prevs = map_trees([tree])[0] if assignment is None else assignment
+    column_of = {name: k for k, name in enumerate(samples)}
+    rows = labels.loc[labels.index.repeat(len(samples))].copy()
+    rows["sample_id"] = list(samples) * len(labels)
+    rows = rows.sort_values(by=["clone_id", "sample_id"], kind="stable", ignore_index=True)
+    in_tree = rows["clone_id"].isin(list(ccfs)).to_numpy()
+    if in_tree.any():
+        ccf, prev = np.full(len(rows), -1.0), np.full(len(rows), -1.0)
+        for k, (clone, sample) in enumerate(zip(rows["clone_id"], rows["sample_id"])):
+            if in_tree[k]:
+                ccf[k] = ccfs[clone][column_of[sample]]
+                prev[k] = clonal_prevs[clone][column_of[sample]]
+    else:  # nothing but outliers: the reference's columns stay integer
+        ccf = prev = np.full(len(rows), -1, dtype=np.int64)
+    rows["ccf"], rows["clonal_prev"] = ccf, prev
+    return rows
 
 
 def get_labels_table(data, tree, clusters=None):
-    """process_trace.py:323-383"""
-    df_records_list = []
-    clone_muts = set()
-    outlier_node_name = tree.outlier_node_name
-    tree_labels = tree.labels
+    """process_trace.py:323-383: (mutation, clone) pairs of the tree; mutations the tree does not hold are listed under
+    the outlier clone.  With a cluster table the tree's data points are clusters and every cluster expands to its
+    mutations."""
+    outlier = tree.outlier_node_name
+    clone_of = tree.labels
     if clusters is None:
-        for idx in tree_labels:
-            df_records_list.append({"mutation_id": data[idx].name, "clone_id": tree_labels[idx]})
-            clone_muts.add(data[idx].name)
-        for x in data:
-            if x.name not in clone_muts:
-                df_records_list.append({"mutation_id": x.name, "clone_id": outlier_node_name})
-        df = pd.DataFrame(df_records_list)
-        df = df.sort_values(by=["clone_id", "mutation_id"])
-    else:
-        clusters_grouped = clusters.groupby("cluster_id")
-        for idx in tree_labels:
-            cluster_id = int(data[idx].name)
-            clone_id = tree_labels[idx]
-            muts_set = clusters_grouped.get_group(cluster_id)["mutation_id"].unique()
-            df_records_list.extend({"mutation_id": mut, "clone_id": clone_id, "cluster_id": cluster_id} for mut in muts_set)
-            clone_muts.update(muts_set)
-        missing_muts_df = clusters.loc[~clusters["mutation_id"].isin(clone_muts)].copy()
-        missing_muts_df["clone_id"] = outlier_node_name
-        df_records_list.extend(missing_muts_df.to_dict("records"))
-        df = pd.DataFrame(df_records_list)
-        df = df.sort_values(by=["clone_id", "cluster_id", "mutation_id"])
-    return df
+        placed = [(data[idx].name, clone) for idx, clone in clone_of.items()]
+        taken = {name for name, _ in placed}
+        placed += [(x.name, outlier) for x in data if x.name not in taken]
+        table = pd.DataFrame(placed, columns=["mutation_id", "clone_id"])
+        return table.sort_values(by=["clone_id", "mutation_id"])
+    members = {cid: grp["mutation_id"].unique() for cid, grp in clusters.groupby("cluster_id")}
+    placed = []
+    for idx, clone in clone_of.items():
+        cid = int(data[idx].name)
+        placed += [(mut, clone, cid) for mut in members[cid]]
+    taken = {mut for mut, _, _ in placed}
+    rest = clusters.loc[~clusters["mutation_id"].isin(taken)]
+    placed += [(mut, outlier, cid) for mut, cid in zip(rest["mutation_id"], rest["cluster_id"])]
+    table = pd.DataFrame(placed, columns=["mutation_id", "clone_id", "cluster_id"])
+    return table.sort_values(by=["clone_id", "cluster_id", "mutation_id"])
