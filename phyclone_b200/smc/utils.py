@@ -1,29 +1,37 @@
-"""Data-point order for SMC (reference smc/utils.py:16-119).  Host-side combinatorics, no arithmetic."""
+"""Order in which an SMC sweep visits the data points of the current tree (reference smc/utils.py:16-119): a random
+linear extension of "descendants before ancestors" -- the points of a subtree come before the points of its root
+node -- with the outliers shuffled in anywhere.  Host-side combinatorics; what matters for parity is the sequence of
+`rng.shuffle` calls, which is the reference's."""
 
 from itertools import repeat
+
+
+def interleave_lists(lists, rng):
+    """A uniformly random merge of the lists that keeps the order inside each (smc/utils.py:103-119): shuffle one
+    marker per element, then deal the lists out in marker order."""
+    markers = []
+    for which, lst in enumerate(lists):
+        markers.extend(repeat(which, len(lst)))
+    rng.shuffle(markers)
+    heads = [iter(lst) for lst in lists]  # the reference pops from the front of each list: O(n) per element
+    return [next(heads[which]) for which in markers]
+
+
+def _subtree_order(tree, rng, node):
+    """Points below `node` in a random compatible order, then the node's own points in random order."""
+    below = interleave_lists([_subtree_order(tree, rng, child) for child in tree.get_children(node)], rng)
+    own = tree.get_data(node)
+    rng.shuffle(own)
+    below.extend(own)
+    return below
 
 
 class RootPermutationDistribution(object):
     @staticmethod
     def sample(tree, rng, source=None):
-        if source is None:
-            sigma = [RootPermutationDistribution.sample(tree, rng, source=node) for node in tree.roots]
-            sigma = interleave_lists(sigma, rng)
-            outliers = list(tree.outliers)
-            rng.shuffle(outliers)
-            return interleave_lists([sigma, outliers], rng)
-        child_sigma = [RootPermutationDistribution.sample(tree, rng, source=child) for child in tree.get_children(source)]
-        sigma = interleave_lists(child_sigma, rng)
-        source_sigma = tree.get_data(source)
-        rng.shuffle(source_sigma)
-        sigma.extend(source_sigma)
-        return sigma
-
-
-def interleave_lists(lists, rng):
-    sentinels = []
-    for i, lst in enumerate(lists):
-        sentinels.extend(repeat(i, len(lst)))
-    rng.shuffle(sentinels)
-    heads = [iter(lst) for lst in lists]  # the reference pops from the front of each list: O(n) per element
-    return [next(heads[idx]) for idx in sentinels]
+        if source is not None:
+            return _subtree_order(tree, rng, source)
+        in_tree = interleave_lists([_subtree_order(tree, rng, root) for root in tree.roots], rng)
+        outliers = list(tree.outliers)
+        rng.shuffle(outliers)
+        return interleave_lists([in_tree, outliers], rng)
