@@ -92,3 +92,25 @@ def test_tree_node_dropin(golden):
         n.log_p[...] = golden["logs_logp_%d" % k]
         n.update_node_from_child_r_vals([tiles[i] for i in golden["logs_idx_%d" % k]])
         assert_close_bucketed(n.log_r, golden["logs_logr_%d" % k], what="golden node %d" % k, max_boundary=8)
+
+
+def test_the_ctypes_stub_printed_in_integration_md_works():
+    """INTEGRATION.md shows the binding a PhyClone maintainer would paste into phyclone/tree/utils.py; run exactly that
+    text against the built library so that the document cannot drift from the ABI."""
+    import re
+
+    from phyclone_b200 import _lib
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    stub = re.findall(r"```python\n(.*?)```", text, flags=re.S)[0]
+    assert "pcb_np_conv_dims_host" in stub and "def compute_log_S" in stub
+    stub = stub.replace('ctypes.CDLL("libphyclone_b200.so")', "ctypes.CDLL(%r)" % _lib.LIB_PATH)
+    ns = {}
+    exec(compile(stub, "INTEGRATION.md", "exec"), ns)  # noqa: S102 -- our own documentation
+    rng = np.random.default_rng(0)
+    a, b, c = (np.log(rng.uniform(0.1, 1000, (8, 101))) for _ in range(3))
+    assert_close(ns["_np_conv_dims"](a, b), onum.conv_pair(a, b), 1e-9, "stub conv")
+    assert_close(ns["_sub_compute_S"](a), onum.prefix_lse(a), 1e-9, "stub scan")
+    assert_close(ns["compute_log_S"]([a, b, c]), onum.log_s([a, b, c]), 1e-9, "stub log_S")
+    assert ns["compute_log_S"]([]) == 0.0
