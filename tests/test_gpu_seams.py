@@ -114,3 +114,30 @@ def test_the_ctypes_stub_printed_in_integration_md_works():
     assert_close(ns["_sub_compute_S"](a), onum.prefix_lse(a), 1e-9, "stub scan")
     assert_close(ns["compute_log_S"]([a, b, c]), onum.log_s([a, b, c]), 1e-9, "stub log_S")
     assert ns["compute_log_S"]([]) == 0.0
+
+
+def test_the_map_stub_printed_in_integration_md_works():
+    """Same for the MAP binding (second code block of INTEGRATION.md), on a tree solved by the reference."""
+    import re
+
+    import networkx as nx
+
+    from phyclone_b200 import _lib
+    from tests.map_utils import case_paths, load_case
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    blocks = re.findall(r"```python\n(.*?)```", open(os.path.join(root, "INTEGRATION.md")).read(), flags=re.S)
+    ns = {"nx": nx}
+    exec(compile(blocks[0].replace('ctypes.CDLL("libphyclone_b200.so")', "ctypes.CDLL(%r)" % _lib.LIB_PATH),
+                 "INTEGRATION.md#1", "exec"), ns)  # noqa: S102
+    exec(compile(blocks[1], "INTEGRATION.md#2", "exec"), ns)  # noqa: S102
+    c = load_case(case_paths()[1])
+    graph = nx.DiGraph()
+    for v, kids in enumerate(c["children"]):
+        graph.add_node(v, log_p=c["log_p"][v])
+    for v, kids in enumerate(c["children"]):
+        for k in kids:
+            graph.add_edge(v, k)
+    got = ns["map_indices"](graph, 0)
+    for v in range(len(c["children"])):
+        np.testing.assert_array_equal(got[v], c["max_idx"][v])
