@@ -25,19 +25,43 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CFG = {"clusters": 50, "samples": 8, "grid": 101, "particles": 100, "muts_per_cluster": 10, "depth": 200,
-       "proposal": "semi-adapted", "resample_threshold": 0.5, "precision": 400, "density": "beta-binomial"}
-WORKLOAD = ("synthetic 50 clusters x 8 samples, grid 101, 100 particles, semi-adapted proposal, 1 chain per GPU "
-            "(BASELINE.json configs[1]); data seed 0, chain seed 1")
 METRIC = "pg_iterations_per_sec"
 UNIT = "PG iterations/s"
+CFG = None  # set by main() from --config (phyclone_b200/workloads.py)
+
+
+def set_config(number):
+    global CFG
+    from phyclone_b200 import workloads
+
+    CFG = workloads.config_dict(number)
+    return CFG
 
 
 # ----------------------------------------------------------------------------- inputs
-def synthetic_counts():
-    from phyclone_b200.simulate import simulate_counts
+def workload_values_cpu():
+    """[T,S,G] grids of the configured workload computed on the CPU (NumPy oracle): CPU arms only."""
+    from oracle import numerics as onum
+    from phyclone_b200 import workloads
 
-    return simulate_counts(CFG["clusters"], CFG["samples"], CFG["muts_per_cluster"], CFG["depth"], seed=0)
+    c = workloads.counts(CFG)
+    if c is None:
+        return workloads.fixture_values(CFG)
+    grids = onum.likelihood_grid(c["ref"], c["alt"], c["tumour_content"], c["cn"], c["mu"], c["log_pi"], c["n_geno"],
+                                 CFG["grid"], CFG["density"], CFG["precision"])
+    return onum.cluster_sum(grids, c["cluster_off"])
+
+
+def workload_values_gpu(ops):
+    """The same grids through the device path (a2/a3 of the hot path); one-off, not timed."""
+    from phyclone_b200 import workloads
+
+    c = workloads.counts(CFG)
+    if c is None:
+        return workloads.fixture_values(CFG)
+    grids = ops.likelihood_grid(c["ref"], c["alt"], c["tumour_content"], c["cn"], c["mu"], c["log_pi"], c["n_geno"],
+                                CFG["grid"], CFG["density"], CFG["precision"])
+    return ops.cluster_sum(grids, c["cluster_off"])
 
 
 def chain_rng(rank, world):
@@ -139,62 +163,132 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU arms
-def oracle_chain_rate(iters, warmup, chain=0, n_chains=1):
-    """PG iterations/s of the CPU port of the reference (oracle/sampler.py, with the reference's tile
-    caches on: its real configuration) on the same workload; 1 core (a chain is single-threaded)."""
-    from oracle import sampler as osm
-    from oracle.synthetic import make_synthetic
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+REF_SHIM = os.path.join(ROOT, "oracle", "refshim")
 
-    syn = make_synthetic(CFG["clusters"], CFG["samples"], CFG["grid"], CFG["muts_per_cluster"], CFG["depth"], seed=0,
-                         density=CFG["density"], precision=CFG["precision"])
-    data = [osm.Datum(i, v) for i, v in enumerate(syn["values"])]
+
+def reference_available():
+    return os.path.isdir(os.path.join(REF_DIR, "phyclone"))
+
+
+def reference_chain_times(values, outlier_probs, cfg, iters, warmup, chain, n_chains, max_seconds):
+    """The UNMODIFIED reference (pip-installed into baseline/_ref by scripts/install_reference.sh; its absent Rust
+    dependency `rustworkx` is served by oracle/refshim) run through its own public entry point
+    `phyclone.run.run_phyclone_chain` (run.py:177-232): 1 burn-in sweep, then warmup + iters PG iterations, caches
+    on (its real configuration).  Returns the cumulative `time` field of its trace entries (entry j = after
+    iteration j-1; its Timer covers burn-in and main loop, run.py:262) -- fewer entries than asked if the wall cap
+    `max_seconds` (the reference's own --max-time) stopped it."""
+    import io
+    from contextlib import redirect_stdout
+
+    for p in (REF_SHIM, REF_DIR):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from phyclone.data.base import DataPoint as RefDataPoint
+    from phyclone.run import run_phyclone_chain as ref_run
+
+    data = []
+    for i, v in enumerate(values):
+        op, opn = (0, 1) if outlier_probs is None else outlier_probs[i]
+        data.append(RefDataPoint(i, v, outlier_prob=op, outlier_prob_not=opn))
+    with redirect_stdout(io.StringIO()):
+        res = ref_run(1, True, 1.0, data, float(max_seconds), warmup + iters, cfg["particles"], 1, 1, cfg["outlier_prob"],
+                      10**9, cfg["proposal"], cfg["resample_threshold"], chain_rng(chain, n_chains), ["s"], 1, chain, 0.0)
+    return [e["time"] for e in res["trace"]]
+
+
+def port_chain_times(values, outlier_probs, cfg, iters, warmup, chain, n_chains, max_seconds):
+    """Same contract as reference_chain_times for the CPU port (oracle/sampler.py, the reference's tile caches on)."""
+    from oracle import sampler as osm
+
+    data = []
+    for i, v in enumerate(values):
+        op, opn = (0, 1) if outlier_probs is None else outlier_probs[i]
+        data.append(osm.Datum(i, v, outlier_prob=op, outlier_prob_not=opn))
+    t_start = time.perf_counter()
     marks = []
-    res = osm.run_chain(data, chain_rng(chain, n_chains), warmup + iters, burnin=1, num_particles=CFG["particles"],
-                        proposal=CFG["proposal"], resample_threshold=CFG["resample_threshold"], use_tile_caches=True,
-                        on_iteration=lambda i, e: marks.append(time.perf_counter()))
-    t0 = marks[warmup - 1] if warmup > 0 else None
-    if t0 is None:
-        raise ValueError("need at least one warm-up iteration for the CPU arm")
-    elapsed = marks[-1] - t0
-    return iters / elapsed, elapsed, res["extensions"]
+
+    class Stop(Exception):
+        pass
+
+    def on_it(i, e):
+        marks.append(time.perf_counter() - t_start)
+        if marks[-1] >= max_seconds:
+            raise Stop()
+
+    try:
+        osm.run_chain(data, chain_rng(chain, n_chains), warmup + iters, burnin=1, num_particles=cfg["particles"],
+                      proposal=cfg["proposal"], resample_threshold=cfg["resample_threshold"],
+                      outlier_prob=cfg["outlier_prob"], use_tile_caches=True, on_iteration=on_it)
+    except Stop:
+        pass
+    # entry 0 = the end of burn-in is not observable through on_iteration: the first warm-up iteration absorbs it
+    return [0.0] + marks
+
+
+def _cpu_chain(kind, cfg, iters, warmup, chain, n_chains, max_seconds):
+    global CFG
+    CFG = cfg
+    from phyclone_b200 import workloads
+
+    values = workload_values_cpu()
+    fn = reference_chain_times if kind == "reference" else port_chain_times
+    return fn(values, workloads.outlier_log_probs(cfg), cfg, iters, warmup, chain, n_chains, max_seconds)
+
+
+def cpu_rate(kind, iters, warmup, n_chains=1, max_seconds=420.0):
+    """(PG iterations/s whole job, timed iterations per chain actually run, warm-up actually run, wall seconds,
+    cores) of the CPU arm `kind` ("reference" | "port") on the configured workload.  Chains run side by side in
+    one single-threaded process each, as the reference's ProcessPoolExecutor does (run.py:111-149)."""
+    cores = min(n_chains, os.cpu_count() or 1)
+    warmup = max(warmup, 1)  # the first iteration carries the Numba JIT / first-touch costs
+    t0 = time.perf_counter()
+    if n_chains == 1:
+        traces = [_cpu_chain(kind, CFG, iters, warmup, 0, 1, max_seconds)]
+    else:
+        from concurrent.futures import ProcessPoolExecutor
+
+        with ProcessPoolExecutor(max_workers=cores) as pool:
+            futs = [pool.submit(_cpu_chain, kind, CFG, iters, warmup, c, n_chains, max_seconds) for c in range(n_chains)]
+            traces = [f.result() for f in futs]
+    wall = time.perf_counter() - t0
+    done = min(len(t) - 1 for t in traces)  # iterations every chain completed
+    warm_done = min(warmup, max(done - 1, 0))
+    timed = done - warm_done
+    if timed < 1:
+        return None, 0, warm_done, wall, cores
+    # the chains ran side by side (in waves if there are fewer cores than chains): the job's time for the timed
+    # iterations is the slowest chain's, times the number of waves
+    waves = -(-n_chains // cores)
+    elapsed = max(t[warm_done + timed] - t[warm_done] for t in traces) * waves
+    return n_chains * timed / elapsed, timed, warm_done, wall, cores
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # bounded sample: at ~10 s per iteration, cap the timed iterations so the run ends within a few minutes
-    iters = min(args.steps, 12)
-    warm = min(max(args.warmup, 1), 2)
-    n_chains = max(args.gpus, 1)  # the GPU arm runs one chain per GPU: same job here
-    cores = min(n_chains, os.cpu_count() or 1)
-    if n_chains == 1:
-        rate, elapsed, ext = oracle_chain_rate(iters, warm)
-    else:
-        # the reference runs its chains in a ProcessPoolExecutor, one single-threaded process per chain (run.py:111-149)
-        from concurrent.futures import ProcessPoolExecutor
-
-        with ProcessPoolExecutor(max_workers=cores) as pool:
-            t0 = time.perf_counter()
-            futs = [pool.submit(oracle_chain_rate, iters, warm, c, n_chains) for c in range(n_chains)]
-            done = [f.result() for f in futs]
-            wall = time.perf_counter() - t0
-        # whole-job rate over the timed iterations: chains ran side by side (queued if there are fewer cores)
-        waves = -(-n_chains // cores)
-        elapsed = max(d[1] for d in done) * waves if waves > 1 else max(d[1] for d in done)
-        rate = n_chains * iters / elapsed
-        elapsed = wall
-    sample = ("%d timed PG iterations per chain, %d chain(s) in %d process(es), after 1 burn-in + %d warm-up iterations "
-              "(%.1f s wall); a chain is single-threaded in the reference" % (iters, n_chains, cores, warm, elapsed))
+    kind = "reference" if reference_available() and not args.port else "port"
+    n_chains = max(args.gpus, 1) if args.chains is None else args.chains  # same job as the GPU arm
+    rate, timed, warm, wall, cores = cpu_rate(kind, args.steps, args.warmup, n_chains, args.ref_max_seconds)
+    if rate is None:
+        print(json.dumps({"impl": "reference", "unavailable": "no PG iteration of %s finished within the %.0f s cap "
+                                                               "(%s)" % (CFG["workload"], args.ref_max_seconds, kind)}))
+        return
+    how = ("unmodified reference (phyclone 0.5.1 pip-installed into baseline/_ref, rustworkx served by oracle/refshim), "
+           "phyclone.run.run_phyclone_chain, caches on" if kind == "reference"
+           else "CPU port of the reference sampler (oracle/sampler.py, tile caches on)")
+    sample = ("%d timed PG iterations per chain (asked: %d) after 1 burn-in sweep + %d warm-up iterations (asked: %d), "
+              "%d chain(s) in %d single-threaded process(es), wall %.1f s, wall cap %.0f s; %s"
+              % (timed, args.steps, warm, args.warmup, n_chains, cores, wall, args.ref_max_seconds, how))
     line = {
-        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 / rate, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": dict(CFG, workload=WORKLOAD, chains=n_chains),
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": timed,
+        "warmup": warm, "requested_steps": args.steps, "requested_warmup": args.warmup, "ms_per_step": 1e3 * n_chains / rate,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": dict(CFG, chains=n_chains),
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-        "note": "CPU port of the reference sampler (oracle/sampler.py, tile caches on); /root/reference is a Python "
-                "package with an uninstallable Rust dependency and does not exist on the GPU box",
+        "gpu_launches": 0, "wall_s": wall,
     }
     print(json.dumps(line))
 
@@ -237,17 +331,16 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- inputs (one-off, a2/a3/a4 of the path on the device; not timed)
-    c = synthetic_counts()
-    grids = ops.likelihood_grid(c["ref"], c["alt"], c["tumour_content"], c["cn"], c["mu"], c["log_pi"], c["n_geno"],
-                                CFG["grid"], CFG["density"], CFG["precision"])
-    values = ops.cluster_sum(grids, c["cluster_off"])
-    data = make_data_points(values)
+    from phyclone_b200 import workloads
+
+    values = workload_values_gpu(ops)
+    data = make_data_points(values, outlier_probs=workloads.outlier_log_probs(CFG))
     fp64_peak, _ = ops.fp64_peak(8192)
     fp64_peak = max(fp64_peak, ops.fp64_peak(8192)[0])
 
     store = TileStore(values, device=dev, variant=TileStore.LATENCY_LAYOUT)  # what run_phyclone_chain uses
     chain = Chain(data, chain_rng(rank, world), num_particles=CFG["particles"], proposal=CFG["proposal"],
-                  resample_threshold=CFG["resample_threshold"], store=store)
+                  resample_threshold=CFG["resample_threshold"], outlier_prob=CFG["outlier_prob"], store=store)
     chain.burnin_step()
     for _ in range(args.warmup):
         chain.step()
@@ -358,10 +451,13 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, elapsed, _ = oracle_chain_rate(2, 1)
-        cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": "2 PG iterations of the same config after 1 burn-in + 1 warm-up iteration (%.1f s), "
-                         "oracle/sampler.py with the reference's tile caches on" % elapsed}
+        kind = "reference" if reference_available() else "port"
+        rate, timed_it, warm_it, wall, _ = cpu_rate(kind, 2, 1, 1, 120.0)
+        cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": kind,
+               "sample": "%d PG iterations of the same config after 1 burn-in sweep + %d warm-up iteration (%.1f s wall, "
+                         "cap 120 s); %s" % (timed_it, warm_it, wall,
+                                             "unmodified reference from baseline/_ref, caches on" if kind == "reference"
+                                             else "oracle/sampler.py with the reference's tile caches on")}
 
     if rank == 0:
         peaks = {}
@@ -380,11 +476,11 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": dict(CFG, workload=WORKLOAD, chains=world,
-                           l2="no explicit flush: one iteration allocates %d fresh tiles (~%d MB) in the arena, larger than "
-                              "the 126 MB L2" % ((s1["adds"] + s1["node_jobs"] - s0["adds"] - s0["node_jobs"]) // args.steps,
-                                                 (s1["adds"] + s1["node_jobs"] - s0["adds"] - s0["node_jobs"]) // args.steps
-                                                 * store.arena.layout.tile_elems * 16 // (1 << 20))),
+            "config": dict(CFG, chains=world),
+            "l2": "no explicit flush: one iteration allocates %d fresh tiles (~%d MB) in the arena, larger than the 126 MB "
+                  "L2" % ((s1["adds"] + s1["node_jobs"] - s0["adds"] - s0["node_jobs"]) // args.steps,
+                          (s1["adds"] + s1["node_jobs"] - s0["adds"] - s0["node_jobs"]) // args.steps
+                          * store.arena.layout.tile_elems * 16 // (1 << 20)),
             "particle_extensions_per_sec": ext / (ms * 1e-3),
             "value_without_kernel_timing": value_plain,  # same iterations, no CUDA events around the kernel launches
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
@@ -417,7 +513,14 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mps-chains", action="store_true", help="skip the 8-chains-on-one-GPU (MPS) leg")
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 4, 5],
+                    help="BASELINE.json configuration number (1-based; 3 = config 2 with --chains 8)")
+    ap.add_argument("--chains", type=int, default=None, help="number of chains of the job (default: one per GPU)")
+    ap.add_argument("--port", action="store_true", help="reference arm: time the CPU port instead of baseline/_ref")
+    ap.add_argument("--ref-max-seconds", type=float, default=420.0,
+                    help="reference arm: wall cap handed to the reference's own --max-time")
     args = ap.parse_args()
+    set_config(args.config)
     if args.impl == "reference":
         run_reference_arm(args)
     else:
