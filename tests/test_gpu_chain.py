@@ -70,7 +70,42 @@ def test_free_running_chain_matches_reference_trace(name):
         if name != "mixing":
             raise
         assert all(np.isfinite(t["log_p_one"]) for t in res["trace"])
-        pytest.xfail("free-running chain left the recorded trajectory on a multinomial knife edge: %s" % e)
+        pytest.xfail("free-running chain left the recorded trajectory on a multinomial knife edge: %s; %s"
+                     % (e, _first_divergence(g)))
+
+
+def _first_divergence(g):
+    """Where the free-running GPU chain leaves the oracle's: both run from the same seed with every draw recorded;
+    report the first call whose inputs or outcome differ -- the two probability vectors, their largest difference in
+    ulps, and numpy's knife-edge quantity p_k / remaining_p next to 0.5."""
+    from tests.tape import RecordingRNG
+    from tests.test_tape_cpu import record_oracle
+
+    _, tape_o = record_oracle(g)
+    rec = RecordingRNG(np.random.default_rng(int(g["meta"][0])))
+    _run(g, rec)
+    for k, (a, b) in enumerate(zip(tape_o, rec.tape)):
+        if a[0] != b[0]:
+            return "call %d: oracle drew %s, GPU sampler drew %s" % (k, a[0], b[0])
+        if a[0] == "multinomial":
+            (n0, p0), (n1, p1) = a[1], b[1]
+            same_in = n0 == n1 and p0.shape == p1.shape
+            if not same_in or not np.array_equal(a[2], b[2]):
+                if not same_in:
+                    return "call %d: multinomial shapes differ (%s vs %s)" % (k, p0.shape, p1.shape)
+                ulp = np.abs(p0 - p1) / np.maximum(np.spacing(np.abs(p0)), 5e-324)
+                j = int(np.argmax(ulp))
+                rem = 1.0 - np.cumsum(p0)[:-1]
+                ratio = p0[1:] / np.where(rem > 0, rem, np.nan)
+                near = float(np.nanmin(np.abs(ratio - 0.5))) if ratio.size else float("nan")
+                return ("first diverging draw = call %d, multinomial(n=%d) over %d weights: outcomes %s (oracle) vs %s "
+                        "(GPU); probability vectors differ by at most %.1f ulp (entry %d: %.17g vs %.17g); closest "
+                        "p_k/remaining_p to the 0.5 branch point of numpy's binomial: |ratio - 0.5| = %.3e"
+                        % (k, n0, p0.size, np.flatnonzero(a[2]).tolist()[:8], np.flatnonzero(b[2]).tolist()[:8],
+                           float(ulp.max()), j, p0[j], p1[j], near))
+        elif a[0] in ("random", "integers") and a[2] != b[2]:
+            return "call %d: %s outcomes differ although the generators were seeded alike" % (k, a[0])
+    return "no diverging draw found in %d calls (traces differ only in floating point)" % min(len(tape_o), len(rec.tape))
 
 
 def test_outlier_marginals_on_device():
@@ -125,25 +160,26 @@ def test_arena_grows_on_demand():
         assert a["log_p_one"] == b["log_p_one"] and a["alpha"] == b["alpha"]
 
 
-@pytest.mark.parametrize("depth", [200, 2000])
-def test_replayed_chain_at_bench_config(depth):
-    """BASELINE configs[1] at full size (50 clusters x 8 samples, grid 101, 100 particles; depth 2000 is the
-    floor-exercising variant of SURVEY.md 8d): one burn-in sweep and one PG iteration of the CPU port, its
-    draws replayed into the GPU sampler, which must ask for the same draws from the same distributions (1e-9)
-    and produce the same topologies, alpha and log_p_one."""
-    from oracle.synthetic import make_synthetic
-    from phyclone_b200.data.base import make_data_points
+def _replay_against_oracle(vals, probs, particles, outlier_prob, proposal, burnin, iters, what, store=None, dp_factory=None):
+    """One oracle chain with its draws recorded, replayed into the GPU sampler: the GPU sampler must ask for the same
+    draws from the same distributions (1e-9) and produce the same topologies, alpha and log_p_one."""
     from phyclone_b200.run import run_phyclone_chain
     from tests.chain_utils import signature
     from tests.tape import RecordingRNG, ReplayRNG
 
-    syn = make_synthetic(50, 8, 101, 10, depth, seed=0, density="beta-binomial", precision=400)
-    vals = syn["values"]
+    if dp_factory is None:
+        from phyclone_b200.data.base import make_data_points
     rec = RecordingRNG(np.random.default_rng(1))
-    want = osm.run_chain([osm.Datum(i, v) for i, v in enumerate(vals)], rec, 1, burnin=1, num_particles=100)
+    if probs is None:
+        odata = [osm.Datum(i, v) for i, v in enumerate(vals)]
+    else:
+        odata = [osm.Datum(i, v, outlier_prob=probs[i][0], outlier_prob_not=probs[i][1]) for i, v in enumerate(vals)]
+    want = osm.run_chain(odata, rec, iters, burnin=burnin, num_particles=particles, proposal=proposal,
+                         outlier_prob=outlier_prob)
     rep = ReplayRNG(rec.tape)
-    res = run_phyclone_chain(1, True, 1.0, make_data_points(vals), float("inf"), 1, 100, 1, 1, 0, 10**9, "semi-adapted",
-                             0.5, rep, ["s"], 1, 0, 0.0)
+    data = make_data_points(vals, outlier_probs=probs) if dp_factory is None else dp_factory(vals, probs)
+    res = run_phyclone_chain(burnin, True, 1.0, data, float("inf"), iters, particles,
+                             1, 1, outlier_prob, 10**9, proposal, 0.5, rep, ["s"], 1, 0, 0.0, store=store)
     assert rep.done()
     assert len(res["trace"]) == len(want["trace"])
     for got, ref in zip(res["trace"], want["trace"]):
@@ -152,7 +188,54 @@ def test_replayed_chain_at_bench_config(depth):
         a = signature(got["tree"], len(vals))
         b = signature(ref["tree"], len(vals), name_of=lambda dp: dp.idx)
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
-    print("depth %d: %d draws replayed, max relative probability error %.2e" % (depth, len(rec.tape), rep.max_p_err))
+    print("%s: %d draws replayed, max relative probability error %.2e, stats %s" % (
+        what, len(rec.tape), rep.max_p_err, res["stats"]))
+    return res
+
+
+@pytest.mark.parametrize("depth", [200, 2000])
+def test_replayed_chain_at_bench_config(depth):
+    """BASELINE configs[1] at full size (50 clusters x 8 samples, grid 101, 100 particles; depth 2000 is the
+    floor-exercising variant of SURVEY.md 8d): one burn-in sweep and one PG iteration of the CPU port, its
+    draws replayed into the GPU sampler."""
+    from oracle.synthetic import make_synthetic
+
+    syn = make_synthetic(50, 8, 101, 10, depth, seed=0, density="beta-binomial", precision=400)
+    _replay_against_oracle(syn["values"], None, 100, 0, "semi-adapted", 1, 1, "config #2, depth %d" % depth)
+
+
+def test_replayed_chain_at_config4_shape():
+    """BASELINE configs[3] at full size: 100 clusters x 20 samples, grid 201, outlier modelling on (outlier_prob 1e-3:
+    outlier candidates in every proposal, outlier marginals, the outlier Gibbs candidate), 100 particles; one burn-in
+    sweep and one PG iteration (~20 k extensions), the (20,201) tile layout driven through the whole sampler."""
+    from oracle.synthetic import make_synthetic
+    from phyclone_b200 import workloads
+
+    cfg = workloads.config_dict(4)
+    syn = make_synthetic(cfg["clusters"], cfg["samples"], cfg["grid"], cfg["muts_per_cluster"], cfg["depth"], seed=0,
+                         density=cfg["density"], precision=cfg["precision"])
+    res = _replay_against_oracle(syn["values"], workloads.outlier_log_probs(cfg), cfg["particles"], cfg["outlier_prob"],
+                                 "semi-adapted", 1, 1, "config #4 shape")
+    assert res["stats"]["extensions"] >= 19000
+
+
+def test_replayed_chain_at_reduced_config5():
+    """Reduced BASELINE configs[4]: 300 unclustered mutations x 4 samples, grid 101, **500 particles** (the
+    unit-per-warp kernel that S = 4 selects, the Gibbs sampler over 300 data points, ~300 k extensions)."""
+    from oracle.synthetic import make_synthetic
+
+    syn = make_synthetic(300, 4, 101, 1, 200, seed=0, density="beta-binomial", precision=400)
+    res = _replay_against_oracle(syn["values"], None, 500, 0, "semi-adapted", 1, 1, "reduced config #5")
+    assert res["stats"]["extensions"] >= 290000
+
+
+@pytest.mark.parametrize("proposal,points", [("fully-adapted", 20), ("bootstrap", 24)])
+def test_replayed_other_proposals(proposal, points):
+    """Fully-adapted (R + 2^R candidates per parent) and bootstrap proposals at >= 20 data points x 50 particles."""
+    from oracle.synthetic import make_synthetic
+
+    syn = make_synthetic(points, 4, 41, 4, 400, seed=0)
+    _replay_against_oracle(syn["values"], None, 50, 0, proposal, 1, 1, "%s, %d points x 50 particles" % (proposal, points))
 
 
 def test_in_extension_flush_equals_generic_flush(monkeypatch):

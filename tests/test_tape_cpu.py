@@ -46,3 +46,21 @@ def test_tape_replay_cpu(name):
     compare_trace(res["trace"], g, 1e-12, name)  # recording does not disturb the oracle
     res2, rep = replay_product(g, tape, FakeTileStore(g["values"]))
     compare_trace(res2["trace"], g, 1e-9, name + " (replayed)")
+
+
+@pytest.mark.parametrize("proposal,points", [("fully-adapted", 20), ("bootstrap", 24)])
+def test_tape_replay_other_proposals_cpu(proposal, points):
+    """Host logic of the GPU test `test_replayed_other_proposals` (>= 20 data points x 50 particles) on the NumPy
+    executor: fully-adapted enumerates R + 2^R candidates per parent, bootstrap draws blind."""
+    from oracle import numerics as onum
+    from oracle.synthetic import make_synthetic
+    from phyclone_b200.data.base import DataPoint
+    from tests.test_gpu_chain import _replay_against_oracle
+
+    syn = make_synthetic(points, 4, 41, 4, 400, seed=0)
+
+    def cpu_points(vals, probs):
+        return [DataPoint(i, v, outlier_marginal_prob=onum.outlier_marginal(v)) for i, v in enumerate(vals)]
+
+    _replay_against_oracle(syn["values"], None, 50, 0, proposal, 1, 1, proposal, store=FakeTileStore(syn["values"]),
+                           dp_factory=cpu_points)
