@@ -110,7 +110,8 @@ int pcb_tile_add_dev(const pcb_arena* arena, const int32_t* a_ids, const int32_t
  *   [0] first index into children[]        [1] number of children (>= 1)
  *   [2] base tile id (log_p) or -1         [3] output tile id or -1 (scores only)
  *   [4] flags (PCB_JOB_*)                  [5] score slot or -1
- *   [6],[7] reserved (0)
+ *   [6] second base tile id + 1, or 0: log_p = tile(base) + tile(base2) formed on the fly (a node refresh right after
+ *       `log_p += value`, tree/tree_node.py:42-52 then :61-71)          [7] reserved (0)
  */
 #define PCB_JOB_SCAN 1      /* apply the prefix log-sum-exp (log_S); without it the job yields log_D */
 #define PCB_JOB_ADD_PRIOR 2 /* add the scalar `prior` (the dummy root's log_p = -log G) */
@@ -215,6 +216,47 @@ int pcb_normalize_segments_dev(const double* log_p, const int64_t* seg_off_dev, 
 /* optional device resampling mode: ancestors[i] = inverse
  * CDF of W at uniforms[i] (NumPy restatement: oracle.numerics.ancestors_from_uniforms) */
 int pcb_resample_host(const double* W, int64_t N, const double* uniforms, int64_t n_draws, int64_t* ancestors);
+
+/* ---- device-resident SMC sweep ------------------------------------------ */
+/* One whole (conditional) SMC sweep over T data points with N particles on the device, no host round trip between
+ * steps: semi-adapted proposal normalisation (smc/kernels/semi_adapted.py:36-194), the particles' draws, particle
+ * construction and incremental weights (smc/kernels/base.py:38-67, smc/samplers/base.py:32-58), swarm weights / ESS
+ * (smc/swarm/swarm.py:21-61), adaptive multinomial resampling (smc/samplers/conditional.py:76-125,
+ * standard.py:20-45) and the final pick (mcmc/particle_gibbs.py:42-48).
+ * Draws are inverse-CDF transforms of uniforms u(seed, step, slot, draw number) (splitmix64 counter hash); the CPU
+ * definition of this mode is oracle/uniform.py.  A particle is the root level of its forest; record layouts:
+ *   int record  [5 + 9*Rmax]: R, n_nodes, n_slots, n_edges, n_outliers, then Rmax-strided fields
+ *                name, log_r tile, log_p tile, n_data, subtree size, edge slot, graph index, kid offset, kid count
+ *   dbl record  [8]: crp sum, multiplicity, outlier prior, outlier marginal, log_p, log_p_one, log_w increment, 0
+ * Conditional sweeps take the retained path as T such records per view: `ret_th_*` = the retained particle after
+ * step t re-read through Tree.from_dict (what extends it), `ret_ba_*` = the same tree as built (what its proposal's
+ * candidates are scored on), `ret_key` = its structure hash, `ret_kids` = the child tile lists its kid offsets index.
+ * Tiles: [tile_base, tile_base + N*Rmax) is per-step candidate scratch, the rest up to tile_limit is handed out to new
+ * root / node tiles.  Small control tables are HOST pointers (copied inside); outputs are HOST buffers filled after the
+ * one stream synchronisation at the end.  status: 0 ok, else bit 1 = more than Rmax roots, 2 = tile range exhausted,
+ * 4 = kid pool exhausted, 8 = non-finite weights (the sweep's outputs are then void). */
+typedef struct {
+  int32_t N, T, Rmax, conditional, outliers, n_tab, n_ret_kids, reserved;
+  double log_alpha, threshold, log_half, log_uniform, lw_uniform, prior;
+  uint64_t seed;
+  int64_t tile_base, tile_limit;
+  const int32_t *dp_idx, *value_id, *single_id; /* [T] */
+  const double *dp_op, *dp_opn, *dp_marg;        /* [T] outlier log prob, not-outlier log prob, outlier marginal */
+  const double *lfact, *logn, *rterm;            /* [n_tab] log n!, log n, FS-CRP root-count term */
+  const int32_t *ret_th_int, *ret_ba_int;        /* [T][5 + 9*Rmax] */
+  const double *ret_th_dbl, *ret_ba_dbl;         /* [T][8] */
+  const uint64_t* ret_key;                       /* [T] */
+  const int32_t* ret_kids;                       /* [n_ret_kids] */
+  int32_t *anc, *kind, *name;                    /* [T][N] ancestor of slot i after step t; decision of particle i */
+  uint64_t* mask;                                /* [T][N] adopted roots of a new node (positions in the parent) */
+  double *raw, *logp, *logq;                     /* [T][N] unnormalised log weight, log_p, proposal log prob */
+  double* ess;                                   /* [T] */
+  int32_t* resampled;                            /* [T] */
+  int32_t *final_idx, *status;
+  int64_t *tiles_used, *n_launches, *conv_pairs; /* may be NULL; conv_pairs = pair convolutions the sweep's jobs folded */
+  double* device_ms;                             /* may be NULL: CUDA-event time of the whole sweep */
+} pcb_sweep_desc;
+int pcb_smc_sweep_dev(const pcb_arena* arena, const pcb_sweep_desc* desc, void* stream);
 
 /* FP64 FMA-chain microbenchmark used as the roofline denominator.
  * Returns achieved FLOP/s (2 flop per FMA) over `iters` dependent-chain rounds. */

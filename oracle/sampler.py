@@ -473,9 +473,12 @@ class Forest:
 # FS-CRP prior + joint                                   tree/distributions.py:6-219
 # ------------------------------------------------------------------------------------
 class Joint:
-    def __init__(self, alpha, c_const=1000):
+    def __init__(self, alpha, c_const=1000, perm_dist=False):
         self.alpha = alpha
         self.log_c = np.log(c_const)
+        # True: particle weights carry the root-permutation density (smc/kernels/base.py:49-55), as in the reference's
+        # posterior tests; production runs without it (run.py:403-417 builds the kernel with perm_dist=None)
+        self.perm_dist = perm_dist
 
     @property
     def log_alpha(self):
@@ -550,14 +553,47 @@ def _freeze_key(d):
     )
 
 
+def perm_log_pdf(t):
+    """RootPermutationDistribution.log_pdf (smc/utils.py:18-66): minus the log number of root permutations."""
+
+    def data_len(i):
+        return len(t.members[t.name_of[i]])
+
+    def sub_len(i):
+        return data_len(i) + sum(data_len(c) for c in rx.descendants(t.g, i))
+
+    def multinomial(sizes):  # utils/math.py:159-177
+        if len(sizes) == 0:
+            return 0
+        res = _lfact(sum(sizes))
+        for x in sizes:
+            res -= _lfact(x)
+        return res
+
+    def count(i):
+        total, sizes = 0, []
+        for c in t.g.successor_indices(i):
+            total += count(c)
+            sizes.append(sub_len(c))
+        total += multinomial(sizes)
+        if t.name_of[i] != ROOT:
+            total += _lfact(data_len(i))
+        return total
+
+    n_out = len(t.members[OUT])
+    n_all = len(t.data)
+    return -(count(t.root_i) + _lbinom(n_all, n_out))
+
+
 class Holder:
     """Scored, frozen tree (TreeHolder): hash by clades/outliers, equality by frozen dict."""
 
     __slots__ = ("log_p", "log_p_one", "h", "frozen", "fkey", "tree_roots", "tree_nodes", "labels", "last_added",
-                 "n_children_last", "tm")
+                 "n_children_last", "tm", "log_pdf")
 
     def __init__(self, t, joint):
         self.log_p, self.log_p_one = joint.both(t)
+        self.log_pdf = perm_log_pdf(t) if getattr(joint, "perm_dist", False) else 0.0  # tree_holder.py:62-65
         self.tree_roots = np.asarray(t.roots)
         self.tree_nodes = t.nodes
         self.h = hash(t)
@@ -620,6 +656,8 @@ class Kernel:
         self._new_cache.clear()
 
     def _lru(self, cache, key, make, size=1024):
+        if getattr(self.rng, "unbounded_caches", False):  # uniform-driven mode (oracle/uniform.py): never evict
+            size = 1 << 62
         hit = cache.get(key)
         if hit is not None:
             cache.move_to_end(key)
@@ -645,7 +683,12 @@ class Kernel:
         return SemiAdapted(self, dp, parent, pt)
 
     def particle(self, log_q, parent, holder):  # base.py:38-57 (perm_dist is None in production)
-        lw = holder.log_p - log_q if parent is None else holder.log_p - parent.log_p - log_q
+        if not getattr(self.joint, "perm_dist", False):
+            lw = holder.log_p - log_q if parent is None else holder.log_p - parent.log_p - log_q
+        elif parent is None:
+            lw = holder.log_p + holder.log_pdf - log_q
+        else:
+            lw = holder.log_p - parent.log_p + holder.log_pdf - parent.holder.log_pdf - log_q
         return Particle(lw, parent, holder)
 
     def propose(self, dp, parent):  # base.py:59-67
@@ -719,7 +762,10 @@ class SemiAdapted(_Dist):  # smc/kernels/semi_adapted.py:11-183
 
         def make():
             t = self.parent.thaw()
-            t.new_root(children=kids, data=[self.dp])
+            adopt = kids
+            if getattr(rng, "canonical_adoption", False):  # oracle/uniform.py: descending root position
+                adopt = [c for c in reversed(t.roots) if c in kids]
+            t.new_root(children=adopt, data=[self.dp])
             return Holder(t, self.k.joint)
 
         return self.k._lru(self.k._new_cache, key, make)
@@ -870,35 +916,56 @@ def _last_term(p, last):  # smc/samplers/base.py:52-58
     return p.log_w - p.log_p + p.log_p_one if last else p.log_w
 
 
+def _at(rng, t, i):
+    """Uniform-driven mode (oracle/uniform.py): announce which (SMC step, particle slot) draws next."""
+    at = getattr(rng, "at", None)
+    if at is not None:
+        at(t, i)
+
+
+def _note(kernel, rec):
+    """Decision log for step-level comparisons with the device sweep (tests)."""
+    log = getattr(kernel, "sweep_log", None)
+    if log is not None:
+        log.append(rec)
+
+
 def smc_unconditional(sigma, kernel, n_particles, threshold):  # standard.py + base.py:32-45
     rng = kernel.rng
     T = len(sigma)
     swarm = Swarm()
     for _ in range(n_particles):
         swarm.add(-np.log(n_particles), None)
-    swarm = _maybe_resample(swarm, rng, n_particles, threshold, None)
+    swarm = _maybe_resample(swarm, rng, n_particles, threshold, None, -1, kernel)
     for it in range(T):
         new = Swarm()
-        for lw, parent in zip(swarm.log_weights, swarm.particles):
+        for i, (lw, parent) in enumerate(zip(swarm.log_weights, swarm.particles)):
+            _at(rng, it, i)
             p = kernel.propose(sigma[it], parent)
             new.add(lw + _last_term(p, it >= T - 1), p)
         swarm = new
+        _note(kernel, ("step", it, list(swarm.raw), [p.log_p for p in swarm.particles],
+                       [p.holder.last_added for p in swarm.particles]))
         if it < T - 1:
-            swarm = _maybe_resample(swarm, rng, n_particles, threshold, None)
+            swarm = _maybe_resample(swarm, rng, n_particles, threshold, None, it, kernel)
     return swarm
 
 
-def _maybe_resample(swarm, rng, n_particles, threshold, retained):
+def _maybe_resample(swarm, rng, n_particles, threshold, retained, it=0, kernel=None):
     """standard.py:20-32 / conditional.py:91-109 (`retained` = callable giving the retained particle)."""
     if swarm.relative_ess > threshold:
         return swarm
     new = Swarm()
     lu = -np.log(n_particles)
+    from .uniform import RESAMPLE_SLOT
+
+    _at(rng, it, RESAMPLE_SLOT)
     if retained is None:
         counts = rng.multinomial(n_particles, swarm.weights)
     else:
         counts = rng.multinomial(n_particles - 1, swarm.weights)
         new.add(lu, retained())
+    _note(kernel, ("resample", it, [int(c) for c in counts]))
     for p, m in zip(swarm.particles, counts):
         for _ in range(m):
             new.add(lu, p)
@@ -938,22 +1005,28 @@ def smc_conditional(tree, sigma, kernel, n_particles, threshold):  # conditional
     swarm = Swarm()
     lu = -np.log(n_particles)
     swarm.add(lu, path[1])
-    for _ in range(n_particles - 1):
+    for i in range(1, n_particles):
+        _at(rng, 0, i)
         swarm.add(lu, kernel.propose(sigma[0], None))
+    _note(kernel, ("step", 0, list(swarm.raw), [p.log_p for p in swarm.particles],
+                   [p.holder.last_added for p in swarm.particles]))
     it = 1
     # base.py:35 resamples right after the initial swarm with the *next* retained particle
     # (conditional.py:101 reads constrained_path[iteration + 1]); uniform weights never trigger it.
-    swarm = _maybe_resample(swarm, rng, n_particles, threshold, lambda: path[it + 1])
+    swarm = _maybe_resample(swarm, rng, n_particles, threshold, lambda: path[it + 1], 0, kernel)
     while it < T:
         new = Swarm()
         last = it >= T - 1
         new.add(swarm.log_weights[0] + _last_term(path[it + 1], last), path[it + 1])
-        for lw, parent in zip(swarm.log_weights[1:], swarm.particles[1:]):
+        for i, (lw, parent) in enumerate(zip(swarm.log_weights[1:], swarm.particles[1:]), 1):
+            _at(rng, it, i)
             p = kernel.propose(sigma[it], parent)
             new.add(lw + _last_term(p, last), p)
         swarm = new
+        _note(kernel, ("step", it, list(swarm.raw), [p.log_p for p in swarm.particles],
+                       [p.holder.last_added for p in swarm.particles]))
         if it < T - 1:
-            swarm = _maybe_resample(swarm, rng, n_particles, threshold, lambda: path[it + 1])
+            swarm = _maybe_resample(swarm, rng, n_particles, threshold, lambda: path[it + 1], it, kernel)
         it += 1
     return swarm
 
@@ -987,20 +1060,39 @@ def sample_sigma(tree, rng, source=None):
 # ------------------------------------------------------------------------------------
 # MCMC moves                                   mcmc/particle_gibbs.py, gibbs_mh.py, concentration.py
 # ------------------------------------------------------------------------------------
-def _pick(swarm, rng):  # utils/math.py:19-21 via particle_gibbs.py:42-48
+def _pick(swarm, rng, kernel=None):  # utils/math.py:19-21 via particle_gibbs.py:42-48
     p = swarm.weights
     p = p / np.sum(p)
-    return swarm.particles[rng.multinomial(1, p).argmax()].thaw()
+    from .uniform import FINAL_SLOT
+
+    _at(rng, 0, FINAL_SLOT)
+    idx = rng.multinomial(1, p).argmax()
+    _note(kernel, ("pick", int(idx)))
+    return swarm.particles[idx].thaw()
+
+
+def _sweep(rng, run):
+    """Uniform-driven mode: one seed from the chain's Generator per sweep (after sigma), keyed uniforms inside."""
+    begin = getattr(rng, "begin", None)
+    if begin is None:
+        return run()
+    begin(int(rng.generator.integers(0, 1 << 62)))
+    try:
+        return run()
+    finally:
+        rng.end()
 
 
 def pg_move(tree, kernel, n_particles, threshold):
     sigma = sample_sigma(tree, kernel.rng)
-    return _pick(smc_conditional(tree, sigma, kernel, n_particles, threshold), kernel.rng)
+    return _sweep(kernel.rng,
+                  lambda: _pick(smc_conditional(tree, sigma, kernel, n_particles, threshold), kernel.rng, kernel))
 
 
 def burnin_move(tree, kernel, n_particles, threshold):  # smc/samplers/unconditional.py
     sigma = sample_sigma(tree, kernel.rng)
-    return _pick(smc_unconditional(sigma, kernel, n_particles, threshold), kernel.rng)
+    return _sweep(kernel.rng,
+                  lambda: _pick(smc_unconditional(sigma, kernel, n_particles, threshold), kernel.rng, kernel))
 
 
 def datapoint_move(tree, joint, rng, outliers):  # gibbs_mh.py:20-70
@@ -1076,12 +1168,15 @@ def alpha_move(joint, tree, rng, a=0.01, b=0.01):  # concentration.py:29-60, run
 # ------------------------------------------------------------------------------------
 def run_chain(data, rng, num_iters, burnin=1, num_particles=100, proposal="semi-adapted", resample_threshold=0.5,
               outlier_prob=0.0, concentration_value=1.0, concentration_update=True, num_samples_data_point=1,
-              num_samples_prune_regraph=1, use_tile_caches=False, on_iteration=None):
+              num_samples_prune_regraph=1, use_tile_caches=False, on_iteration=None, sweep_log=None):
     """Returns {"trace": [...], "extensions": int, "convs": int}; trace entry =
-    {"iter", "alpha", "log_p_one", "tree": frozen dict, "clades", "outliers"} (run.py:293-302)."""
+    {"iter", "alpha", "log_p_one", "tree": frozen dict, "clades", "outliers"} (run.py:293-302).
+    `sweep_log`: a list that receives the step / resample / pick records of every SMC sweep (see `_note`)."""
     tm = TileMath(use_tile_caches)
     joint = Joint(concentration_value)
     kernel = KERNELS[proposal](joint, rng, tm, outlier_proposal_prob=0.1 if outlier_prob > 0 else 0.0)
+    if sweep_log is not None:
+        kernel.sweep_log = sweep_log
     tree = Forest.single_node(data, tm)
 
     def moves(t):

@@ -73,6 +73,7 @@ SIGNATURES = {
     "pcb_normalize_segments_host": (C.c_int, [_P, _P, _i64, _P, _P, _P]),
     "pcb_normalize_segments_dev": (C.c_int, [_P, _P, _i64, _P, _P, _P, _P, _P]),
     "pcb_resample_host": (C.c_int, [_P, _i64, _P, _i64, _P]),
+    "pcb_smc_sweep_dev": (C.c_int, [C.POINTER(Arena), _P, _P]),
     "pcb_fp64_peak": (C.c_int, [_i32, C.POINTER(_f64), C.POINTER(_f64)]),
 }
 

@@ -6,7 +6,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "pcb_api.cu")
-DEPS = [SRC] + [os.path.join(HERE, "csrc", f) for f in ("pcb_kernels.cuh", "pcb_device.cuh")] + [
+DEPS = [SRC] + [os.path.join(HERE, "csrc", f) for f in ("pcb_kernels.cuh", "pcb_device.cuh", "pcb_sweep.cuh")] + [
     os.path.join(os.path.dirname(HERE), "include", "phyclone_b200.h")
 ]
 OUT_DIR = os.path.join(HERE, "lib")

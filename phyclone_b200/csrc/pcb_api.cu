@@ -11,6 +11,7 @@
 
 #include "../../include/phyclone_b200.h"
 #include "pcb_kernels.cuh"
+#include "pcb_sweep.cuh"
 
 namespace {
 
@@ -115,6 +116,17 @@ long long lane_slots(int G, int L, int P) {
   return P * ((U + P - 1) / P) * (Q + 1) * L * L;
 }
 
+// CTAs of a launch whose job count only the device knows: a pool that covers the device once at the kernel's occupancy
+int pool_ctas() {
+  static int v = 0;
+  if (!v) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    v = sms * 8;
+  }
+  return v;
+}
+
 template <int L>
 int launch_jobs_L(const pcb::JobKernelParams& kp, long long n_jobs, int threads, size_t smem, cudaStream_t st) {
   static size_t configured = 0;
@@ -122,7 +134,7 @@ int launch_jobs_L(const pcb::JobKernelParams& kp, long long n_jobs, int threads,
     PCB_CUDA(cudaFuncSetAttribute(pcb::node_jobs_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  const long long grid = n_jobs * kp.row_blocks;
+  const long long grid = kp.n_jobs_dev ? std::min<long long>(n_jobs * kp.row_blocks, pool_ctas()) : n_jobs * kp.row_blocks;
   if (grid > 2147483647ll) return fail(PCB_ERR_ARG, "too many jobs for one launch");
   pcb::node_jobs_kernel<L><<<(unsigned)grid, threads, smem, st>>>(kp);
   PCB_LAUNCH_CHECK();
@@ -136,7 +148,8 @@ int launch_wide_L(const pcb::JobKernelParams& kp, long long n_jobs, size_t smem,
     PCB_CUDA(cudaFuncSetAttribute(pcb::node_jobs_wide_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  const long long grid = (n_jobs * kp.S + 31) / 32;
+  long long grid = (n_jobs * kp.S + 31) / 32;
+  if (kp.n_jobs_dev) grid = std::min<long long>(grid, pool_ctas() / 4);
   if (grid > 2147483647ll) return fail(PCB_ERR_ARG, "too many jobs for one launch");
   pcb::node_jobs_wide_kernel<L><<<(unsigned)grid, 32 * kp.P, smem, st>>>(kp);
   PCB_LAUNCH_CHECK();
@@ -413,13 +426,14 @@ int pcb_timing_end(double* total_ms, int64_t* n_launches) {
 }
 
 static int node_jobs_launch(const pcb_arena* a, const int32_t* jobs_dev, const int32_t* children_dev, int64_t n_jobs,
-                            double prior, double* rows_lse, double* rows_last, void* stream);
+                            double prior, double* rows_lse, double* rows_last, void* stream,
+                            const int* n_jobs_dev = nullptr);
 
-int pcb_node_jobs_dev(const pcb_arena* a, const int32_t* jobs_dev, const int32_t* children_dev, int64_t n_jobs,
-                      double prior, double* rows_lse, double* rows_last, void* stream) {
+static int jobs_launch_timed(const pcb_arena* a, const int32_t* jobs_dev, const int32_t* children_dev, int64_t n_jobs,
+                             double prior, double* rows_lse, double* rows_last, void* stream, const int* n_jobs_dev) {
   const bool timed = g_timing.on && n_jobs > 0 && g_timing.used + 2 <= g_timing.cap;
   if (timed) PCB_CUDA(cudaEventRecord(g_timing.ev[g_timing.used], (cudaStream_t)stream));
-  const int rc = node_jobs_launch(a, jobs_dev, children_dev, n_jobs, prior, rows_lse, rows_last, stream);
+  const int rc = node_jobs_launch(a, jobs_dev, children_dev, n_jobs, prior, rows_lse, rows_last, stream, n_jobs_dev);
   if (timed && rc == PCB_OK) {
     PCB_CUDA(cudaEventRecord(g_timing.ev[g_timing.used + 1], (cudaStream_t)stream));
     g_timing.used += 2;
@@ -427,8 +441,15 @@ int pcb_node_jobs_dev(const pcb_arena* a, const int32_t* jobs_dev, const int32_t
   return rc;
 }
 
+int pcb_node_jobs_dev(const pcb_arena* a, const int32_t* jobs_dev, const int32_t* children_dev, int64_t n_jobs,
+                      double prior, double* rows_lse, double* rows_last, void* stream) {
+  return jobs_launch_timed(a, jobs_dev, children_dev, n_jobs, prior, rows_lse, rows_last, stream, nullptr);
+}
+
+// n_jobs_dev != NULL: `n_jobs` is only an upper bound, the count is read on the device (tables written by a kernel
+// earlier in the stream)
 static int node_jobs_launch(const pcb_arena* a, const int32_t* jobs_dev, const int32_t* children_dev, int64_t n_jobs,
-                            double prior, double* rows_lse, double* rows_last, void* stream) {
+                            double prior, double* rows_lse, double* rows_last, void* stream, const int* n_jobs_dev) {
   int rc = check_arena(a);
   if (rc) return rc;
   if (n_jobs <= 0) return PCB_OK;
@@ -455,6 +476,7 @@ static int node_jobs_launch(const pcb_arena* a, const int32_t* jobs_dev, const i
   kp.row_blocks = (l.S + l.rows_per_cta - 1) / l.rows_per_cta;
   kp.double_b = jobs_double_b();
   kp.n_jobs = n_jobs;
+  kp.n_jobs_dev = n_jobs_dev;
   if (l.kernel == 1) {
     const size_t wsmem = wide_smem_bytes(l.lanes_per_row, l.pitch);
     cudaStream_t wst = (cudaStream_t)stream;
@@ -882,6 +904,250 @@ int pcb_resample_host(const double* W, int64_t N, const double* uniforms, int64_
   PCB_LAUNCH_CHECK();
   PCB_CUDA(cudaMemcpyAsync(ancestors, hs.out.p, (size_t)n_draws * 8, cudaMemcpyDeviceToHost, 0));
   PCB_CUDA(cudaStreamSynchronize(0));
+  return PCB_OK;
+}
+
+// ---- device-resident SMC sweep ---------------------------------------------------------------------------
+extern "C++" {
+namespace {
+struct SweepWorkspace {
+  DevBuf ints, dbls, keys, outs;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+};
+thread_local SweepWorkspace g_sw;
+
+struct Carver {
+  char* base;
+  size_t off = 0;
+  template <class T>
+  T* take(size_t n) {
+    off = (off + 15) & ~(size_t)15;
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+}  // namespace
+}  // extern "C++"
+
+int pcb_smc_sweep_dev(const pcb_arena* a, const pcb_sweep_desc* d, void* stream) {
+  namespace sw = pcb::sweep;
+  int rc = check_arena(a);
+  if (rc) return rc;
+  if (!d) return fail(PCB_ERR_ARG, "smc_sweep: null descriptor");
+  const int N = d->N, T = d->T, Rmax = d->Rmax, S = a->layout.S;
+  if (N < 1 || N > 1024 || T < 1 || Rmax < 1 || Rmax > sw::kMaxRoots)
+    return fail(PCB_ERR_ARG, "smc_sweep: need 1 <= N <= 1024, T >= 1, 1 <= Rmax <= 64");
+  if (d->conditional && (N < 2 || !d->ret_th_int || !d->ret_ba_int || !d->ret_th_dbl || !d->ret_ba_dbl || !d->ret_key))
+    return fail(PCB_ERR_ARG, "smc_sweep: conditional sweep without a retained path (or N < 2)");
+  if (!d->dp_idx || !d->value_id || !d->single_id || !d->dp_op || !d->dp_opn || !d->dp_marg || !d->lfact || !d->logn ||
+      !d->rterm || d->n_tab < Rmax + 2)
+    return fail(PCB_ERR_ARG, "smc_sweep: missing input table");
+  if (!d->anc || !d->kind || !d->name || !d->mask || !d->raw || !d->logp || !d->logq || !d->ess || !d->resampled ||
+      !d->final_idx || !d->status)
+    return fail(PCB_ERR_ARG, "smc_sweep: missing output buffer");
+  const long long scratch = (long long)N * Rmax;
+  if (d->tile_base < 0 || d->tile_limit > a->capacity || d->tile_base + scratch + 2ll * N > d->tile_limit)
+    return fail(PCB_ERR_ARG, "smc_sweep: tile range too small for the candidate scratch");
+  for (int t = 0; t < T; ++t)
+    if (d->value_id[t] < 0 || d->value_id[t] >= a->capacity || d->single_id[t] < 0 || d->single_id[t] >= a->capacity)
+      return fail(PCB_ERR_ARG, "smc_sweep: data tile id outside the arena");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int irec = sw::IHEAD + sw::F_COUNT * Rmax;
+  const int n_ret_kids = d->conditional ? d->n_ret_kids : 0;
+  const long long maxB = (long long)N * (Rmax + 1);
+  const int pool_cap = n_ret_kids + N * T * std::min(Rmax, 16) + 64;
+  const size_t TN = (size_t)T * N;
+
+  // ---- carve the workspace (two passes: size, then pointers)
+  sw::Params P{};
+  size_t need_i = 0, need_d = 0, need_k = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    Carver ci{pass ? g_sw.ints.as<char>() : nullptr}, cd{pass ? g_sw.dbls.as<char>() : nullptr},
+        ck{pass ? g_sw.keys.as<char>() : nullptr};
+    P.dp_idx = ci.take<int>(T);
+    P.value_id = ci.take<int>(T);
+    P.single_id = ci.take<int>(T);
+    P.ret_th_int = ci.take<int>(d->conditional ? (size_t)T * irec : 0);
+    P.ret_ba_int = ci.take<int>(d->conditional ? (size_t)T * irec : 0);
+    P.kid_pool = ci.take<int>(pool_cap);
+    P.cur_int = ci.take<int>((size_t)N * irec);
+    P.ext_int = ci.take<int>((size_t)N * irec);
+    P.use_ret = ci.take<int>(N);
+    P.cand_off = ci.take<int>(N + 1);
+    P.job_off = ci.take<int>(N + 1);
+    P.jobsB = ci.take<int>((size_t)maxB * 8);
+    P.kidsB = ci.take<int>((size_t)maxB * Rmax);
+    P.addA = ci.take<int>((size_t)N * Rmax);
+    P.addB = ci.take<int>((size_t)N * Rmax);
+    P.addO = ci.take<int>((size_t)N * Rmax);
+    P.jobsD = ci.take<int>((size_t)2 * N * 8);
+    P.kidsD = ci.take<int>((size_t)2 * N * Rmax);
+    P.jobsE = ci.take<int>((size_t)N * 8);
+    P.kidsE = ci.take<int>((size_t)N * Rmax);
+    P.slotE = ci.take<int>(N);
+    P.dec_kind = ci.take<int>(N);
+    P.dec_name = ci.take<int>(N);
+    P.nB = ci.take<int>(8);  // nB, nAdd, nD, nE, pool_top, tile_top, status, final
+    P.o_anc = ci.take<int>(TN);
+    P.o_kind = ci.take<int>(TN);
+    P.o_name = ci.take<int>(TN);
+    P.o_resampled = ci.take<int>(T);
+    need_i = ci.off;
+    P.dp_op = cd.take<double>(T);
+    P.dp_opn = cd.take<double>(T);
+    P.dp_marg = cd.take<double>(T);
+    P.lfact = cd.take<double>(d->n_tab);
+    P.logn = cd.take<double>(d->n_tab);
+    P.rterm = cd.take<double>(d->n_tab);
+    P.ret_th_dbl = cd.take<double>(d->conditional ? (size_t)T * sw::DREC : 0);
+    P.ret_ba_dbl = cd.take<double>(d->conditional ? (size_t)T * sw::DREC : 0);
+    P.cur_dbl = cd.take<double>((size_t)N * sw::DREC);
+    P.ext_dbl = cd.take<double>((size_t)N * sw::DREC);
+    P.lw = cd.take<double>(N);
+    P.raw = cd.take<double>(N);
+    P.scB_lse = cd.take<double>((size_t)maxB * S);
+    P.scB_last = cd.take<double>((size_t)maxB * S);
+    P.scE_lse = cd.take<double>((size_t)N * S);
+    P.scE_last = cd.take<double>((size_t)N * S);
+    P.dec_logq = cd.take<double>(N);
+    P.dec_lp = cd.take<double>(N);
+    P.dec_lp1 = cd.take<double>(N);
+    P.o_raw = cd.take<double>(TN);
+    P.o_logp = cd.take<double>(TN);
+    P.o_logq = cd.take<double>(TN);
+    P.o_ess = cd.take<double>(T);
+    need_d = cd.off;
+    P.ret_key = ck.take<sw::u64>(d->conditional ? T : 0);
+    P.cur_key = ck.take<sw::u64>(N);
+    P.ext_key = ck.take<sw::u64>(N);
+    P.dec_mask = ck.take<sw::u64>(N);
+    P.o_mask = ck.take<sw::u64>(TN);
+    P.pairs = ck.take<sw::u64>(1);
+    need_k = ck.off;
+    if (!pass) {
+      if ((rc = g_sw.ints.ensure(need_i + 64))) return rc;
+      if ((rc = g_sw.dbls.ensure(need_d + 64))) return rc;
+      if ((rc = g_sw.keys.ensure(need_k + 64))) return rc;
+    }
+  }
+  P.nAdd = P.nB + 1;
+  P.nD = P.nB + 2;
+  P.nE = P.nB + 3;
+  P.pool_top = P.nB + 4;
+  P.tile_top = P.nB + 5;
+  P.status = P.nB + 6;
+  P.o_final = P.nB + 7;
+  P.N = N;
+  P.T = T;
+  P.Rmax = Rmax;
+  P.conditional = d->conditional ? 1 : 0;
+  P.outliers = d->outliers ? 1 : 0;
+  P.S = S;
+  P.irec = irec;
+  P.n_tab = d->n_tab;
+  P.log_alpha = d->log_alpha;
+  P.threshold = d->threshold;
+  P.log_half = d->log_half;
+  P.seed = d->seed;
+  P.pool_cap = pool_cap;
+  P.tile_limit = (int)d->tile_limit;
+  P.scratch0 = (int)d->tile_base;
+
+  // ---- inputs: host -> device
+  auto up = [&](const void* dst, const void* src, size_t bytes) -> cudaError_t {
+    if (!bytes) return cudaSuccess;
+    return cudaMemcpyAsync(const_cast<void*>(dst), src, bytes, cudaMemcpyHostToDevice, st);
+  };
+  PCB_CUDA(up(P.dp_idx, d->dp_idx, (size_t)T * 4));
+  PCB_CUDA(up(P.value_id, d->value_id, (size_t)T * 4));
+  PCB_CUDA(up(P.single_id, d->single_id, (size_t)T * 4));
+  PCB_CUDA(up(P.dp_op, d->dp_op, (size_t)T * 8));
+  PCB_CUDA(up(P.dp_opn, d->dp_opn, (size_t)T * 8));
+  PCB_CUDA(up(P.dp_marg, d->dp_marg, (size_t)T * 8));
+  PCB_CUDA(up(P.lfact, d->lfact, (size_t)d->n_tab * 8));
+  PCB_CUDA(up(P.logn, d->logn, (size_t)d->n_tab * 8));
+  PCB_CUDA(up(P.rterm, d->rterm, (size_t)d->n_tab * 8));
+  if (d->conditional) {
+    PCB_CUDA(up(P.ret_th_int, d->ret_th_int, (size_t)T * irec * 4));
+    PCB_CUDA(up(P.ret_ba_int, d->ret_ba_int, (size_t)T * irec * 4));
+    PCB_CUDA(up(P.ret_th_dbl, d->ret_th_dbl, (size_t)T * sw::DREC * 8));
+    PCB_CUDA(up(P.ret_ba_dbl, d->ret_ba_dbl, (size_t)T * sw::DREC * 8));
+    PCB_CUDA(up(P.ret_key, d->ret_key, (size_t)T * 8));
+    if (n_ret_kids) PCB_CUDA(up(P.kid_pool, d->ret_kids, (size_t)n_ret_kids * 4));
+  }
+  const int counters[8] = {0, 0, 0, 0, n_ret_kids, (int)(d->tile_base + scratch), 0, -1};
+  PCB_CUDA(up(P.nB, counters, sizeof(counters)));
+  PCB_CUDA(cudaMemsetAsync(P.pairs, 0, 8, st));
+
+  if (!g_sw.e0) {
+    PCB_CUDA(cudaEventCreate(&g_sw.e0));
+    PCB_CUDA(cudaEventCreate(&g_sw.e1));
+  }
+  PCB_CUDA(cudaEventRecord(g_sw.e0, st));
+  const pcb_layout& l = a->layout;
+  const int threads1 = std::min(1024, 32 * ((N + 31) / 32));
+  sw::init_kernel<<<1, threads1, 0, st>>>(P, d->lw_uniform);
+  PCB_LAUNCH_CHECK();
+  int64_t launches = 1;
+  for (int t = 0; t < T; ++t) {
+    sw::build_kernel<<<1, 1024, 0, st>>>(P, t);
+    PCB_LAUNCH_CHECK();
+    if (t > 0 || !d->conditional || true) {
+      const int wpb = 8;
+      const long long max_rows = (long long)N * std::min(Rmax, t + 1) * S;
+      const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((max_rows + wpb - 1) / wpb, 148 * 8));
+      if (t > 0) {
+        sw::add_list_kernel<<<grid, wpb * 32, 0, st>>>(P.addA, P.addB, P.addO, P.nAdd, a->lg, a->lin, a->rmax, l.S, l.G,
+                                                      l.pitch, l.lead, l.tile_elems);
+        PCB_LAUNCH_CHECK();
+        ++launches;
+      }
+    }
+    const long long boundB = (long long)N * (std::min(Rmax, t) + 1);
+    if ((rc = jobs_launch_timed(a, P.jobsB, P.kidsB, boundB, d->prior, P.scB_lse, P.scB_last, stream, P.nB))) return rc;
+    sw::decide_kernel<<<1, threads1, 0, st>>>(P, t);
+    PCB_LAUNCH_CHECK();
+    launches += 3;
+    if (t > 0) {
+      if ((rc = jobs_launch_timed(a, P.jobsD, P.kidsD, 2ll * N, d->prior, nullptr, nullptr, stream, P.nD))) return rc;
+      if ((rc = jobs_launch_timed(a, P.jobsE, P.kidsE, N, d->prior, P.scE_lse, P.scE_last, stream, P.nE))) return rc;
+      launches += 2;
+    }
+    sw::weigh_kernel<<<1, 1024, 0, st>>>(P, t, d->log_uniform, d->lw_uniform);
+    PCB_LAUNCH_CHECK();
+    ++launches;
+  }
+  PCB_CUDA(cudaEventRecord(g_sw.e1, st));
+
+  // ---- outputs: device -> host, one synchronisation for the whole sweep
+  auto down = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st);
+  };
+  int tail[8];
+  PCB_CUDA(down(d->anc, P.o_anc, TN * 4));
+  PCB_CUDA(down(d->kind, P.o_kind, TN * 4));
+  PCB_CUDA(down(d->name, P.o_name, TN * 4));
+  PCB_CUDA(down(d->mask, P.o_mask, TN * 8));
+  PCB_CUDA(down(d->raw, P.o_raw, TN * 8));
+  PCB_CUDA(down(d->logp, P.o_logp, TN * 8));
+  PCB_CUDA(down(d->logq, P.o_logq, TN * 8));
+  PCB_CUDA(down(d->ess, P.o_ess, (size_t)T * 8));
+  PCB_CUDA(down(d->resampled, P.o_resampled, (size_t)T * 4));
+  PCB_CUDA(down(tail, P.nB, sizeof(tail)));
+  unsigned long long pairs = 0;
+  PCB_CUDA(down(&pairs, P.pairs, 8));
+  PCB_CUDA(cudaStreamSynchronize(st));
+  if (d->conv_pairs) *d->conv_pairs = (int64_t)pairs;
+  *d->final_idx = tail[7];
+  *d->status = tail[6];
+  if (d->tiles_used) *d->tiles_used = (int64_t)tail[5] - d->tile_base;
+  if (d->n_launches) *d->n_launches = launches;
+  if (d->device_ms) {
+    float ms = 0.f;
+    PCB_CUDA(cudaEventElapsedTime(&ms, g_sw.e0, g_sw.e1));
+    *d->device_ms = ms;
+  }
   return PCB_OK;
 }
 

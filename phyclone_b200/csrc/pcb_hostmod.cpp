@@ -424,6 +424,17 @@ PyObject* Book_done(Book* self, PyObject* arg) {
   Py_RETURN_NONE;
 }
 
+// reserve(n) -> first id of a block of n consecutive tiles handed to somebody else (the device-resident SMC sweep
+// allocates its tiles itself), or -1 if the arena is too small: the caller grows it and asks again
+PyObject* Book_reserve(Book* self, PyObject* arg) {
+  const long long n = PyLong_AsLongLong(arg);
+  if (n == -1 && PyErr_Occurred()) return nullptr;
+  if (n < 0 || self->top + n > self->capacity) return PyLong_FromLong(-1);
+  const long long first = self->top;
+  self->top += n;
+  return PyLong_FromLongLong(first);
+}
+
 PyObject* Book_set_capacity(Book* self, PyObject* arg) {
   const long long c = PyLong_AsLongLong(arg);
   if (c == -1 && PyErr_Occurred()) return nullptr;
@@ -452,6 +463,7 @@ PyMethodDef Book_methods[] = {
     {"pack", (PyCFunction)Book_pack, METH_NOARGS, "(packed bytes, plan, n_slots, plan as int32 x 6 records) of the pending batch"},
     {"done", (PyCFunction)Book_done, METH_O, "hand back the [2, n_slots] scores of the packed batch"},
     {"set_capacity", (PyCFunction)Book_set_capacity, METH_O, ""},
+    {"reserve", (PyCFunction)Book_reserve, METH_O, "first id of n consecutive tiles set aside (or -1 if the arena is full)"},
     {"counters", (PyCFunction)Book_counters, METH_NOARGS, ""},
     {nullptr, nullptr, 0, nullptr}};
 
@@ -927,7 +939,32 @@ PyObject* FState_get_lr(FState* self, void*) {
   return t;
 }
 
+PyObject* ints_tuple(const std::vector<int>& v) {
+  PyObject* t = PyTuple_New((Py_ssize_t)v.size());
+  if (!t) return nullptr;
+  for (size_t i = 0; i < v.size(); ++i) PyTuple_SET_ITEM(t, (Py_ssize_t)i, PyLong_FromLong(v[i]));
+  return t;
+}
+
+// export() -> (roots, lr, lp, kids, ndata, size, slot, gidx, n_nodes, n_slots, n_edges, n_out, crp, mult, oprior, omarg,
+//              skey): everything the device-resident sweep needs to take the state over (smc/device_sweep.py)
+PyObject* FState_export(FState* self, PyObject*) {
+  PyObject* roots = roots_tuple_of(self);
+  PyObject* kids = PyTuple_New((Py_ssize_t)self->kids->size());
+  if (!roots || !kids) {
+    Py_XDECREF(roots);
+    Py_XDECREF(kids);
+    return nullptr;
+  }
+  for (size_t i = 0; i < self->kids->size(); ++i) PyTuple_SET_ITEM(kids, (Py_ssize_t)i, ints_tuple((*self->kids)[i]));
+  return Py_BuildValue("(NNNNNNNNlllldddd K)", roots, ints_tuple(*self->lr), ints_tuple(*self->lp), kids,
+                       ints_tuple(*self->ndata), ints_tuple(*self->size), ints_tuple(*self->slot), ints_tuple(*self->gidx),
+                       self->n_nodes, self->n_slots, self->n_edges, self->n_out, self->crp, self->mult, self->oprior,
+                       self->omarg, (unsigned long long)self->skey);
+}
+
 PyMethodDef FState_methods[] = {
+    {"export", (PyCFunction)FState_export, METH_NOARGS, "all fields as a tuple"},
     {"extend", (PyCFunction)FState_extend, METH_VARARGS, "thawed successor state (None if the arena is full)"},
     {"score_attach_all", (PyCFunction)FState_score_attach_all, METH_VARARGS, ""},
     {"score_new", (PyCFunction)FState_score_new, METH_VARARGS, ""},

@@ -27,6 +27,8 @@ struct JobKernelParams {
   long long tile_elems;
   double prior;
   long long n_jobs;
+  const int* n_jobs_dev;  // not NULL: the job count lives on the device (tables written by a kernel of the same
+                          // stream, pcb_sweep.cuh) and the grid is only an upper bound / a persistent pool of CTAs
   int S, G, Q, U, P, pitch, lead, RB, row_blocks;
   int double_b;  // 1: two operand buffers (next child prefetched during the fold step), 0: one
 };
@@ -246,23 +248,10 @@ __global__ void __launch_bounds__(32, (L == 13) ? 12 : 1) node_jobs_kernel(const
   double* bufB0 = bufA + rows_elems;
   double* bufB1 = bufB0 + rows_elems;
 
-  const int job = blockIdx.x / p.row_blocks;
-  const int rb = blockIdx.x - job * p.row_blocks;
-  const int32_t* jr = p.jobs + (size_t)job * 8;
-  const int coff = jr[0], C = jr[1], base = jr[2], outt = jr[3], flags = jr[4], slot = jr[5];
-  const int r0 = rb * p.RB;
-  const int nrows = min(p.RB, p.S - r0);
   const int P = p.P, G = p.G, pitch = p.pitch, lead = p.lead, Q = p.Q;
   const int tid = threadIdx.x;
   const int lrow = tid / P;
   const int lir = tid & (P - 1);
-  const bool row_ok = lrow < nrows;
-  const int row = r0 + lrow;
-  const uint32_t bytes = (uint32_t)nrows * pitch * 8u;
-  const bool scan = flags & 1;
-  const double addc = (flags & 2) ? p.prior : 0.0;
-  const bool shortcut = scan && base < 0 && outt < 0;
-
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
@@ -270,6 +259,28 @@ __global__ void __launch_bounds__(32, (L == 13) ? 12 : 1) node_jobs_kernel(const
     mbar_fence_init();
   }
   __syncwarp();
+  // A CTA walks work items blockIdx.x, blockIdx.x + gridDim.x, ...: a host-sized launch has one item per CTA; a launch
+  // whose job count only the device knows (n_jobs_dev) runs a fixed pool of CTAs.  The mbarriers live across items,
+  // so their phases are running counters.
+  const long long n_work = (p.n_jobs_dev ? (long long)*p.n_jobs_dev : p.n_jobs) * p.row_blocks;
+  uint32_t ph0 = 0, ph1 = 0, ph2 = 0;
+  for (long long work = blockIdx.x; work < n_work; work += gridDim.x) {
+  if (work != (long long)blockIdx.x) {  // the previous item's generic accesses to A / B precede this item's TMA writes
+    __syncwarp();
+    if (tid == 0) fence_proxy_async();
+  }
+  const int job = (int)(work / p.row_blocks);
+  const int rb = (int)(work - (long long)job * p.row_blocks);
+  const int32_t* jr = p.jobs + (size_t)job * 8;
+  const int coff = jr[0], C = jr[1], base = jr[2], outt = jr[3], flags = jr[4], slot = jr[5], base2 = jr[6] - 1;
+  const int r0 = rb * p.RB;
+  const int nrows = min(p.RB, p.S - r0);
+  const bool row_ok = lrow < nrows;
+  const int row = r0 + lrow;
+  const uint32_t bytes = (uint32_t)nrows * pitch * 8u;
+  const bool scan = flags & 1;
+  const double addc = (flags & 2) ? p.prior : 0.0;
+  const bool shortcut = scan && base < 0 && outt < 0;
 
   // child tile ids: one coalesced load per 32 children, handed out by shuffles.  (Reading children[coff + j] when
   // step j needs it put two dependent global loads -- id, then row maximum / TMA source -- on the serial path of
@@ -291,7 +302,8 @@ __global__ void __launch_bounds__(32, (L == 13) ? 12 : 1) node_jobs_kernel(const
   }
 
   double M = row_ok ? p.rmax[(size_t)c0 * p.S + row] : 0.0;
-  mbar_wait(&bars[0], 0);
+  mbar_wait(&bars[0], ph0 & 1);
+  ++ph0;
 
   double* a_row = bufA + lrow * pitch + lead;
   const int u = lir;  // the layout guarantees ceil(Q/2) <= P: one unit (strip pair) per lane
@@ -309,9 +321,15 @@ __global__ void __launch_bounds__(32, (L == 13) ? 12 : 1) node_jobs_kernel(const
     int cnext = 0;
     if (j + 1 < C) cnext = ((j + 1) & 31) ? __shfl_sync(0xffffffffu, my_child, (j + 1) & 31) : p.children[coff + j + 1];
     const double mB = row_ok ? p.rmax[(size_t)cj * p.S + row] : 0.0;
-    double* Bcur = (!db || (j & 1)) ? bufB0 : bufB1;
-    uint64_t* bbar = (!db || (j & 1)) ? &bars[1] : &bars[2];
-    mbar_wait(bbar, db ? (((j - 1) >> 1) & 1) : ((j - 1) & 1));
+    const bool first_buf = !db || (j & 1);
+    double* Bcur = first_buf ? bufB0 : bufB1;
+    if (first_buf) {
+      mbar_wait(&bars[1], ph1 & 1);
+      ++ph1;
+    } else {
+      mbar_wait(&bars[2], ph2 & 1);
+      ++ph2;
+    }
     if (db && j + 1 < C && tid == 0) {  // prefetch the next operand into the buffer step j-1 released
       double* Bnext = (j & 1) ? bufB1 : bufB0;
       uint64_t* nbar = (j & 1) ? &bars[2] : &bars[1];
@@ -396,7 +414,7 @@ __global__ void __launch_bounds__(32, (L == 13) ? 12 : 1) node_jobs_kernel(const
       p.sc_lse[(size_t)slot * p.S + row] = (M + addc) + log(t2);
       p.sc_last[(size_t)slot * p.S + row] = (M + addc) + log(t1);
     }
-    return;
+    continue;
   }
 
   // ---- epilogue 2: elementwise log_D / log_S, + log_p, store tile, optional scores --
@@ -419,7 +437,8 @@ __global__ void __launch_bounds__(32, (L == 13) ? 12 : 1) node_jobs_kernel(const
       for (int k = lir; k < G; k += P) yrow[k] = log(yrow[k]) + M;
     }
   } else {
-    mbar_wait(&bars[1], 0);
+    mbar_wait(&bars[1], ph1 & 1);
+    ++ph1;
     const double* lrow_ptr = bufB0 + lrow * pitch + lead;
     if (scan) {
       row_prefix_lse(lrow_ptr, yrow, G, P, lir, row_ok);
@@ -432,6 +451,9 @@ __global__ void __launch_bounds__(32, (L == 13) ? 12 : 1) node_jobs_kernel(const
   double vmax = -INFINITY;
   if (row_ok) {
     const double* bptr = (base >= 0) ? p.lg + (size_t)base * p.tile_elems + (size_t)row * pitch + lead : nullptr;
+    // second addend of the base (record field [6] = id + 1): log_p = tile(base) + tile(base2) formed on the fly, so a
+    // node refresh after `log_p += value` needs no materialised log_p first (tree/tree_node.py:42-52 then :61-71)
+    const double* b2ptr = (bptr && base2 >= 0) ? p.lg + (size_t)base2 * p.tile_elems + (size_t)row * pitch + lead : nullptr;
     // the log_p tile comes from global memory: four loads in flight per lane instead of one load-use round trip per
     // element (a third of the stall samples of a live launch sat on this line)
     for (int k = lir; k < G; k += 4 * P) {
@@ -440,6 +462,11 @@ __global__ void __launch_bounds__(32, (L == 13) ? 12 : 1) node_jobs_kernel(const
 #pragma unroll
         for (int t = 0; t < 4; ++t)
           if (k + t * P < G) bb[t] = bptr[k + t * P];
+        if (b2ptr) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            if (k + t * P < G) bb[t] += b2ptr[k + t * P];
+        }
       }
 #pragma unroll
       for (int t = 0; t < 4; ++t)
@@ -477,6 +504,7 @@ __global__ void __launch_bounds__(32, (L == 13) ? 12 : 1) node_jobs_kernel(const
       p.sc_last[(size_t)slot * p.S + row] = yrow[G - 1];
     }
   }
+  }  // work items
 }
 
 // ---------------------------------------------------------------------------------
@@ -500,10 +528,25 @@ __global__ void __launch_bounds__(128) node_jobs_wide_kernel(const JobKernelPara
   double* red = bufB + 32 * pitch;
   double* Msh = red + P * 32;
   const int tid = threadIdx.x, u = tid >> 5, lane = tid & 31;
-  const long long g0 = (long long)blockIdx.x * 32;
-  const long long total_rows = p.n_jobs * S;
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  // a CTA walks 32-row blocks blockIdx.x, blockIdx.x + gridDim.x, ... (see node_jobs_kernel): running mbarrier phases
+  const long long n_jobs_all = p.n_jobs_dev ? (long long)*p.n_jobs_dev : p.n_jobs;
+  const long long total_rows = n_jobs_all * S;
+  const long long n_blocks = (total_rows + 31) / 32;
+  uint32_t ph0 = 0, ph1 = 0;
+  for (long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+  if (blk != (long long)blockIdx.x) {  // the previous block's generic accesses precede this block's TMA writes
+    __syncthreads();
+    if (tid == 0) fence_proxy_async();
+  }
+  const long long g0 = blk * 32;
   const int job_first = (int)(g0 / S);
-  const int jobs_here = (int)min((long long)(32 / S), p.n_jobs - job_first);
+  const int jobs_here = (int)min((long long)(32 / S), n_jobs_all - job_first);
   const uint32_t job_bytes = (uint32_t)S * pitch * 8u;
 
   // ---- fold phase identity: lane = row slot ---------------------------------------
@@ -518,12 +561,6 @@ __global__ void __launch_bounds__(128) node_jobs_wide_kernel(const JobKernelPara
   const bool needB0 = row_ok && (C >= 2 || !((jr[4] & 1) && jr[2] < 0 && jr[3] < 0));
   const bool armed0 = __any_sync(0xffffffffu, needB0);
 
-  if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    mbar_fence_init();
-  }
-  __syncthreads();
   if (tid == 0) {
     int nb = 0;
     for (int q = 0; q < jobs_here; ++q) {
@@ -545,11 +582,11 @@ __global__ void __launch_bounds__(128) node_jobs_wide_kernel(const JobKernelPara
     }
   }
   double M = row_ok ? p.rmax[(size_t)p.children[coff] * S + row] : 0.0;
-  mbar_wait(&bars[0], 0);
-  int phase = 0;
+  mbar_wait(&bars[0], ph0 & 1);
+  ++ph0;
   if (armed0) {
-    mbar_wait(&bars[1], 0);
-    phase = 1;
+    mbar_wait(&bars[1], ph1 & 1);
+    ++ph1;
   }
 
   double* a_row = bufA + lane * pitch + lead;
@@ -561,8 +598,8 @@ __global__ void __launch_bounds__(128) node_jobs_wide_kernel(const JobKernelPara
   // ---- left fold over the children (tree/utils.py:33-47) --------------------------
   for (int j = 1; j < Cmax; ++j) {
     if (j >= 2) {
-      mbar_wait(&bars[1], phase & 1);
-      ++phase;
+      mbar_wait(&bars[1], ph1 & 1);
+      ++ph1;
     }
     const bool act = row_ok && j < C && unit_ok;
     double y1[L], y2[L];
@@ -643,7 +680,7 @@ __global__ void __launch_bounds__(128) node_jobs_wide_kernel(const JobKernelPara
   const int ejl = erow / S;
   const int er = erow - ejl * S;
   const int32_t* ej = p.jobs + (size_t)(job_first + (e_ok ? ejl : 0)) * 8;
-  const int eC = ej[1], base = ej[2], outt = ej[3], flags = ej[4], slot = ej[5];
+  const int eC = ej[1], base = ej[2], outt = ej[3], flags = ej[4], slot = ej[5], base2 = ej[6] - 1;
   const bool scan = flags & 1;
   const double addc = (flags & 2) ? p.prior : 0.0;
   const bool shortcut = scan && base < 0 && outt < 0;
@@ -693,6 +730,7 @@ __global__ void __launch_bounds__(128) node_jobs_wide_kernel(const JobKernelPara
   double vmax = -INFINITY;
   if (full) {
     const double* bptr = (base >= 0) ? p.lg + (size_t)base * p.tile_elems + (size_t)er * pitch + lead : nullptr;
+    const double* b2ptr = (bptr && base2 >= 0) ? p.lg + (size_t)base2 * p.tile_elems + (size_t)er * pitch + lead : nullptr;
     // the log_p tile comes from global memory: four loads in flight per lane instead of one load-use round trip per
     // element (a third of the stall samples of a live launch sat on this line)
     for (int k = lir; k < G; k += 4 * P) {
@@ -701,6 +739,11 @@ __global__ void __launch_bounds__(128) node_jobs_wide_kernel(const JobKernelPara
 #pragma unroll
         for (int t = 0; t < 4; ++t)
           if (k + t * P < G) bb[t] = bptr[k + t * P];
+        if (b2ptr) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            if (k + t * P < G) bb[t] += b2ptr[k + t * P];
+        }
       }
 #pragma unroll
       for (int t = 0; t < 4; ++t)
@@ -738,6 +781,7 @@ __global__ void __launch_bounds__(128) node_jobs_wide_kernel(const JobKernelPara
       p.sc_last[(size_t)slot * S + er] = yrow[G - 1];
     }
   }
+  }  // 32-row blocks
 }
 
 // ---------------------------------------------------------------------------------

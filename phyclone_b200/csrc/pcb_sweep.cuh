@@ -1,0 +1,779 @@
+// Device-resident (conditional) SMC sweep: proposal normalisation, draws, particle construction, weights / ESS and
+// resampling for all T data points without a host round trip.
+//
+// Reference path (relative to the reference package phyclone/): smc/samplers/base.py:32-58 (sweep loop, _get_log_w),
+// smc/samplers/conditional.py:76-125 and standard.py:20-45 (swarm init / update / resample),
+// smc/kernels/semi_adapted.py:36-194 (candidates, log_q, sample), smc/kernels/base.py:38-67 (create_particle),
+// smc/swarm/swarm.py:21-61 (weights, ESS), tree/distributions.py:39-133,186-219 (FS-CRP prior terms),
+// mcmc/particle_gibbs.py:42-48 (final pick).
+//
+// A particle is the root level of its forest (what csrc/pcb_hostmod.cpp calls a ForestState): the ordered roots with
+// their log_r / log_p tile ids, child tile lists, data counts and subtree sizes plus the running prior statistics
+// and the structure hash.  Per step the host-free pipeline is
+//     build   candidate tiles (root + value) and candidate score jobs of every particle        [1 CTA]
+//     add     tile_add over the candidate list                                                  [grid]
+//     jobs    node_jobs kernel: candidate scores (dummy-root folds)                             [persistent pool]
+//     decide  log_q / q, the particle's draws, successor state, node + score jobs               [1 CTA]
+//     jobs    node_jobs kernel: new node / re-folded root tiles                                 [persistent pool]
+//     jobs    node_jobs kernel: scores of the new-node trees                                    [persistent pool]
+//     weigh   log_w, log_Z, W, ESS, resampling (ancestors), state permutation                   [1 CTA]
+// Draws are inverse-CDF transforms of uniforms keyed by (seed, step, slot, draw number); the CPU definition of this
+// mode, decision for decision, is oracle/uniform.py + oracle/sampler.py run with a SweepRNG.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "pcb_device.cuh"
+
+namespace pcb {
+namespace sweep {
+
+typedef unsigned long long u64;
+
+constexpr int IHEAD = 5;  // R, n_nodes, n_slots, n_edges, n_out
+enum { F_NAME = 0, F_LR, F_LP, F_NDATA, F_SIZE, F_SLOT, F_GIDX, F_KOFF, F_KCNT, F_COUNT };
+constexpr int DREC = 8;  // crp, mult, oprior, omarg, log_p, log_p_one, log_w increment (retained path), spare
+enum { D_CRP = 0, D_MULT, D_OPRIOR, D_OMARG, D_LOGP, D_LOGP1, D_LOGW };
+enum { K_ATTACH = 0, K_NEW = 1, K_OUTLIER = 2 };
+constexpr int FLAG_RETAINED_PARENT = 8;  // decision flag: the parent was value-equal to the retained particle
+constexpr int JOB_SCAN = 1, JOB_ADD_PRIOR = 2;
+constexpr u64 GOLDEN = 0x9E3779B97F4A7C15ull;
+constexpr int RESAMPLE_SLOT = (1 << 20) - 1, FINAL_SLOT = (1 << 20) - 2;
+enum { ST_OK = 0, ST_ROOTS = 1, ST_TILES = 2, ST_POOL = 4, ST_NUMERIC = 8 };
+
+struct Params {
+  int N, T, Rmax, conditional, outliers, S, irec, n_tab;
+  double log_alpha, threshold, log_half;
+  u64 seed;
+  const int *dp_idx, *value_id, *single_id;
+  const double *dp_op, *dp_opn, *dp_marg;
+  const double *lfact, *logn, *rterm;
+  const int *ret_th_int, *ret_ba_int;
+  const double *ret_th_dbl, *ret_ba_dbl;
+  const u64* ret_key;
+  int *cur_int, *ext_int;
+  double *cur_dbl, *ext_dbl;
+  u64 *cur_key, *ext_key;
+  double *lw, *raw;
+  int *use_ret, *cand_off, *job_off;
+  int *jobsB, *kidsB, *nB, *addA, *addB, *addO, *nAdd;
+  int *jobsD, *kidsD, *nD, *jobsE, *kidsE, *nE;
+  double *scB_lse, *scB_last, *scE_lse, *scE_last;
+  int *slotE, *dec_kind, *dec_name;
+  u64* dec_mask;
+  double *dec_logq, *dec_lp, *dec_lp1;
+  int *kid_pool, *pool_top, *tile_top;
+  int pool_cap, tile_limit, scratch0;
+  int *o_anc, *o_kind, *o_name;
+  u64* o_mask;
+  double *o_raw, *o_logp, *o_logq, *o_ess;
+  int *o_resampled, *o_final, *status;
+  u64* pairs;  // pair convolutions requested so far (sum over jobs of children - 1): the roofline's work count
+};
+
+__host__ __device__ inline u64 mix64(u64 z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+// oracle/uniform.py::u01
+__host__ __device__ inline double u01(u64 seed, int t, int i, int c) {
+  const u64 idx = (((u64)t << 40) | ((u64)i << 20) | (u64)c) + 1ull;
+  return (double)(mix64(seed + GOLDEN * idx) >> 11) * (1.0 / 9007199254740992.0);
+}
+// structure hash pieces of csrc/pcb_hostmod.cpp (its mix64 differs from the one above)
+__device__ inline u64 hmix(u64 x) {
+  x ^= x >> 30;
+  x *= 0xbf58476d1ce4e5b9ull;
+  x ^= x >> 27;
+  x *= 0x94d049bb133111ebull;
+  x ^= x >> 31;
+  return x;
+}
+__device__ inline u64 edge_hash(long long e, long long s, long long d) {
+  return hmix(hmix(hmix((u64)e + 0x9e3779b97f4a7c15ull) ^ (u64)s) ^ (u64)d);
+}
+__device__ inline u64 data_hash(long long node, long long pos, long long idx) {
+  return hmix(hmix(hmix((u64)node + 0x632be59bd9b4e019ull) ^ (u64)pos) ^ (u64)idx) ^ 0x5bd1e995ull;
+}
+
+__device__ inline int* fld(int* rec, int f, int Rmax) { return rec + IHEAD + f * Rmax; }
+__device__ inline const int* fld(const int* rec, int f, int Rmax) { return rec + IHEAD + f * Rmax; }
+
+// which records describe particle i as a PARENT at step t: its own, or -- if its tree equals the retained particle's
+// (structure hash) -- the retained path's thawed state and as-built base (the value-keyed proposal cache of
+// smc/kernels/semi_adapted.py:219-237: the retained path's proposal is built first and serves every equal particle)
+struct ParentView {
+  const int *pI, *bI;
+  const double *pD, *bD;
+  bool ret;
+};
+__device__ inline ParentView parent_view(const Params& p, int t, int i) {
+  ParentView v;
+  v.ret = p.conditional && t >= 1 && p.cur_key[i] == p.ret_key[t - 1];
+  if (v.ret) {
+    v.pI = p.ret_th_int + (size_t)(t - 1) * p.irec;
+    v.bI = p.ret_ba_int + (size_t)(t - 1) * p.irec;
+    v.pD = p.ret_th_dbl + (size_t)(t - 1) * DREC;
+    v.bD = p.ret_ba_dbl + (size_t)(t - 1) * DREC;
+  } else {
+    v.pI = v.bI = p.cur_int + (size_t)i * p.irec;
+    v.pD = v.bD = p.cur_dbl + (size_t)i * DREC;
+  }
+  return v;
+}
+
+__device__ inline void put_job(int* jobs, int j, int coff, int C, int base, int out, int flags, int slot, int base2) {
+  int* r = jobs + (size_t)j * 8;
+  r[0] = coff;
+  r[1] = C;
+  r[2] = base;
+  r[3] = out;
+  r[4] = flags;
+  r[5] = slot;
+  r[6] = base2 + 1;
+  r[7] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// build: candidate tiles + candidate score jobs of step t (semi_adapted.py:85-141)
+// candidates of a parent with R roots, in the reference's order: attach to root 0..R-1 (base order), the outlier
+// tree if outliers are modelled, the lone new-root tree if the parent is empty
+// ------------------------------------------------------------------------------------------------------------
+__global__ void build_kernel(const Params p, const int t) {
+  __shared__ int sh_jobs[1024], sh_adds[1024];
+  const int first = p.conditional ? 1 : 0;
+  const int Rmax = p.Rmax;
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+    int nj = 0, na = 0;
+    if (i >= first && i < p.N) {
+      const ParentView v = parent_view(p, t, i);
+      const int R = v.bI[0];
+      nj = R + ((p.outliers && R > 0) ? 1 : 0) + (R == 0 ? 1 : 0);
+      na = R;
+      p.use_ret[i] = v.ret ? 1 : 0;
+    }
+    sh_jobs[i] = nj;
+    sh_adds[i] = na;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int rj = 0, ra = 0;
+    for (int i = 0; i < p.N; ++i) {
+      const int a = sh_jobs[i], b = sh_adds[i];
+      sh_jobs[i] = rj;
+      sh_adds[i] = ra;
+      rj += a;
+      ra += b;
+    }
+    *p.nB = rj;
+    *p.nAdd = ra;
+    *p.nD = 0;
+    *p.nE = 0;
+  }
+  __syncthreads();
+  u64 my_pairs = 0;
+  const int vid = p.value_id[t], sid = p.single_id[t];
+  for (int i = first + threadIdx.x; i < p.N; i += blockDim.x) {
+    const ParentView v = parent_view(p, t, i);
+    const int R = v.bI[0];
+    const int* lr = fld(v.bI, F_LR, Rmax);
+    const int j0 = sh_jobs[i], a0 = sh_adds[i];
+    p.job_off[i] = j0;
+    for (int r = 0; r < R; ++r) {
+      const int c = p.scratch0 + a0 + r;
+      p.addA[a0 + r] = lr[r];
+      p.addB[a0 + r] = vid;
+      p.addO[a0 + r] = c;
+      const int j = j0 + r;
+      int* kids = p.kidsB + (size_t)j * Rmax;
+      for (int q = 0; q < R; ++q) kids[q] = (q == r) ? c : lr[q];
+      put_job(p.jobsB, j, j * Rmax, R, -1, -1, JOB_SCAN | JOB_ADD_PRIOR, j, -1);
+    }
+    if (R > 0 && p.outliers) {
+      const int j = j0 + R;
+      int* kids = p.kidsB + (size_t)j * Rmax;
+      for (int q = 0; q < R; ++q) kids[q] = lr[q];
+      put_job(p.jobsB, j, j * Rmax, R, -1, -1, JOB_SCAN | JOB_ADD_PRIOR, j, -1);
+    }
+    if (R == 0) {
+      const int j = j0;
+      p.kidsB[(size_t)j * Rmax] = sid;
+      put_job(p.jobsB, j, j * Rmax, 1, -1, -1, JOB_SCAN | JOB_ADD_PRIOR, j, -1);
+    }
+    if (R > 1) my_pairs += (u64)(R + ((p.outliers) ? 1 : 0)) * (u64)(R - 1);
+  }
+  if (my_pairs) atomicAdd(p.pairs, my_pairs);
+}
+
+// out = a + b for a device-counted list (tree/tree_node.py:47-52: log_r += value), one warp per (tile, row)
+__global__ void add_list_kernel(const int* __restrict__ a_ids, const int* __restrict__ b_ids,
+                                const int* __restrict__ out_ids, const int* __restrict__ n_dev, double* lg, double* lin,
+                                double* rmax, int S, int G, int pitch, int lead, long long tile_elems) {
+  const long long n_rows = (long long)(*n_dev) * S;
+  const int lane = threadIdx.x & 31;
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); wid < n_rows; wid += warps) {
+    const long long tl = wid / S;
+    const int s = (int)(wid - tl * S);
+    const long long off = (long long)s * pitch + lead;
+    const double* pa = lg + (long long)a_ids[tl] * tile_elems + off;
+    const double* pb = lg + (long long)b_ids[tl] * tile_elems + off;
+    const long long o = (long long)out_ids[tl] * tile_elems + off;
+    double m = -INFINITY;
+    for (int k = lane; k < G; k += 32) m = fmax(m, pa[k] + pb[k]);
+    m = group_max(m, 32);
+    for (int k = lane; k < G; k += 32) {
+      const double v = pa[k] + pb[k];
+      lg[o + k] = v;
+      lin[o + k] = (v == -INFINITY) ? 0.0 : exp(v - m);
+    }
+    if (lane == 0) rmax[(long long)out_ids[tl] * S + s] = m;
+  }
+}
+
+// sum over samples in sample order (tree/distributions.py:197-200)
+__device__ inline double row_sum(const double* rows, int slot, int S) {
+  double acc = 0.0;
+  const double* r = rows + (size_t)slot * S;
+  for (int s = 0; s < S; ++s) acc += r[s];
+  return acc;
+}
+
+__device__ inline double tab(const double* t, int n, int n_tab, bool lf) {
+  if (n < n_tab) return t[n];
+  return lf ? lgamma((double)n + 1.0) : log((double)n);
+}
+
+// (log_p prior, log_p_one prior) from running statistics: csrc/pcb_hostmod.cpp::priors (tree/distributions.py:39-133);
+// `sizes` = subtree sizes of the roots in order
+__device__ inline void priors(const Params& p, long n, double crp, double mult, const int* sizes, int n_sizes,
+                              double oprior, double omarg, double& lp, double& lp1) {
+  const double base = (double)n * p.log_alpha + crp;
+  lp = base - (double)(n - 1) * tab(p.logn, (int)n + 1, p.n_tab, false) - mult;
+  double ways = 0.0;
+  for (int i = 0; i < n_sizes; ++i) ways += (double)(sizes[i] - 1) * tab(p.logn, sizes[i], p.n_tab, false);
+  lp1 = base + (-ways + p.rterm[n_sizes]) - mult;
+  const double extra = oprior + omarg;
+  lp += extra;
+  lp1 += extra;
+}
+
+// smallest k with q[0] + ... + q[k] > u (left-to-right float64 sums); the last index catches the remainder
+__device__ inline int inv_cdf(const double* q, int n, double u) {
+  double acc = 0.0;
+  for (int k = 0; k < n - 1; ++k) {
+    acc += q[k];
+    if (acc > u) return k;
+  }
+  return n - 1;
+}
+
+__device__ inline int alloc_tiles(const Params& p, int n) {
+  const int t0 = atomicAdd(p.tile_top, n);
+  if (t0 + n > p.tile_limit) {
+    atomicOr(p.status, ST_TILES);
+    return p.scratch0;  // in bounds; the sweep is void and the host reruns it with a larger arena
+  }
+  return t0;
+}
+
+constexpr int kMaxRoots = 64;
+
+// ------------------------------------------------------------------------------------------------------------
+// decide: proposal normalisation (a17), the particle's draws, successor state, node / score jobs
+// ------------------------------------------------------------------------------------------------------------
+__global__ void decide_kernel(const Params p, const int t) {
+  const int first = p.conditional ? 1 : 0;
+  const int Rmax = p.Rmax;
+  const int vid = p.value_id[t], sid = p.single_id[t], dpidx = p.dp_idx[t];
+  const double op = p.dp_op[t], opn = p.dp_opn[t], marg = p.dp_marg[t];
+  for (int i = first + threadIdx.x; i < p.N; i += blockDim.x) {
+    const ParentView v = parent_view(p, t, i);
+    const int R = v.bI[0];
+    const int j0 = p.job_off[i];
+    double c_lp[kMaxRoots + 2], c_lp1[kMaxRoots + 2], q[kMaxRoots + 2];
+    int sizes[kMaxRoots + 1];
+    // ---- candidates, scored on the base state (semi_adapted.py:85-141; pcb_hostmod.cpp score_attach_all /
+    //      score_outlier / score_new)
+    const int* b_nd = fld(v.bI, F_NDATA, Rmax);
+    const int* b_sz = fld(v.bI, F_SIZE, Rmax);
+    const int* b_nm = fld(v.bI, F_NAME, Rmax);
+    const long bn = v.bI[1];
+    const double b_crp = v.bD[D_CRP], b_mult = v.bD[D_MULT], b_opr = v.bD[D_OPRIOR], b_om = v.bD[D_OMARG];
+    int n_cand = 0;
+    {
+      const double opr = (op != 0.0) ? b_opr + opn : b_opr;
+      const double head = (double)bn * p.log_alpha;
+      double ways = 0.0;
+      for (int r = 0; r < R; ++r) ways += (double)(b_sz[r] - 1) * tab(p.logn, b_sz[r], p.n_tab, false);
+      const double tail_p = -(double)(bn - 1) * tab(p.logn, (int)bn + 1, p.n_tab, false) - b_mult + (opr + b_om);
+      const double tail_one = (-ways + p.rterm[R]) - b_mult + (opr + b_om);
+      for (int r = 0; r < R; ++r) {
+        const int m = b_nd[r];
+        const double crp = head + (b_crp + (m >= 1 ? tab(p.lfact, m, p.n_tab, true) - tab(p.lfact, m - 1, p.n_tab, true) : 0.0));
+        c_lp[r] = (crp + tail_p) + row_sum(p.scB_lse, j0 + r, p.S);
+        c_lp1[r] = (crp + tail_one) + row_sum(p.scB_last, j0 + r, p.S);
+      }
+      n_cand = R;
+    }
+    int out_idx = -1, new_idx = -1;
+    if (p.outliers) {
+      const double opr = (op != 0.0) ? b_opr + op : b_opr;
+      double lp, lp1;
+      priors(p, bn, b_crp, b_mult, b_sz, R, opr, b_om + marg, lp, lp1);
+      if (R > 0) {
+        lp += row_sum(p.scB_lse, j0 + R, p.S);
+        lp1 += row_sum(p.scB_last, j0 + R, p.S);
+      }
+      out_idx = n_cand;
+      c_lp[n_cand] = lp;
+      c_lp1[n_cand] = lp1;
+      ++n_cand;
+    }
+    if (R == 0) {
+      const double opr = (op != 0.0) ? b_opr + opn : b_opr;
+      const int one = 1;
+      double lp, lp1;
+      priors(p, bn + 1, b_crp, b_mult, &one, 1, opr, b_om, lp, lp1);
+      lp += row_sum(p.scB_lse, j0, p.S);
+      lp1 += row_sum(p.scB_last, j0, p.S);
+      new_idx = n_cand;
+      c_lp[n_cand] = lp;
+      c_lp1[n_cand] = lp1;
+      ++n_cand;
+    }
+    // log_q = log_p - LSE(log_p); q = exp(log_q) / sum   (semi_adapted.py:151-163, utils/math.py:102-121)
+    double mx = -INFINITY;
+    for (int c = 0; c < n_cand; ++c) mx = fmax(mx, c_lp[c]);
+    if (!(mx > -INFINITY) || !(mx < INFINITY)) atomicOr(p.status, ST_NUMERIC);
+    double tot = 0.0;
+    for (int c = 0; c < n_cand; ++c) tot += exp(c_lp[c] - mx);
+    const double lse = log(tot) + mx;
+    double qs = 0.0;
+    for (int c = 0; c < n_cand; ++c) {
+      q[c] = exp(c_lp[c] - lse);
+      qs += q[c];
+    }
+    for (int c = 0; c < n_cand; ++c) q[c] /= qs;
+
+    // ---- the particle's draws (semi_adapted.py:63-83, 165-194; conventions of oracle/uniform.py)
+    int kind, pick = -1, k_new = 0;
+    u64 taken_base = 0;  // NEW: chosen positions in BASE order (= the parent's tree_roots the reference draws from)
+    double logq;
+    bool known;  // log_p of the new particle is one of the candidates'
+    if (R == 0) {
+      pick = inv_cdf(q, n_cand, u01(p.seed, t, i, 0));
+      kind = (pick == out_idx) ? K_OUTLIER : K_NEW;
+      logq = c_lp[pick] - lse;
+      known = true;
+    } else if (u01(p.seed, t, i, 0) < 0.5) {
+      pick = inv_cdf(q, n_cand, u01(p.seed, t, i, 1));
+      kind = (pick == out_idx) ? K_OUTLIER : K_ATTACH;
+      logq = p.log_half + (c_lp[pick] - lse);
+      known = true;
+    } else {
+      kind = K_NEW;
+      known = false;
+      k_new = min(R, (int)(u01(p.seed, t, i, 1) * (double)(R + 1)));
+      unsigned char pos[kMaxRoots];
+      for (int r = 0; r < R; ++r) pos[r] = (unsigned char)r;
+      for (int m = 0; m < k_new; ++m) {
+        const int rest = R - m;
+        const int j = m + min(rest - 1, (int)(u01(p.seed, t, i, 2 + m) * (double)rest));
+        const unsigned char tmp = pos[m];
+        pos[m] = pos[j];
+        pos[j] = tmp;
+        taken_base |= 1ull << pos[m];
+      }
+      const double lbin = tab(p.lfact, R, p.n_tab, true) - tab(p.lfact, k_new, p.n_tab, true) -
+                          tab(p.lfact, R - k_new, p.n_tab, true);
+      logq = p.log_half - (tab(p.logn, R + 1, p.n_tab, false) + lbin);
+    }
+
+    // ---- successor state = extend(thawed parent, edit)   (pcb_hostmod.cpp fstate_extend)
+    const int* s_nm = fld(v.pI, F_NAME, Rmax);
+    const int* s_lr = fld(v.pI, F_LR, Rmax);
+    const int* s_lp = fld(v.pI, F_LP, Rmax);
+    const int* s_nd = fld(v.pI, F_NDATA, Rmax);
+    const int* s_sz = fld(v.pI, F_SIZE, Rmax);
+    const int* s_sl = fld(v.pI, F_SLOT, Rmax);
+    const int* s_gi = fld(v.pI, F_GIDX, Rmax);
+    const int* s_ko = fld(v.pI, F_KOFF, Rmax);
+    const int* s_kc = fld(v.pI, F_KCNT, Rmax);
+    const int pn = v.pI[1], ps = v.pI[2], pe = v.pI[3], po = v.pI[4];
+    const double s_crp = v.pD[D_CRP], s_mult = v.pD[D_MULT], s_opr = v.pD[D_OPRIOR], s_om = v.pD[D_OMARG];
+    const u64 s_key = v.ret ? p.ret_key[t - 1] : p.cur_key[i];
+    int* eI = p.ext_int + (size_t)i * p.irec;
+    double* eD = p.ext_dbl + (size_t)i * DREC;
+    int* e_nm = fld(eI, F_NAME, Rmax);
+    int* e_lr = fld(eI, F_LR, Rmax);
+    int* e_lp = fld(eI, F_LP, Rmax);
+    int* e_nd = fld(eI, F_NDATA, Rmax);
+    int* e_sz = fld(eI, F_SIZE, Rmax);
+    int* e_sl = fld(eI, F_SLOT, Rmax);
+    int* e_gi = fld(eI, F_GIDX, Rmax);
+    int* e_ko = fld(eI, F_KOFF, Rmax);
+    int* e_kc = fld(eI, F_KCNT, Rmax);
+    double lp_new = 0.0, lp1_new = 0.0;
+    int name_out = -1, slot_e = -1;
+    u64 mask_out = 0;
+    if (kind != K_NEW || R == 0) {
+      lp_new = c_lp[pick];
+      lp1_new = c_lp1[pick];
+    }
+    if (kind == K_OUTLIER || kind == K_ATTACH) {
+      for (int r = 0; r < R; ++r) {
+        e_nm[r] = s_nm[r];
+        e_lr[r] = s_lr[r];
+        e_lp[r] = s_lp[r];
+        e_nd[r] = s_nd[r];
+        e_sz[r] = s_sz[r];
+        e_sl[r] = s_sl[r];
+        e_gi[r] = s_gi[r];
+        e_ko[r] = s_ko[r];
+        e_kc[r] = s_kc[r];
+      }
+      eI[0] = R;
+      eI[1] = pn;
+      eI[2] = ps;
+      eI[3] = pe;
+      eD[D_MULT] = s_mult;
+    }
+    if (kind == K_OUTLIER) {
+      eI[4] = po + 1;
+      eD[D_CRP] = s_crp;
+      eD[D_OMARG] = s_om + marg;
+      eD[D_OPRIOR] = (op != 0.0) ? s_opr + op : s_opr;
+      p.ext_key[i] = s_key ^ data_hash(-1, po, dpidx);
+    } else if (kind == K_ATTACH) {
+      const int name = b_nm[pick];
+      int j = 0;
+      while (j < R && s_nm[j] != name) ++j;
+      if (j >= R) {
+        atomicOr(p.status, ST_NUMERIC);
+        j = 0;
+      }
+      const int n = s_nd[j];
+      const bool leaf = s_kc[j] == 0;
+      const int t1 = alloc_tiles(p, leaf ? 1 : 2);
+      // log_p += value (tree/tree_node.py:42-46): copy of the old log_p tile plus the value tile
+      const int jd = atomicAdd(p.nD, leaf ? 1 : 2);
+      p.kidsD[(size_t)jd * Rmax] = s_lp[j];
+      put_job(p.jobsD, jd, jd * Rmax, 1, vid, t1, 0, -1, -1);
+      e_lp[j] = t1;
+      if (leaf) {
+        e_lr[j] = t1;
+      } else {
+        // log_r = log_p + log_S(children) re-derived as Tree.from_dict does (tree/tree_node.py:61-71), with
+        // log_p = old log_p + value formed on the fly (base + base2)
+        int* kids = p.kidsD + (size_t)(jd + 1) * Rmax;
+        for (int c = 0; c < s_kc[j]; ++c) kids[c] = p.kid_pool[s_ko[j] + c];
+        put_job(p.jobsD, jd + 1, (jd + 1) * Rmax, s_kc[j], s_lp[j], t1 + 1, JOB_SCAN, -1, vid);
+        e_lr[j] = t1 + 1;
+        if (s_kc[j] > 1) atomicAdd(p.pairs, (u64)(s_kc[j] - 1));
+      }
+      e_nd[j] = n + 1;
+      eI[4] = po;
+      eD[D_CRP] = s_crp + (n >= 1 ? tab(p.lfact, n, p.n_tab, true) - tab(p.lfact, n - 1, p.n_tab, true) : 0.0);
+      eD[D_OMARG] = s_om;
+      eD[D_OPRIOR] = (op != 0.0) ? s_opr + opn : s_opr;
+      p.ext_key[i] = s_key ^ data_hash(name, n, dpidx);
+      name_out = name;
+    } else {
+      // positions taken in the THAWED parent's root order; the new node folds its children in that order
+      u64 take = 0;
+      for (int r = 0; r < R; ++r)
+        if (taken_base >> r & 1ull) {
+          const int name = b_nm[r];
+          int j = 0;
+          while (j < R && s_nm[j] != name) ++j;
+          if (j < R) take |= 1ull << j;
+        }
+      const int k = k_new;
+      const int Rn = R - k + 1;
+      if (Rn > Rmax) {
+        atomicOr(p.status, ST_ROOTS);
+      } else {
+        int lr_new = sid, koff = 0;
+        if (k > 0) {
+          lr_new = alloc_tiles(p, 1);
+          koff = atomicAdd(p.pool_top, k);
+          const int jd = atomicAdd(p.nD, 1);
+          int* kids = p.kidsD + (size_t)jd * Rmax;
+          int c = 0;
+          const bool pool_ok = koff + k <= p.pool_cap;
+          if (!pool_ok) atomicOr(p.status, ST_POOL);
+          for (int r = 0; r < R; ++r)
+            if (take >> r & 1ull) {
+              kids[c] = s_lr[r];
+              if (pool_ok) p.kid_pool[koff + c] = s_lr[r];
+              ++c;
+            }
+          put_job(p.jobsD, jd, jd * Rmax, k, sid, lr_new, JOB_SCAN, -1, -1);
+          if (k > 1) atomicAdd(p.pairs, (u64)(k - 1));
+        }
+        int sz = 1;
+        u64 key = s_key ^ edge_hash(pe, 0, ps) ^ data_hash(pn, 0, dpidx);
+        for (int r = 0; r < R; ++r)
+          if (take >> r & 1ull) {
+            sz += s_sz[r];
+            key ^= edge_hash(s_sl[r], 0, s_gi[r]) ^ edge_hash(s_sl[r], ps, s_gi[r]);
+          }
+        e_nm[0] = pn;
+        e_lr[0] = lr_new;
+        e_lp[0] = sid;
+        e_nd[0] = 1;
+        e_sz[0] = sz;
+        e_sl[0] = pe;
+        e_gi[0] = ps;
+        e_ko[0] = koff;
+        e_kc[0] = k;
+        sizes[0] = sz;
+        int w = 1;
+        for (int r = 0; r < R; ++r)
+          if (!(take >> r & 1ull)) {
+            e_nm[w] = s_nm[r];
+            e_lr[w] = s_lr[r];
+            e_lp[w] = s_lp[r];
+            e_nd[w] = s_nd[r];
+            e_sz[w] = s_sz[r];
+            e_sl[w] = s_sl[r];
+            e_gi[w] = s_gi[r];
+            e_ko[w] = s_ko[r];
+            e_kc[w] = s_kc[r];
+            sizes[w] = s_sz[r];
+            ++w;
+          }
+        eI[0] = Rn;
+        eI[1] = pn + 1;
+        eI[2] = ps + 1;
+        eI[3] = pe + 1;
+        eI[4] = po;
+        const double mult = s_mult - tab(p.lfact, R, p.n_tab, true) + tab(p.lfact, R - k + 1, p.n_tab, true) +
+                            tab(p.lfact, k, p.n_tab, true);
+        const double opr = (op != 0.0) ? s_opr + opn : s_opr;
+        eD[D_MULT] = mult;
+        eD[D_CRP] = s_crp;
+        eD[D_OMARG] = s_om;
+        eD[D_OPRIOR] = opr;
+        p.ext_key[i] = key;
+        if (R > 0) {  // the new tree is scored from its roots (score_new); an empty parent's lone candidate was
+          priors(p, pn + 1, s_crp, mult, sizes, Rn, opr, s_om, lp_new, lp1_new);
+          slot_e = atomicAdd(p.nE, 1);
+          int* kids = p.kidsE + (size_t)slot_e * Rmax;
+          for (int c = 0; c < Rn; ++c) kids[c] = e_lr[c];
+          put_job(p.jobsE, slot_e, slot_e * Rmax, Rn, -1, -1, JOB_SCAN | JOB_ADD_PRIOR, slot_e, -1);
+          if (Rn > 1) atomicAdd(p.pairs, (u64)(Rn - 1));
+        }
+      }
+      name_out = pn;
+      mask_out = take;
+    }
+    (void)known;
+    p.slotE[i] = slot_e;
+    p.dec_kind[i] = kind | (v.ret ? FLAG_RETAINED_PARENT : 0);
+    p.dec_name[i] = name_out;
+    p.dec_mask[i] = mask_out;
+    p.dec_logq[i] = logq;
+    p.dec_lp[i] = lp_new;
+    p.dec_lp1[i] = lp1_new;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// weigh: incremental weights (kernels/base.py:38-57, samplers/base.py:52-58), swarm statistics (swarm.py:21-61),
+// adaptive multinomial resampling as inverse-CDF ancestors (conditional.py:91-109, standard.py:20-32), the final
+// pick (particle_gibbs.py:42-48) and the permutation of the particle states for the next step.  One CTA.
+// ------------------------------------------------------------------------------------------------------------
+__device__ inline double block_sum(double v, double* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = group_sum(v, 32);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  for (int i = 0; i < nw; ++i) r += sh[i];
+  return r;
+}
+__device__ inline double block_max(double v, double* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = group_max(v, 32);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  double r = -INFINITY;
+  for (int i = 0; i < nw; ++i) r = fmax(r, sh[i]);
+  return r;
+}
+
+__global__ void weigh_kernel(const Params p, const int t, const double log_uniform, const double lw_uniform) {
+  __shared__ double sh_red[32];
+  __shared__ double sh_w[1024];
+  __shared__ int sh_cnt[1024];
+  __shared__ int sh_anc[1024];
+  __shared__ int sh_flag;
+  const int first = p.conditional ? 1 : 0;
+  const int N = p.N, i = threadIdx.x;
+  const bool last = t >= p.T - 1;
+  double raw = -INFINITY;
+  if (i < N) {
+    if (i >= first) {
+      double lp = p.dec_lp[i], lp1 = p.dec_lp1[i];
+      const int se = p.slotE[i];
+      if (se >= 0) {
+        lp += row_sum(p.scE_lse, se, p.S);
+        lp1 += row_sum(p.scE_last, se, p.S);
+      }
+      const double plp = p.cur_dbl[(size_t)i * DREC + D_LOGP];  // 0 for the empty start (parent None)
+      double w = (lp - plp) - p.dec_logq[i];
+      if (last) w = w - lp + lp1;
+      p.ext_dbl[(size_t)i * DREC + D_LOGP] = lp;
+      p.ext_dbl[(size_t)i * DREC + D_LOGP1] = lp1;
+      raw = (p.conditional && t == 0) ? log_uniform : p.lw[i] + w;
+      p.o_logp[(size_t)t * N + i] = lp;
+      p.o_logq[(size_t)t * N + i] = p.dec_logq[i];
+      p.o_kind[(size_t)t * N + i] = p.dec_kind[i];
+      p.o_name[(size_t)t * N + i] = p.dec_name[i];
+      p.o_mask[(size_t)t * N + i] = p.dec_mask[i];
+    } else {  // the retained particle of this step
+      const double* rd = p.ret_th_dbl + (size_t)t * DREC;
+      double w = rd[D_LOGW];
+      if (last) w = w - rd[D_LOGP] + rd[D_LOGP1];
+      raw = (t == 0) ? log_uniform : p.lw[0] + w;
+      p.o_logp[(size_t)t * N] = rd[D_LOGP];
+      p.o_logq[(size_t)t * N] = 0.0;
+      p.o_kind[(size_t)t * N] = -1;
+      p.o_name[(size_t)t * N] = -1;
+      p.o_mask[(size_t)t * N] = 0;
+    }
+    p.o_raw[(size_t)t * N + i] = raw;
+  }
+  // retained record of this step into ext slot 0
+  if (p.conditional) {
+    const int* ri = p.ret_th_int + (size_t)t * p.irec;
+    for (int k = threadIdx.x; k < p.irec; k += blockDim.x) p.ext_int[k] = ri[k];
+    if (threadIdx.x < DREC) p.ext_dbl[threadIdx.x] = p.ret_th_dbl[(size_t)t * DREC + threadIdx.x];
+    if (threadIdx.x == 0) p.ext_key[0] = p.ret_key[t];
+  }
+  // ---- log_Z, log_W, W, ESS
+  const double m = block_max(raw, sh_red);
+  const double e = (i < N) ? exp(raw - m) : 0.0;
+  const double tot = block_sum(e, sh_red);
+  const double log_z = log(tot) + m;
+  const double log_W = raw - log_z;
+  double W = (i < N) ? exp(log_W) : 0.0;
+  const double wsum = block_sum(W, sh_red);
+  W /= wsum;
+  const double sq = block_sum(W * W, sh_red);
+  const double ess = 1.0 / sq;
+  const bool resample = !last && (ess / (double)N) <= p.threshold;
+  if (!(m > -INFINITY) || !(wsum > 0.0)) {
+    if (threadIdx.x == 0) atomicOr(p.status, ST_NUMERIC);
+  }
+  sh_w[i] = W;
+  sh_cnt[i] = 0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    p.o_ess[t] = ess;
+    p.o_resampled[t] = resample ? 1 : 0;
+    sh_flag = 0;
+  }
+  if (last) {
+    // final pick: p = W / sum(W) once more (utils/math.py:19-21 via particle_gibbs.py:42-48)
+    const double w2sum = block_sum((i < N) ? W : 0.0, sh_red);
+    if (threadIdx.x == 0) {
+      const double u = u01(p.seed, 0, FINAL_SLOT, 0);
+      double acc = 0.0;
+      int pick = N - 1;
+      for (int k = 0; k < N - 1; ++k) {
+        acc += sh_w[k] / w2sum;
+        if (acc > u) {
+          pick = k;
+          break;
+        }
+      }
+      *p.o_final = pick;
+    }
+  }
+  if (resample) {
+    // cdf left to right in shared memory (thread 0), then one binary search per draw
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double acc = 0.0;
+      for (int k = 0; k < N; ++k) {
+        acc += sh_w[k];
+        sh_w[k] = acc;
+      }
+    }
+    __syncthreads();
+    const int n_draw = N - first;
+    if (i < n_draw) {
+      const double u = u01(p.seed, t, RESAMPLE_SLOT, i);
+      int lo = 0, hi = N - 1;  // smallest k with cdf[k] > u; the last index catches the remainder
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (sh_w[mid] > u)
+          hi = mid;
+        else
+          lo = mid + 1;
+      }
+      atomicAdd(&sh_cnt[lo], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {  // exclusive prefix of the multiplicities: particle k fills slots [start, start + count)
+      int run = first;
+      for (int k = 0; k < N; ++k) {
+        const int c = sh_cnt[k];
+        sh_cnt[k] = run;
+        run += c;
+      }
+      if (first) sh_anc[0] = 0;
+    }
+    __syncthreads();
+    if (i < N) {
+      const int beg = sh_cnt[i], end = (i + 1 < N) ? sh_cnt[i + 1] : N;
+      for (int s = beg; s < end; ++s) sh_anc[s] = i;
+    }
+  } else if (i < N) {
+    sh_anc[i] = i;
+  }
+  __syncthreads();
+  if (i < N) {
+    p.o_anc[(size_t)t * N + i] = sh_anc[i];
+    p.lw[i] = resample ? lw_uniform : log_W;
+  }
+  // ---- next step's parents: cur[s] = ext[anc[s]]
+  if (!last) {
+    for (int s = 0; s < N; ++s) {
+      const int a = sh_anc[s];
+      const int* src = p.ext_int + (size_t)a * p.irec;
+      int* dst = p.cur_int + (size_t)s * p.irec;
+      const int R = src[0];
+      // only the live part of each field is copied
+      for (int k = threadIdx.x; k < IHEAD + F_COUNT * p.Rmax; k += blockDim.x) {
+        const int f = (k < IHEAD) ? -1 : (k - IHEAD) % p.Rmax;
+        if (f < R) dst[k] = src[k];
+      }
+      if (threadIdx.x < DREC) p.cur_dbl[(size_t)s * DREC + threadIdx.x] = p.ext_dbl[(size_t)a * DREC + threadIdx.x];
+      if (threadIdx.x == 0) p.cur_key[s] = p.ext_key[a];
+    }
+  }
+}
+
+__global__ void init_kernel(const Params p, const double lw0) {
+  for (int i = threadIdx.x; i < p.N; i += blockDim.x) {
+    int* r = p.cur_int + (size_t)i * p.irec;
+    r[0] = 0;
+    r[1] = 0;
+    r[2] = 1;
+    r[3] = 0;
+    r[4] = 0;
+    for (int k = 0; k < DREC; ++k) p.cur_dbl[(size_t)i * DREC + k] = 0.0;
+    p.cur_key[i] = 0;
+    p.lw[i] = lw0;
+  }
+}
+
+}  // namespace sweep
+}  // namespace pcb

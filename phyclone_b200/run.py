@@ -51,7 +51,7 @@ class Chain(object):
 
     def __init__(self, data, rng, num_particles=100, proposal="semi-adapted", resample_threshold=0.5, outlier_prob=0.0,
                  concentration_value=1.0, concentration_update=True, num_samples_data_point=1,
-                 num_samples_prune_regraph=1, device=None, store=None):
+                 num_samples_prune_regraph=1, device=None, store=None, sweep="host"):
         self.data = data
         self.rng = rng
         # the tree walks recurse once per level and a forest over T data points can be T deep
@@ -65,10 +65,15 @@ class Chain(object):
         self.dp_sampler = DataPointSampler(self.tree_dist, rng, outliers=(outlier_prob > 0))
         self.prg_sampler = PruneRegraphSampler(self.tree_dist, rng)
         self.conc_sampler = GammaPriorConcentrationSampler(0.01, 0.01, rng=rng)
+        # sweep="device": the SMC sweeps run device-resident with uniform-driven draws (smc/device_sweep.py); only the
+        # semi-adapted proposal has that form, the other proposals keep the host sampler
+        if sweep == "device" and proposal != "semi-adapted":
+            raise ValueError("sweep='device' needs the semi-adapted proposal")
+        self.sweep = sweep
         self.burnin_sampler = UnconditionalSMCSampler(self.kernel, num_particles=num_particles,
-                                                      resample_threshold=resample_threshold)
+                                                      resample_threshold=resample_threshold, sweep=sweep)
         self.tree_sampler = ParticleGibbsTreeSampler(self.kernel, rng, num_particles=num_particles,
-                                                     resample_threshold=resample_threshold)
+                                                     resample_threshold=resample_threshold, sweep=sweep)
         self.concentration_update = concentration_update
         self.num_samples_data_point = num_samples_data_point
         self.num_samples_prune_regraph = num_samples_prune_regraph
@@ -126,20 +131,25 @@ class Chain(object):
 
     @property
     def stats(self):
-        return dict(self.store.stats, extensions=self.kernel.num_extensions)
+        d = dict(self.store.stats, extensions=self.kernel.num_extensions)
+        for name, sampler in (("sweep", self.tree_sampler), ("burnin_sweep", self.burnin_sampler)):
+            dev = getattr(sampler, "_device", None)
+            if dev is not None:
+                d[name] = dict(dev.stats)
+        return d
 
 
 def run_phyclone_chain(burnin, concentration_update, concentration_value, data, max_time, num_iters, num_particles,
                        num_samples_data_point, num_samples_prune_regraph, outlier_prob, print_freq, proposal,
                        resample_threshold, rng, samples, thin, chain_num, subtree_update_prob, device=None,
-                       store=None, on_iteration=None):
+                       store=None, on_iteration=None, sweep="host"):
     """run.py:177-232 (+ :235-380).  Returns {"data", "samples", "trace", "chain_num", "stats"}."""
     if subtree_update_prob != 0.0:
         raise NotImplementedError("the subtree particle-Gibbs move is outside the B200 hot path (DESIGN.md section 7)")
     chain = Chain(data, rng, num_particles=num_particles, proposal=proposal, resample_threshold=resample_threshold,
                   outlier_prob=outlier_prob, concentration_value=concentration_value,
                   concentration_update=concentration_update, num_samples_data_point=num_samples_data_point,
-                  num_samples_prune_regraph=num_samples_prune_regraph, device=device, store=store)
+                  num_samples_prune_regraph=num_samples_prune_regraph, device=device, store=store, sweep=sweep)
     timer = Timer()
     for i in range(burnin):
         with timer:

@@ -225,14 +225,29 @@ class ConditionalSMCSampler(AbstractSMCSampler):
 class UnconditionalSMCSampler(object):
     """smc/samplers/unconditional.py"""
 
-    def __init__(self, kernel, num_particles=20, resample_threshold=0.5):
+    def __init__(self, kernel, num_particles=20, resample_threshold=0.5, sweep="host"):
         self.kernel = kernel
         self.num_particles = num_particles
         self.resample_threshold = resample_threshold
         self._rng = kernel.rng
+        self._device = None
+        if sweep == "device":
+            from .device_sweep import DeviceSweep
+
+            self._device = DeviceSweep(kernel, num_particles, resample_threshold)
+        elif sweep != "host":
+            raise ValueError("sweep must be 'host' or 'device'")
 
     def sample_tree(self, tree):
         data_sigma = RootPermutationDistribution.sample(tree, self._rng)
+        if self._device is not None:
+            from .device_sweep import SweepFallback
+
+            seed = int(self._rng.integers(0, 1 << 62))
+            try:
+                return self._device.run(data_sigma, seed, None)
+            except SweepFallback:
+                self._device.stats["fallbacks"] += 1
         smc_sampler = SMCSampler(data_sigma, self.kernel, num_particles=self.num_particles,
                                  resample_threshold=self.resample_threshold)
         swarm = smc_sampler.sample()

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def worker(rank, n, steps, warmup, barrier, q):
+def worker(rank, n, steps, warmup, barrier, q, config=2, sweep="host"):
     import numpy as np
     import torch
 
@@ -22,14 +22,13 @@ def worker(rank, n, steps, warmup, barrier, q):
     from phyclone_b200.data.base import make_data_points
     from phyclone_b200.run import Chain
 
-    c = bench.synthetic_counts()
-    cfg = bench.CFG
-    grids = ops.likelihood_grid(c["ref"], c["alt"], c["tumour_content"], c["cn"], c["mu"], c["log_pi"], c["n_geno"],
-                                cfg["grid"], cfg["density"], cfg["precision"])
-    values = ops.cluster_sum(grids, c["cluster_off"])
-    data = make_data_points(values)
+    from phyclone_b200 import workloads
+
+    cfg = bench.set_config(config)
+    values = bench.workload_values_gpu(ops)
+    data = make_data_points(values, outlier_probs=workloads.outlier_log_probs(cfg))
     rng = np.random.default_rng(1).spawn(max(n, 2))[rank] if n > 1 else np.random.default_rng(1)
-    chain = Chain(data, rng, num_particles=cfg["particles"])
+    chain = Chain(data, rng, num_particles=cfg["particles"], outlier_prob=cfg["outlier_prob"], sweep=sweep)
     chain.burnin_step()
     for _ in range(warmup):
         chain.step()
@@ -57,12 +56,12 @@ def main():
         sweep(args)
 
 
-def run_chains_once(n, steps, warmup, timeout=600):
+def run_chains_once(n, steps, warmup, timeout=600, config=2, sweep="host"):
     """n chains, one process each, same GPU; returns the aggregate PG iterations/s over the common timed window."""
     ctx = mp.get_context("spawn")
     barrier = ctx.Barrier(n)
     q = ctx.Queue()
-    procs = [ctx.Process(target=worker, args=(r, n, steps, warmup, barrier, q), daemon=True) for r in range(n)]
+    procs = [ctx.Process(target=worker, args=(r, n, steps, warmup, barrier, q, config, sweep), daemon=True) for r in range(n)]
     for p in procs:
         p.start()
     try:
