@@ -1089,6 +1089,39 @@ def pg_move(tree, kernel, n_particles, threshold):
                   lambda: _pick(smc_conditional(tree, sigma, kernel, n_particles, threshold), kernel.rng, kernel))
 
 
+def subtree_pg_move(tree, kernel, n_particles, threshold):  # mcmc/particle_gibbs.py:51-109
+    """ParticleGibbsSubtreeSampler: re-sample the subtree under the parent of a node picked through a random data
+    point (outliers travel with the subtree), then re-weight every particle by the full tree it completes."""
+    rng, joint = kernel.rng, kernel.joint
+    nodes = [label for label in tree.labels.values() if label != OUT]
+    child = rng.choice(nodes)
+    top = tree.parent(child)
+    parent = tree.parent(top)
+    sub = tree.subtree(top)
+    tree.prune(sub)
+    for dp in tree.outliers:
+        tree.members[OUT].remove(dp)
+        sub.attach(dp, OUT)
+    sigma = sample_sigma(sub, rng)
+
+    def run():
+        swarm = smc_conditional(sub, sigma, kernel, n_particles, threshold)
+        fixed = Swarm()
+        for p, w in zip(swarm.particles, swarm.raw):
+            part = p.thaw()
+            w = w - p.log_p_one
+            full = tree.clone()
+            full.graft(part, parent=parent)
+            for dp in part.outliers:
+                full.attach(dp, OUT)
+            full.refresh_all()
+            q = Particle(p.log_w, p.parent, Holder(full, joint))
+            fixed.add(w + q.log_p_one, q)
+        return _pick(fixed, rng, kernel)
+
+    return _sweep(rng, run)
+
+
 def burnin_move(tree, kernel, n_particles, threshold):  # smc/samplers/unconditional.py
     sigma = sample_sigma(tree, kernel.rng)
     return _sweep(kernel.rng,
@@ -1168,7 +1201,8 @@ def alpha_move(joint, tree, rng, a=0.01, b=0.01):  # concentration.py:29-60, run
 # ------------------------------------------------------------------------------------
 def run_chain(data, rng, num_iters, burnin=1, num_particles=100, proposal="semi-adapted", resample_threshold=0.5,
               outlier_prob=0.0, concentration_value=1.0, concentration_update=True, num_samples_data_point=1,
-              num_samples_prune_regraph=1, use_tile_caches=False, on_iteration=None, sweep_log=None):
+              num_samples_prune_regraph=1, use_tile_caches=False, on_iteration=None, sweep_log=None,
+              subtree_update_prob=0.0):
     """Returns {"trace": [...], "extensions": int, "convs": int}; trace entry =
     {"iter", "alpha", "log_p_one", "tree": frozen dict, "clades", "outliers"} (run.py:293-302).
     `sweep_log`: a list that receives the step / resample / pick records of every SMC sweep (see `_note`)."""
@@ -1204,8 +1238,10 @@ def run_chain(data, rng, num_iters, burnin=1, num_particles=100, proposal="semi-
     trace = [entry(0, tree)]
     for i in range(num_iters):
         kernel.clear()
-        rng.random()  # run.py:268 (subtree_update_prob = 0: the draw is still consumed)
-        tree = moves(pg_move(tree, kernel, num_particles, resample_threshold))
+        if rng.random() < subtree_update_prob:  # run.py:268 (the draw is consumed even when the probability is 0)
+            tree = moves(subtree_pg_move(tree, kernel, num_particles, resample_threshold))
+        else:
+            tree = moves(pg_move(tree, kernel, num_particles, resample_threshold))
         if concentration_update:
             alpha_move(joint, tree, rng)
         trace.append(entry(i, tree))

@@ -13,7 +13,7 @@ import numpy as np
 
 from .mcmc.concentration import GammaPriorConcentrationSampler
 from .mcmc.gibbs_mh import DataPointSampler, PruneRegraphSampler
-from .mcmc.particle_gibbs import ParticleGibbsTreeSampler
+from .mcmc.particle_gibbs import ParticleGibbsSubtreeSampler, ParticleGibbsTreeSampler
 from .smc.kernels import BootstrapKernel, FullyAdaptedKernel, SemiAdaptedKernel
 from .smc.samplers import UnconditionalSMCSampler
 from .tiles import TileStore
@@ -51,7 +51,7 @@ class Chain(object):
 
     def __init__(self, data, rng, num_particles=100, proposal="semi-adapted", resample_threshold=0.5, outlier_prob=0.0,
                  concentration_value=1.0, concentration_update=True, num_samples_data_point=1,
-                 num_samples_prune_regraph=1, device=None, store=None, sweep="host"):
+                 num_samples_prune_regraph=1, device=None, store=None, sweep="host", subtree_update_prob=0.0):
         self.data = data
         self.rng = rng
         # the tree walks recurse once per level and a forest over T data points can be T deep
@@ -74,6 +74,9 @@ class Chain(object):
                                                       resample_threshold=resample_threshold, sweep=sweep)
         self.tree_sampler = ParticleGibbsTreeSampler(self.kernel, rng, num_particles=num_particles,
                                                      resample_threshold=resample_threshold, sweep=sweep)
+        self.subtree_sampler = ParticleGibbsSubtreeSampler(self.kernel, rng, num_particles=num_particles,
+                                                           resample_threshold=resample_threshold)
+        self.subtree_update_prob = subtree_update_prob
         self.concentration_update = concentration_update
         self.num_samples_data_point = num_samples_data_point
         self.num_samples_prune_regraph = num_samples_prune_regraph
@@ -102,8 +105,11 @@ class Chain(object):
         """run.py:261-288: PG sweep, data-point Gibbs, prune-regraph, relabel, concentration update."""
         self.kernel.clear_proposal_dist_caches()
         self.store.reset()
-        self.rng.random()  # run.py:268: the subtree-move coin is drawn even when its probability is 0
-        tree = self.tree = self._local_moves(self.tree_sampler.sample_tree(self.tree))
+        if self.rng.random() < self.subtree_update_prob:  # run.py:268-271 (the coin is drawn even at probability 0)
+            tree = self.subtree_sampler.sample_tree(self.tree)
+        else:
+            tree = self.tree_sampler.sample_tree(self.tree)
+        tree = self.tree = self._local_moves(tree)
         if self.concentration_update:
             node_sizes = [len(v) for k, v in tree.node_data.items() if k != tree.outlier_node_name]
             self.tree_dist.prior.alpha = self.conc_sampler.sample(self.tree_dist.prior.alpha, len(node_sizes),
@@ -144,12 +150,11 @@ def run_phyclone_chain(burnin, concentration_update, concentration_value, data, 
                        resample_threshold, rng, samples, thin, chain_num, subtree_update_prob, device=None,
                        store=None, on_iteration=None, sweep="host"):
     """run.py:177-232 (+ :235-380).  Returns {"data", "samples", "trace", "chain_num", "stats"}."""
-    if subtree_update_prob != 0.0:
-        raise NotImplementedError("the subtree particle-Gibbs move is outside the B200 hot path (DESIGN.md section 7)")
     chain = Chain(data, rng, num_particles=num_particles, proposal=proposal, resample_threshold=resample_threshold,
                   outlier_prob=outlier_prob, concentration_value=concentration_value,
                   concentration_update=concentration_update, num_samples_data_point=num_samples_data_point,
-                  num_samples_prune_regraph=num_samples_prune_regraph, device=device, store=store, sweep=sweep)
+                  num_samples_prune_regraph=num_samples_prune_regraph, device=device, store=store, sweep=sweep,
+                  subtree_update_prob=subtree_update_prob)
     timer = Timer()
     for i in range(burnin):
         with timer:

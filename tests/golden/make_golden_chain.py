@@ -64,11 +64,11 @@ def tree_signature(tree_dict, n_data):
     return own, par
 
 
-def record(name, data, seed, iters, particles, outlier_prob, proposal="semi-adapted", burnin=1):
+def record(name, data, seed, iters, particles, outlier_prob, proposal="semi-adapted", burnin=1, subtree_update_prob=0.0):
     rng = np.random.default_rng(seed)
     with redirect_stdout(io.StringIO()):
         res = run_phyclone_chain(burnin, True, 1.0, data, float("inf"), iters, particles, 1, 1, outlier_prob, 10**9,
-                                 proposal, 0.5, rng, ["s"], 1, 0, 0.0)
+                                 proposal, 0.5, rng, ["s"], 1, 0, subtree_update_prob)
     n = len(data)
     tr = res["trace"]
     own, par = zip(*[tree_signature(e["tree"], n) for e in tr])
@@ -84,10 +84,22 @@ def record(name, data, seed, iters, particles, outlier_prob, proposal="semi-adap
         "outlier_prob_run": np.array(outlier_prob),
         "proposal": np.array(proposal),
         "rng_after": np.array(rng.random()),
+        "subtree_update_prob": np.array(subtree_update_prob),
     }
     path = os.path.join(HERE, "chain_%s.npz" % name)
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes; final log_p_one", tr[-1]["log_p_one"])
+
+
+def main_subtree():
+    """Traces with the subtree particle-Gibbs move on (mcmc/particle_gibbs.py:51-109, run.py:268-271)."""
+    bypass_tile_caches()
+    syn = make_synthetic(n_clusters=12, n_samples=3, grid_size=41, muts_per_cluster=4, depth=800, seed=0)
+    data = [RefDataPoint(i, v) for i, v in enumerate(syn["values"][:10])]
+    record("syn10_subtree", data, seed=2, iters=12, particles=12, outlier_prob=0, subtree_update_prob=0.5)
+    lo, lon = np.log(1e-3) * 4, np.log1p(-1e-3) * 4
+    data = [RefDataPoint(i, v, outlier_prob=lo, outlier_prob_not=lon) for i, v in enumerate(syn["values"][:8])]
+    record("syn8_subtree_outliers", data, seed=4, iters=10, particles=10, outlier_prob=1e-3, subtree_update_prob=0.5)
 
 
 def main():
@@ -112,4 +124,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if "--subtree" in sys.argv:
+        main_subtree()
+    else:
+        main()

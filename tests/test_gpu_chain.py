@@ -18,7 +18,7 @@ from tests.parity import assert_close_bucketed
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["mixing", "syn12", "syn8_outliers", "syn6_fully", "syn6_boot"]
+CASES = ["mixing", "syn12", "syn8_outliers", "syn6_fully", "syn6_boot", "syn10_subtree", "syn8_subtree_outliers"]
 
 
 def _data(g):
@@ -35,7 +35,8 @@ def _run(g, rng):
 
     seed, iters, particles, burnin = [int(x) for x in g["meta"]]
     return run_phyclone_chain(burnin, True, 1.0, _data(g), float("inf"), iters, particles, 1, 1,
-                              float(g["outlier_prob_run"]), 10**9, str(g["proposal"]), 0.5, rng, ["s"], 1, 0, 0.0)
+                              float(g["outlier_prob_run"]), 10**9, str(g["proposal"]), 0.5, rng, ["s"], 1, 0,
+                              float(g["subtree_update_prob"]) if "subtree_update_prob" in g else 0.0)
 
 
 @pytest.mark.parametrize("name", CASES)

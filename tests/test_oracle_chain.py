@@ -7,7 +7,7 @@ import pytest
 from oracle import sampler as osm
 from tests.chain_utils import compare_trace, load_chain
 
-CASES = ["mixing", "syn12", "syn8_outliers", "syn6_fully", "syn6_boot"]
+CASES = ["mixing", "syn12", "syn8_outliers", "syn6_fully", "syn6_boot", "syn10_subtree", "syn8_subtree_outliers"]
 
 
 def run_oracle(g, **kw):
@@ -17,7 +17,8 @@ def run_oracle(g, **kw):
     seed, iters, particles, burnin = [int(x) for x in g["meta"]]
     rng = np.random.default_rng(seed)
     res = osm.run_chain(data, rng, iters, burnin=burnin, num_particles=particles, proposal=str(g["proposal"]),
-                        outlier_prob=float(g["outlier_prob_run"]), **kw)
+                        outlier_prob=float(g["outlier_prob_run"]),
+                        subtree_update_prob=float(g["subtree_update_prob"]) if "subtree_update_prob" in g else 0.0, **kw)
     return res, rng
 
 

@@ -18,7 +18,8 @@ def record_oracle(g):
     seed, iters, particles, burnin = [int(x) for x in g["meta"]]
     rec = RecordingRNG(np.random.default_rng(seed))
     res = osm.run_chain(data, rec, iters, burnin=burnin, num_particles=particles, proposal=str(g["proposal"]),
-                        outlier_prob=float(g["outlier_prob_run"]))
+                        outlier_prob=float(g["outlier_prob_run"]),
+                        subtree_update_prob=float(g["subtree_update_prob"]) if "subtree_update_prob" in g else 0.0)
     return res, rec.tape
 
 
@@ -34,12 +35,14 @@ def replay_product(g, tape, store):
     seed, iters, particles, burnin = [int(x) for x in g["meta"]]
     rep = ReplayRNG(tape)
     res = run_phyclone_chain(burnin, True, 1.0, data, float("inf"), iters, particles, 1, 1, float(g["outlier_prob_run"]),
-                             10**9, str(g["proposal"]), 0.5, rep, ["s"], 1, 0, 0.0, store=store)
+                             10**9, str(g["proposal"]), 0.5, rep, ["s"], 1, 0,
+                             float(g["subtree_update_prob"]) if "subtree_update_prob" in g else 0.0, store=store)
     assert rep.done(), "product consumed %d of %d recorded draws" % (rep.pos, len(tape))
     return res, rep
 
 
-@pytest.mark.parametrize("name", ["mixing", "syn12", "syn8_outliers", "syn6_fully", "syn6_boot"])
+@pytest.mark.parametrize("name", ["mixing", "syn12", "syn8_outliers", "syn6_fully", "syn6_boot", "syn10_subtree",
+                                  "syn8_subtree_outliers"])
 def test_tape_replay_cpu(name):
     g = load_chain(name)
     res, tape = record_oracle(g)
