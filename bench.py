@@ -340,7 +340,8 @@ def run_ours(args):
 
     store = TileStore(values, device=dev, variant=TileStore.LATENCY_LAYOUT)  # what run_phyclone_chain uses
     chain = Chain(data, chain_rng(rank, world), num_particles=CFG["particles"], proposal=CFG["proposal"],
-                  resample_threshold=CFG["resample_threshold"], outlier_prob=CFG["outlier_prob"], store=store)
+                  resample_threshold=CFG["resample_threshold"], outlier_prob=CFG["outlier_prob"], store=store,
+                  sweep=args.sweep)
     chain.burnin_step()
     for _ in range(args.warmup):
         chain.step()
@@ -384,7 +385,10 @@ def run_ours(args):
     launches = ops.launch_count() - launches0
     s1 = dict(chain.stats)
     kernel_ms, n_timed = ops.timing_end()
-    conv_pairs = s1["conv_pairs"] - s0["conv_pairs"]
+    def all_pairs(st):  # pair convolutions folded by flushes of the tile store + by device-resident sweeps
+        return st["conv_pairs"] + sum(st.get(k, {}).get("conv_pairs", 0) for k in ("sweep", "burnin_sweep"))
+
+    conv_pairs = all_pairs(s1) - all_pairs(s0)
     flop = conv_pairs * CFG["samples"] * CFG["grid"] * (CFG["grid"] + 1)  # 2 flop x S*G*(G+1)/2 FMA per pair conv
     n_launch = max(n_timed, 1)
     achieved = flop / max(kernel_ms * 1e-3, 1e-12)
@@ -497,8 +501,11 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "chains_on_one_gpu_mps": mps_chains,
             "clocks": clocks.summary(),
-            "per_step": {k: (s1[k] - s0[k]) / args.steps for k in ("flushes", "launches", "node_jobs", "adds", "scores",
-                                                                    "conv_pairs", "memo_hits", "extensions")},
+            "per_step": dict({k: (s1[k] - s0[k]) / args.steps for k in ("flushes", "launches", "node_jobs", "adds", "scores",
+                                                                         "conv_pairs", "memo_hits", "extensions")},
+                             **({"sweep_" + k: (s1["sweep"][k] - s0["sweep"][k]) / args.steps for k in s1["sweep"]}
+                                if "sweep" in s1 else {})),
+            "sweep": args.sweep,
         }
         print(json.dumps(line))
     if world > 1:
@@ -513,6 +520,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mps-chains", action="store_true", help="skip the 8-chains-on-one-GPU (MPS) leg")
+    ap.add_argument("--sweep", default="device", choices=["host", "device"],
+                    help="SMC sweeps on the host (NumPy Generator draws, RNG-identical to the reference) or device-resident "
+                         "(uniform-driven draws, csrc/pcb_sweep.cuh)")
     ap.add_argument("--config", type=int, default=2, choices=[1, 2, 4, 5],
                     help="BASELINE.json configuration number (1-based; 3 = config 2 with --chains 8)")
     ap.add_argument("--chains", type=int, default=None, help="number of chains of the job (default: one per GPU)")

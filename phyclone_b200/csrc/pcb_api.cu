@@ -122,7 +122,7 @@ int pool_ctas() {
   if (!v) {
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    v = sms * 8;
+    v = sms * 12;
   }
   return v;
 }
@@ -974,17 +974,17 @@ int pcb_smc_sweep_dev(const pcb_arena* a, const pcb_sweep_desc* d, void* stream)
     P.cur_int = ci.take<int>((size_t)N * irec);
     P.ext_int = ci.take<int>((size_t)N * irec);
     P.use_ret = ci.take<int>(N);
-    P.cand_off = ci.take<int>(N + 1);
+    P.rep = ci.take<int>(N + 1);
     P.job_off = ci.take<int>(N + 1);
     P.jobsB = ci.take<int>((size_t)maxB * 8);
     P.kidsB = ci.take<int>((size_t)maxB * Rmax);
     P.addA = ci.take<int>((size_t)N * Rmax);
     P.addB = ci.take<int>((size_t)N * Rmax);
     P.addO = ci.take<int>((size_t)N * Rmax);
-    P.jobsD = ci.take<int>((size_t)2 * N * 8);
-    P.kidsD = ci.take<int>((size_t)2 * N * Rmax);
-    P.jobsE = ci.take<int>((size_t)N * 8);
-    P.kidsE = ci.take<int>((size_t)N * Rmax);
+    P.jobsD = ci.take<int>((size_t)N * 8);
+    P.kidsD = ci.take<int>((size_t)N * Rmax);
+    P.jobsE = ci.take<int>((size_t)2 * N * 8);
+    P.kidsE = ci.take<int>((size_t)2 * N * Rmax);
     P.slotE = ci.take<int>(N);
     P.dec_kind = ci.take<int>(N);
     P.dec_name = ci.take<int>(N);
@@ -1008,8 +1008,8 @@ int pcb_smc_sweep_dev(const pcb_arena* a, const pcb_sweep_desc* d, void* stream)
     P.raw = cd.take<double>(N);
     P.scB_lse = cd.take<double>((size_t)maxB * S);
     P.scB_last = cd.take<double>((size_t)maxB * S);
-    P.scE_lse = cd.take<double>((size_t)N * S);
-    P.scE_last = cd.take<double>((size_t)N * S);
+    P.scE_lse = cd.take<double>((size_t)2 * N * S);
+    P.scE_last = cd.take<double>((size_t)2 * N * S);
     P.dec_logq = cd.take<double>(N);
     P.dec_lp = cd.take<double>(N);
     P.dec_lp1 = cd.take<double>(N);
@@ -1090,28 +1090,29 @@ int pcb_smc_sweep_dev(const pcb_arena* a, const pcb_sweep_desc* d, void* stream)
   sw::init_kernel<<<1, threads1, 0, st>>>(P, d->lw_uniform);
   PCB_LAUNCH_CHECK();
   int64_t launches = 1;
+  const int first = d->conditional ? 1 : 0;
+  const unsigned grid_build = (unsigned)((N - first + sw::kBuildWarps - 1) / sw::kBuildWarps);
+  const unsigned grid_decide = (unsigned)((N - first + sw::kDecideWarps - 1) / sw::kDecideWarps);
   for (int t = 0; t < T; ++t) {
-    sw::build_kernel<<<1, 1024, 0, st>>>(P, t);
+    sw::build_kernel<<<grid_build, 32 * sw::kBuildWarps, 0, st>>>(P, t);
     PCB_LAUNCH_CHECK();
-    if (t > 0 || !d->conditional || true) {
+    if (t > 0) {
       const int wpb = 8;
-      const long long max_rows = (long long)N * std::min(Rmax, t + 1) * S;
+      const long long max_rows = (long long)N * std::min(Rmax, t) * S;
       const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((max_rows + wpb - 1) / wpb, 148 * 8));
-      if (t > 0) {
-        sw::add_list_kernel<<<grid, wpb * 32, 0, st>>>(P.addA, P.addB, P.addO, P.nAdd, a->lg, a->lin, a->rmax, l.S, l.G,
-                                                      l.pitch, l.lead, l.tile_elems);
-        PCB_LAUNCH_CHECK();
-        ++launches;
-      }
+      sw::add_list_kernel<<<grid, wpb * 32, 0, st>>>(P.addA, P.addB, P.addO, P.nAdd, a->lg, a->lin, a->rmax, l.S, l.G,
+                                                    l.pitch, l.lead, l.tile_elems);
+      PCB_LAUNCH_CHECK();
+      ++launches;
     }
     const long long boundB = (long long)N * (std::min(Rmax, t) + 1);
     if ((rc = jobs_launch_timed(a, P.jobsB, P.kidsB, boundB, d->prior, P.scB_lse, P.scB_last, stream, P.nB))) return rc;
-    sw::decide_kernel<<<1, threads1, 0, st>>>(P, t);
+    sw::decide_kernel<<<grid_decide, 32 * sw::kDecideWarps, 0, st>>>(P, t);
     PCB_LAUNCH_CHECK();
     launches += 3;
     if (t > 0) {
-      if ((rc = jobs_launch_timed(a, P.jobsD, P.kidsD, 2ll * N, d->prior, nullptr, nullptr, stream, P.nD))) return rc;
-      if ((rc = jobs_launch_timed(a, P.jobsE, P.kidsE, N, d->prior, P.scE_lse, P.scE_last, stream, P.nE))) return rc;
+      if ((rc = jobs_launch_timed(a, P.jobsD, P.kidsD, N, d->prior, nullptr, nullptr, stream, P.nD))) return rc;
+      if ((rc = jobs_launch_timed(a, P.jobsE, P.kidsE, 2ll * N, d->prior, P.scE_lse, P.scE_last, stream, P.nE))) return rc;
       launches += 2;
     }
     sw::weigh_kernel<<<1, 1024, 0, st>>>(P, t, d->log_uniform, d->lw_uniform);

@@ -55,7 +55,7 @@ struct Params {
   double *cur_dbl, *ext_dbl;
   u64 *cur_key, *ext_key;
   double *lw, *raw;
-  int *use_ret, *cand_off, *job_off;
+  int *use_ret, *rep, *job_off;
   int *jobsB, *kidsB, *nB, *addA, *addB, *addO, *nAdd;
   int *jobsD, *kidsD, *nD, *jobsE, *kidsE, *nE;
   double *scB_lse, *scB_last, *scE_lse, *scE_last;
@@ -136,74 +136,65 @@ __device__ inline void put_job(int* jobs, int j, int coff, int C, int base, int 
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// build: candidate tiles + candidate score jobs of step t (semi_adapted.py:85-141)
-// candidates of a parent with R roots, in the reference's order: attach to root 0..R-1 (base order), the outlier
-// tree if outliers are modelled, the lone new-root tree if the parent is empty
+// build: candidate tiles + candidate score jobs of step t (semi_adapted.py:85-141).  One warp per particle.
+// Candidates of a parent with R roots, in the reference's order: attach to root 0..R-1 (base order), the outlier
+// tree if outliers are modelled, the lone new-root tree if the parent is empty.  Particles with equal trees (equal
+// structure hash -- resampled copies, or lineages that met) share ONE set of candidates, built by the first of them
+// (`rep`): the value-keyed proposal cache of the reference (semi_adapted.py:219-237), which is also what keeps the
+// candidate launch at the number of DISTINCT parents.
 // ------------------------------------------------------------------------------------------------------------
+constexpr int kBuildWarps = 8;
+
 __global__ void build_kernel(const Params p, const int t) {
-  __shared__ int sh_jobs[1024], sh_adds[1024];
   const int first = p.conditional ? 1 : 0;
   const int Rmax = p.Rmax;
-  for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
-    int nj = 0, na = 0;
-    if (i >= first && i < p.N) {
-      const ParentView v = parent_view(p, t, i);
-      const int R = v.bI[0];
-      nj = R + ((p.outliers && R > 0) ? 1 : 0) + (R == 0 ? 1 : 0);
-      na = R;
-      p.use_ret[i] = v.ret ? 1 : 0;
+  const int lane = threadIdx.x & 31;
+  const int i = first + blockIdx.x * kBuildWarps + (threadIdx.x >> 5);
+  if (i >= p.N) return;
+  const u64 key = p.cur_key[i];
+  int rep = i;
+  for (int j = first + lane; j < i; j += 32)
+    if (p.cur_key[j] == key) {
+      rep = j;
+      break;
     }
-    sh_jobs[i] = nj;
-    sh_adds[i] = na;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int rj = 0, ra = 0;
-    for (int i = 0; i < p.N; ++i) {
-      const int a = sh_jobs[i], b = sh_adds[i];
-      sh_jobs[i] = rj;
-      sh_adds[i] = ra;
-      rj += a;
-      ra += b;
-    }
-    *p.nB = rj;
-    *p.nAdd = ra;
-    *p.nD = 0;
-    *p.nE = 0;
-  }
-  __syncthreads();
-  u64 my_pairs = 0;
-  const int vid = p.value_id[t], sid = p.single_id[t];
-  for (int i = first + threadIdx.x; i < p.N; i += blockDim.x) {
-    const ParentView v = parent_view(p, t, i);
-    const int R = v.bI[0];
-    const int* lr = fld(v.bI, F_LR, Rmax);
-    const int j0 = sh_jobs[i], a0 = sh_adds[i];
+  rep = __reduce_min_sync(0xffffffffu, rep);
+  if (lane == 0) p.rep[i] = rep;
+  if (rep != i) return;
+  const ParentView v = parent_view(p, t, i);
+  const int R = v.bI[0];
+  const int* lr = fld(v.bI, F_LR, Rmax);
+  const int nj = R + ((p.outliers && R > 0) ? 1 : 0) + (R == 0 ? 1 : 0);
+  int j0 = 0, a0 = 0;
+  if (lane == 0) {
+    j0 = atomicAdd(p.nB, nj);
+    a0 = atomicAdd(p.nAdd, R);
     p.job_off[i] = j0;
-    for (int r = 0; r < R; ++r) {
-      const int c = p.scratch0 + a0 + r;
-      p.addA[a0 + r] = lr[r];
-      p.addB[a0 + r] = vid;
-      p.addO[a0 + r] = c;
-      const int j = j0 + r;
-      int* kids = p.kidsB + (size_t)j * Rmax;
-      for (int q = 0; q < R; ++q) kids[q] = (q == r) ? c : lr[q];
-      put_job(p.jobsB, j, j * Rmax, R, -1, -1, JOB_SCAN | JOB_ADD_PRIOR, j, -1);
-    }
-    if (R > 0 && p.outliers) {
-      const int j = j0 + R;
-      int* kids = p.kidsB + (size_t)j * Rmax;
-      for (int q = 0; q < R; ++q) kids[q] = lr[q];
-      put_job(p.jobsB, j, j * Rmax, R, -1, -1, JOB_SCAN | JOB_ADD_PRIOR, j, -1);
-    }
-    if (R == 0) {
-      const int j = j0;
-      p.kidsB[(size_t)j * Rmax] = sid;
-      put_job(p.jobsB, j, j * Rmax, 1, -1, -1, JOB_SCAN | JOB_ADD_PRIOR, j, -1);
-    }
-    if (R > 1) my_pairs += (u64)(R + ((p.outliers) ? 1 : 0)) * (u64)(R - 1);
+    if (R > 1) atomicAdd(p.pairs, (u64)(R + (p.outliers ? 1 : 0)) * (u64)(R - 1));
   }
-  if (my_pairs) atomicAdd(p.pairs, my_pairs);
+  j0 = __shfl_sync(0xffffffffu, j0, 0);
+  a0 = __shfl_sync(0xffffffffu, a0, 0);
+  const int vid = p.value_id[t], sid = p.single_id[t];
+  for (int r = lane; r < R; r += 32) {
+    const int c = p.scratch0 + a0 + r;
+    p.addA[a0 + r] = lr[r];
+    p.addB[a0 + r] = vid;
+    p.addO[a0 + r] = c;
+    const int j = j0 + r;
+    int* kids = p.kidsB + (size_t)j * Rmax;
+    for (int q = 0; q < R; ++q) kids[q] = (q == r) ? c : lr[q];
+    put_job(p.jobsB, j, j * Rmax, R, -1, -1, JOB_SCAN | JOB_ADD_PRIOR, j, -1);
+  }
+  if (R > 0 && p.outliers) {
+    const int j = j0 + R;
+    int* kids = p.kidsB + (size_t)j * Rmax;
+    for (int q = lane; q < R; q += 32) kids[q] = lr[q];
+    if (lane == 0) put_job(p.jobsB, j, j * Rmax, R, -1, -1, JOB_SCAN | JOB_ADD_PRIOR, j, -1);
+  }
+  if (R == 0 && lane == 0) {
+    p.kidsB[(size_t)j0 * Rmax] = sid;
+    put_job(p.jobsB, j0, j0 * Rmax, 1, -1, -1, JOB_SCAN | JOB_ADD_PRIOR, j0, -1);
+  }
 }
 
 // out = a + b for a device-counted list (tree/tree_node.py:47-52: log_r += value), one warp per (tile, row)
@@ -279,46 +270,58 @@ __device__ inline int alloc_tiles(const Params& p, int n) {
 }
 
 constexpr int kMaxRoots = 64;
+constexpr int kDecideWarps = 8;
 
 // ------------------------------------------------------------------------------------------------------------
-// decide: proposal normalisation (a17), the particle's draws, successor state, node / score jobs
+// decide: proposal normalisation (a17), the particle's draws, successor state, node / score jobs.
+// One warp per particle: lane r scores candidate r and copies root r of the state; the scalar logic is executed
+// redundantly by all lanes (warp-uniform), side effects by lane 0.
+// Jobs: table D = tiles of NEW nodes (the scores of their trees need them), table E = scores of the new-node trees
+// plus the refreshed tiles of roots that took the data point (only the next step reads those): two dependent launches.
 // ------------------------------------------------------------------------------------------------------------
 __global__ void decide_kernel(const Params p, const int t) {
+  __shared__ double sh_lp[kDecideWarps][kMaxRoots + 2], sh_lp1[kDecideWarps][kMaxRoots + 2],
+      sh_q[kDecideWarps][kMaxRoots + 2];
   const int first = p.conditional ? 1 : 0;
   const int Rmax = p.Rmax;
+  const int lane = threadIdx.x & 31, wslot = threadIdx.x >> 5;
+  const int i = first + blockIdx.x * kDecideWarps + wslot;
+  if (i >= p.N) return;
+  double* c_lp = sh_lp[wslot];
+  double* c_lp1 = sh_lp1[wslot];
+  double* q = sh_q[wslot];
   const int vid = p.value_id[t], sid = p.single_id[t], dpidx = p.dp_idx[t];
   const double op = p.dp_op[t], opn = p.dp_opn[t], marg = p.dp_marg[t];
-  for (int i = first + threadIdx.x; i < p.N; i += blockDim.x) {
-    const ParentView v = parent_view(p, t, i);
-    const int R = v.bI[0];
-    const int j0 = p.job_off[i];
-    double c_lp[kMaxRoots + 2], c_lp1[kMaxRoots + 2], q[kMaxRoots + 2];
-    int sizes[kMaxRoots + 1];
-    // ---- candidates, scored on the base state (semi_adapted.py:85-141; pcb_hostmod.cpp score_attach_all /
-    //      score_outlier / score_new)
-    const int* b_nd = fld(v.bI, F_NDATA, Rmax);
-    const int* b_sz = fld(v.bI, F_SIZE, Rmax);
-    const int* b_nm = fld(v.bI, F_NAME, Rmax);
-    const long bn = v.bI[1];
-    const double b_crp = v.bD[D_CRP], b_mult = v.bD[D_MULT], b_opr = v.bD[D_OPRIOR], b_om = v.bD[D_OMARG];
-    int n_cand = 0;
-    {
-      const double opr = (op != 0.0) ? b_opr + opn : b_opr;
-      const double head = (double)bn * p.log_alpha;
-      double ways = 0.0;
-      for (int r = 0; r < R; ++r) ways += (double)(b_sz[r] - 1) * tab(p.logn, b_sz[r], p.n_tab, false);
-      const double tail_p = -(double)(bn - 1) * tab(p.logn, (int)bn + 1, p.n_tab, false) - b_mult + (opr + b_om);
-      const double tail_one = (-ways + p.rterm[R]) - b_mult + (opr + b_om);
-      for (int r = 0; r < R; ++r) {
-        const int m = b_nd[r];
-        const double crp = head + (b_crp + (m >= 1 ? tab(p.lfact, m, p.n_tab, true) - tab(p.lfact, m - 1, p.n_tab, true) : 0.0));
-        c_lp[r] = (crp + tail_p) + row_sum(p.scB_lse, j0 + r, p.S);
-        c_lp1[r] = (crp + tail_one) + row_sum(p.scB_last, j0 + r, p.S);
-      }
-      n_cand = R;
+  const ParentView v = parent_view(p, t, i);
+  const int R = v.bI[0];
+  const int j0 = p.job_off[p.rep[i]];
+  // ---- candidates, scored on the base state (semi_adapted.py:85-141; pcb_hostmod.cpp score_attach_all /
+  //      score_outlier / score_new)
+  const int* b_nd = fld(v.bI, F_NDATA, Rmax);
+  const int* b_sz = fld(v.bI, F_SIZE, Rmax);
+  const int* b_nm = fld(v.bI, F_NAME, Rmax);
+  const long bn = v.bI[1];
+  const double b_crp = v.bD[D_CRP], b_mult = v.bD[D_MULT], b_opr = v.bD[D_OPRIOR], b_om = v.bD[D_OMARG];
+  int n_cand = R;
+  {
+    const double opr = (op != 0.0) ? b_opr + opn : b_opr;
+    const double head = (double)bn * p.log_alpha;
+    double ways = 0.0;
+    for (int r = 0; r < R; ++r) ways += (double)(b_sz[r] - 1) * tab(p.logn, b_sz[r], p.n_tab, false);
+    const double tail_p = -(double)(bn - 1) * tab(p.logn, (int)bn + 1, p.n_tab, false) - b_mult + (opr + b_om);
+    const double tail_one = (-ways + p.rterm[R]) - b_mult + (opr + b_om);
+    for (int r = lane; r < R; r += 32) {
+      const int m = b_nd[r];
+      const double crp =
+          head + (b_crp + (m >= 1 ? tab(p.lfact, m, p.n_tab, true) - tab(p.lfact, m - 1, p.n_tab, true) : 0.0));
+      c_lp[r] = (crp + tail_p) + row_sum(p.scB_lse, j0 + r, p.S);
+      c_lp1[r] = (crp + tail_one) + row_sum(p.scB_last, j0 + r, p.S);
     }
-    int out_idx = -1, new_idx = -1;
-    if (p.outliers) {
+  }
+  int out_idx = -1;
+  if (p.outliers) {
+    out_idx = n_cand;
+    if (lane == 0) {
       const double opr = (op != 0.0) ? b_opr + op : b_opr;
       double lp, lp1;
       priors(p, bn, b_crp, b_mult, b_sz, R, opr, b_om + marg, lp, lp1);
@@ -326,200 +329,269 @@ __global__ void decide_kernel(const Params p, const int t) {
         lp += row_sum(p.scB_lse, j0 + R, p.S);
         lp1 += row_sum(p.scB_last, j0 + R, p.S);
       }
-      out_idx = n_cand;
       c_lp[n_cand] = lp;
       c_lp1[n_cand] = lp1;
-      ++n_cand;
     }
-    if (R == 0) {
+    ++n_cand;
+  }
+  if (R == 0) {
+    if (lane == 0) {
       const double opr = (op != 0.0) ? b_opr + opn : b_opr;
       const int one = 1;
       double lp, lp1;
       priors(p, bn + 1, b_crp, b_mult, &one, 1, opr, b_om, lp, lp1);
       lp += row_sum(p.scB_lse, j0, p.S);
       lp1 += row_sum(p.scB_last, j0, p.S);
-      new_idx = n_cand;
       c_lp[n_cand] = lp;
       c_lp1[n_cand] = lp1;
-      ++n_cand;
     }
-    // log_q = log_p - LSE(log_p); q = exp(log_q) / sum   (semi_adapted.py:151-163, utils/math.py:102-121)
-    double mx = -INFINITY;
-    for (int c = 0; c < n_cand; ++c) mx = fmax(mx, c_lp[c]);
-    if (!(mx > -INFINITY) || !(mx < INFINITY)) atomicOr(p.status, ST_NUMERIC);
-    double tot = 0.0;
-    for (int c = 0; c < n_cand; ++c) tot += exp(c_lp[c] - mx);
-    const double lse = log(tot) + mx;
-    double qs = 0.0;
-    for (int c = 0; c < n_cand; ++c) {
-      q[c] = exp(c_lp[c] - lse);
-      qs += q[c];
-    }
-    for (int c = 0; c < n_cand; ++c) q[c] /= qs;
+    ++n_cand;
+  }
+  __syncwarp();
+  // log_q = log_p - LSE(log_p); q = exp(log_q) / sum   (semi_adapted.py:151-163, utils/math.py:102-121); sums run
+  // left to right as in the reference's scalar loop
+  double mx = -INFINITY;
+  for (int c = 0; c < n_cand; ++c) mx = fmax(mx, c_lp[c]);
+  if (!(mx > -INFINITY) || !(mx < INFINITY)) {
+    if (lane == 0) atomicOr(p.status, ST_NUMERIC);
+  }
+  for (int c = lane; c < n_cand; c += 32) q[c] = exp(c_lp[c] - mx);
+  __syncwarp();
+  double tot = 0.0;
+  for (int c = 0; c < n_cand; ++c) tot += q[c];
+  const double lse = log(tot) + mx;
+  __syncwarp();
+  for (int c = lane; c < n_cand; c += 32) q[c] = exp(c_lp[c] - lse);
+  __syncwarp();
+  double qs = 0.0;
+  for (int c = 0; c < n_cand; ++c) qs += q[c];
+  __syncwarp();
+  for (int c = lane; c < n_cand; c += 32) q[c] /= qs;
+  __syncwarp();
 
-    // ---- the particle's draws (semi_adapted.py:63-83, 165-194; conventions of oracle/uniform.py)
-    int kind, pick = -1, k_new = 0;
-    u64 taken_base = 0;  // NEW: chosen positions in BASE order (= the parent's tree_roots the reference draws from)
-    double logq;
-    bool known;  // log_p of the new particle is one of the candidates'
-    if (R == 0) {
-      pick = inv_cdf(q, n_cand, u01(p.seed, t, i, 0));
-      kind = (pick == out_idx) ? K_OUTLIER : K_NEW;
-      logq = c_lp[pick] - lse;
-      known = true;
-    } else if (u01(p.seed, t, i, 0) < 0.5) {
-      pick = inv_cdf(q, n_cand, u01(p.seed, t, i, 1));
-      kind = (pick == out_idx) ? K_OUTLIER : K_ATTACH;
-      logq = p.log_half + (c_lp[pick] - lse);
-      known = true;
-    } else {
-      kind = K_NEW;
-      known = false;
-      k_new = min(R, (int)(u01(p.seed, t, i, 1) * (double)(R + 1)));
-      unsigned char pos[kMaxRoots];
-      for (int r = 0; r < R; ++r) pos[r] = (unsigned char)r;
-      for (int m = 0; m < k_new; ++m) {
-        const int rest = R - m;
-        const int j = m + min(rest - 1, (int)(u01(p.seed, t, i, 2 + m) * (double)rest));
-        const unsigned char tmp = pos[m];
-        pos[m] = pos[j];
-        pos[j] = tmp;
-        taken_base |= 1ull << pos[m];
-      }
-      const double lbin = tab(p.lfact, R, p.n_tab, true) - tab(p.lfact, k_new, p.n_tab, true) -
-                          tab(p.lfact, R - k_new, p.n_tab, true);
-      logq = p.log_half - (tab(p.logn, R + 1, p.n_tab, false) + lbin);
+  // ---- the particle's draws (semi_adapted.py:63-83, 165-194; conventions of oracle/uniform.py)
+  int kind, pick = -1, k_new = 0;
+  u64 taken_base = 0;  // NEW: chosen positions in BASE order (= the parent's tree_roots the reference draws from)
+  double logq;
+  if (R == 0) {
+    pick = inv_cdf(q, n_cand, u01(p.seed, t, i, 0));
+    kind = (pick == out_idx) ? K_OUTLIER : K_NEW;
+    logq = c_lp[pick] - lse;
+  } else if (u01(p.seed, t, i, 0) < 0.5) {
+    pick = inv_cdf(q, n_cand, u01(p.seed, t, i, 1));
+    kind = (pick == out_idx) ? K_OUTLIER : K_ATTACH;
+    logq = p.log_half + (c_lp[pick] - lse);
+  } else {
+    kind = K_NEW;
+    k_new = min(R, (int)(u01(p.seed, t, i, 1) * (double)(R + 1)));
+    unsigned char pos[kMaxRoots];
+    for (int r = 0; r < R; ++r) pos[r] = (unsigned char)r;
+    for (int m = 0; m < k_new; ++m) {
+      const int rest = R - m;
+      const int j = m + min(rest - 1, (int)(u01(p.seed, t, i, 2 + m) * (double)rest));
+      const unsigned char tmp = pos[m];
+      pos[m] = pos[j];
+      pos[j] = tmp;
+      taken_base |= 1ull << pos[m];
     }
+    const double lbin =
+        tab(p.lfact, R, p.n_tab, true) - tab(p.lfact, k_new, p.n_tab, true) - tab(p.lfact, R - k_new, p.n_tab, true);
+    logq = p.log_half - (tab(p.logn, R + 1, p.n_tab, false) + lbin);
+  }
 
-    // ---- successor state = extend(thawed parent, edit)   (pcb_hostmod.cpp fstate_extend)
-    const int* s_nm = fld(v.pI, F_NAME, Rmax);
-    const int* s_lr = fld(v.pI, F_LR, Rmax);
-    const int* s_lp = fld(v.pI, F_LP, Rmax);
-    const int* s_nd = fld(v.pI, F_NDATA, Rmax);
-    const int* s_sz = fld(v.pI, F_SIZE, Rmax);
-    const int* s_sl = fld(v.pI, F_SLOT, Rmax);
-    const int* s_gi = fld(v.pI, F_GIDX, Rmax);
-    const int* s_ko = fld(v.pI, F_KOFF, Rmax);
-    const int* s_kc = fld(v.pI, F_KCNT, Rmax);
-    const int pn = v.pI[1], ps = v.pI[2], pe = v.pI[3], po = v.pI[4];
-    const double s_crp = v.pD[D_CRP], s_mult = v.pD[D_MULT], s_opr = v.pD[D_OPRIOR], s_om = v.pD[D_OMARG];
-    const u64 s_key = v.ret ? p.ret_key[t - 1] : p.cur_key[i];
-    int* eI = p.ext_int + (size_t)i * p.irec;
-    double* eD = p.ext_dbl + (size_t)i * DREC;
-    int* e_nm = fld(eI, F_NAME, Rmax);
-    int* e_lr = fld(eI, F_LR, Rmax);
-    int* e_lp = fld(eI, F_LP, Rmax);
-    int* e_nd = fld(eI, F_NDATA, Rmax);
-    int* e_sz = fld(eI, F_SIZE, Rmax);
-    int* e_sl = fld(eI, F_SLOT, Rmax);
-    int* e_gi = fld(eI, F_GIDX, Rmax);
-    int* e_ko = fld(eI, F_KOFF, Rmax);
-    int* e_kc = fld(eI, F_KCNT, Rmax);
-    double lp_new = 0.0, lp1_new = 0.0;
-    int name_out = -1, slot_e = -1;
-    u64 mask_out = 0;
-    if (kind != K_NEW || R == 0) {
-      lp_new = c_lp[pick];
-      lp1_new = c_lp1[pick];
+  // ---- successor state = extend(thawed parent, edit)   (pcb_hostmod.cpp fstate_extend)
+  const int* s_nm = fld(v.pI, F_NAME, Rmax);
+  const int* s_lr = fld(v.pI, F_LR, Rmax);
+  const int* s_lp = fld(v.pI, F_LP, Rmax);
+  const int* s_nd = fld(v.pI, F_NDATA, Rmax);
+  const int* s_sz = fld(v.pI, F_SIZE, Rmax);
+  const int* s_sl = fld(v.pI, F_SLOT, Rmax);
+  const int* s_gi = fld(v.pI, F_GIDX, Rmax);
+  const int* s_ko = fld(v.pI, F_KOFF, Rmax);
+  const int* s_kc = fld(v.pI, F_KCNT, Rmax);
+  const int pn = v.pI[1], ps = v.pI[2], pe = v.pI[3], po = v.pI[4];
+  const double s_crp = v.pD[D_CRP], s_mult = v.pD[D_MULT], s_opr = v.pD[D_OPRIOR], s_om = v.pD[D_OMARG];
+  const u64 s_key = v.ret ? p.ret_key[t - 1] : p.cur_key[i];
+  int* eI = p.ext_int + (size_t)i * p.irec;
+  double* eD = p.ext_dbl + (size_t)i * DREC;
+  int* e_nm = fld(eI, F_NAME, Rmax);
+  int* e_lr = fld(eI, F_LR, Rmax);
+  int* e_lp = fld(eI, F_LP, Rmax);
+  int* e_nd = fld(eI, F_NDATA, Rmax);
+  int* e_sz = fld(eI, F_SIZE, Rmax);
+  int* e_sl = fld(eI, F_SLOT, Rmax);
+  int* e_gi = fld(eI, F_GIDX, Rmax);
+  int* e_ko = fld(eI, F_KOFF, Rmax);
+  int* e_kc = fld(eI, F_KCNT, Rmax);
+  double lp_new = 0.0, lp1_new = 0.0;
+  int name_out = -1, slot_e = -1;
+  u64 mask_out = 0;
+  if (kind != K_NEW || R == 0) {
+    lp_new = c_lp[pick];
+    lp1_new = c_lp1[pick];
+  }
+  if (kind == K_OUTLIER || kind == K_ATTACH) {
+    for (int r = lane; r < R; r += 32) {
+      e_nm[r] = s_nm[r];
+      e_lr[r] = s_lr[r];
+      e_lp[r] = s_lp[r];
+      e_nd[r] = s_nd[r];
+      e_sz[r] = s_sz[r];
+      e_sl[r] = s_sl[r];
+      e_gi[r] = s_gi[r];
+      e_ko[r] = s_ko[r];
+      e_kc[r] = s_kc[r];
     }
-    if (kind == K_OUTLIER || kind == K_ATTACH) {
-      for (int r = 0; r < R; ++r) {
-        e_nm[r] = s_nm[r];
-        e_lr[r] = s_lr[r];
-        e_lp[r] = s_lp[r];
-        e_nd[r] = s_nd[r];
-        e_sz[r] = s_sz[r];
-        e_sl[r] = s_sl[r];
-        e_gi[r] = s_gi[r];
-        e_ko[r] = s_ko[r];
-        e_kc[r] = s_kc[r];
-      }
+    __syncwarp();
+  }
+  if (kind == K_OUTLIER) {
+    if (lane == 0) {
       eI[0] = R;
       eI[1] = pn;
       eI[2] = ps;
       eI[3] = pe;
-      eD[D_MULT] = s_mult;
-    }
-    if (kind == K_OUTLIER) {
       eI[4] = po + 1;
+      eD[D_MULT] = s_mult;
       eD[D_CRP] = s_crp;
       eD[D_OMARG] = s_om + marg;
       eD[D_OPRIOR] = (op != 0.0) ? s_opr + op : s_opr;
       p.ext_key[i] = s_key ^ data_hash(-1, po, dpidx);
-    } else if (kind == K_ATTACH) {
-      const int name = b_nm[pick];
-      int j = 0;
-      while (j < R && s_nm[j] != name) ++j;
-      if (j >= R) {
-        atomicOr(p.status, ST_NUMERIC);
-        j = 0;
-      }
-      const int n = s_nd[j];
-      const bool leaf = s_kc[j] == 0;
-      const int t1 = alloc_tiles(p, leaf ? 1 : 2);
+    }
+  } else if (kind == K_ATTACH) {
+    const int name = b_nm[pick];
+    int j = 0;
+    while (j < R && s_nm[j] != name) ++j;
+    if (j >= R) {
+      if (lane == 0) atomicOr(p.status, ST_NUMERIC);
+      j = 0;
+    }
+    const int n = s_nd[j];
+    const int kc = s_kc[j];
+    const bool leaf = kc == 0;
+    int t1 = 0, je = 0;
+    if (lane == 0) {
+      t1 = alloc_tiles(p, leaf ? 1 : 2);
+      je = atomicAdd(p.nE, leaf ? 1 : 2);
+    }
+    t1 = __shfl_sync(0xffffffffu, t1, 0);
+    je = __shfl_sync(0xffffffffu, je, 0);
+    if (!leaf) {
+      // log_r = log_p + log_S(children) re-derived as Tree.from_dict does (tree/tree_node.py:61-71), with
+      // log_p = old log_p + value formed on the fly (base + base2)
+      int* kids = p.kidsE + (size_t)(je + 1) * Rmax;
+      for (int c = lane; c < kc; c += 32) kids[c] = p.kid_pool[s_ko[j] + c];
+    }
+    if (lane == 0) {
       // log_p += value (tree/tree_node.py:42-46): copy of the old log_p tile plus the value tile
-      const int jd = atomicAdd(p.nD, leaf ? 1 : 2);
-      p.kidsD[(size_t)jd * Rmax] = s_lp[j];
-      put_job(p.jobsD, jd, jd * Rmax, 1, vid, t1, 0, -1, -1);
+      p.kidsE[(size_t)je * Rmax] = s_lp[j];
+      put_job(p.jobsE, je, je * Rmax, 1, vid, t1, 0, -1, -1);
       e_lp[j] = t1;
       if (leaf) {
         e_lr[j] = t1;
       } else {
-        // log_r = log_p + log_S(children) re-derived as Tree.from_dict does (tree/tree_node.py:61-71), with
-        // log_p = old log_p + value formed on the fly (base + base2)
-        int* kids = p.kidsD + (size_t)(jd + 1) * Rmax;
-        for (int c = 0; c < s_kc[j]; ++c) kids[c] = p.kid_pool[s_ko[j] + c];
-        put_job(p.jobsD, jd + 1, (jd + 1) * Rmax, s_kc[j], s_lp[j], t1 + 1, JOB_SCAN, -1, vid);
+        put_job(p.jobsE, je + 1, (je + 1) * Rmax, kc, s_lp[j], t1 + 1, JOB_SCAN, -1, vid);
         e_lr[j] = t1 + 1;
-        if (s_kc[j] > 1) atomicAdd(p.pairs, (u64)(s_kc[j] - 1));
+        if (kc > 1) atomicAdd(p.pairs, (u64)(kc - 1));
       }
       e_nd[j] = n + 1;
+      eI[0] = R;
+      eI[1] = pn;
+      eI[2] = ps;
+      eI[3] = pe;
       eI[4] = po;
+      eD[D_MULT] = s_mult;
       eD[D_CRP] = s_crp + (n >= 1 ? tab(p.lfact, n, p.n_tab, true) - tab(p.lfact, n - 1, p.n_tab, true) : 0.0);
       eD[D_OMARG] = s_om;
       eD[D_OPRIOR] = (op != 0.0) ? s_opr + opn : s_opr;
       p.ext_key[i] = s_key ^ data_hash(name, n, dpidx);
-      name_out = name;
+    }
+    name_out = name;
+  } else {
+    // positions taken in the THAWED parent's root order; the new node folds its children in that order
+    u64 take = 0;
+    for (int r = 0; r < R; ++r)
+      if (taken_base >> r & 1ull) {
+        const int name = b_nm[r];
+        int j = 0;
+        while (j < R && s_nm[j] != name) ++j;
+        if (j < R) take |= 1ull << j;
+      }
+    const int k = k_new;
+    const int Rn = R - k + 1;
+    if (Rn > Rmax) {
+      if (lane == 0) atomicOr(p.status, ST_ROOTS);
     } else {
-      // positions taken in the THAWED parent's root order; the new node folds its children in that order
-      u64 take = 0;
-      for (int r = 0; r < R; ++r)
-        if (taken_base >> r & 1ull) {
-          const int name = b_nm[r];
-          int j = 0;
-          while (j < R && s_nm[j] != name) ++j;
-          if (j < R) take |= 1ull << j;
-        }
-      const int k = k_new;
-      const int Rn = R - k + 1;
-      if (Rn > Rmax) {
-        atomicOr(p.status, ST_ROOTS);
-      } else {
-        int lr_new = sid, koff = 0;
+      int lr_new = sid, koff = 0, jd = 0;
+      const bool score = R > 0;  // an empty parent's lone candidate already is this tree
+      if (lane == 0) {
         if (k > 0) {
           lr_new = alloc_tiles(p, 1);
           koff = atomicAdd(p.pool_top, k);
-          const int jd = atomicAdd(p.nD, 1);
-          int* kids = p.kidsD + (size_t)jd * Rmax;
-          int c = 0;
-          const bool pool_ok = koff + k <= p.pool_cap;
-          if (!pool_ok) atomicOr(p.status, ST_POOL);
-          for (int r = 0; r < R; ++r)
-            if (take >> r & 1ull) {
-              kids[c] = s_lr[r];
-              if (pool_ok) p.kid_pool[koff + c] = s_lr[r];
-              ++c;
-            }
-          put_job(p.jobsD, jd, jd * Rmax, k, sid, lr_new, JOB_SCAN, -1, -1);
+          jd = atomicAdd(p.nD, 1);
+          if (koff + k > p.pool_cap) atomicOr(p.status, ST_POOL);
           if (k > 1) atomicAdd(p.pairs, (u64)(k - 1));
         }
-        int sz = 1;
-        u64 key = s_key ^ edge_hash(pe, 0, ps) ^ data_hash(pn, 0, dpidx);
-        for (int r = 0; r < R; ++r)
-          if (take >> r & 1ull) {
-            sz += s_sz[r];
-            key ^= edge_hash(s_sl[r], 0, s_gi[r]) ^ edge_hash(s_sl[r], ps, s_gi[r]);
+        if (score) {
+          slot_e = atomicAdd(p.nE, 1);
+          if (Rn > 1) atomicAdd(p.pairs, (u64)(Rn - 1));
+        }
+      }
+      lr_new = __shfl_sync(0xffffffffu, lr_new, 0);
+      koff = __shfl_sync(0xffffffffu, koff, 0);
+      jd = __shfl_sync(0xffffffffu, jd, 0);
+      slot_e = __shfl_sync(0xffffffffu, slot_e, 0);
+      const bool pool_ok = koff + k <= p.pool_cap;
+      int* kidsD = p.kidsD + (size_t)jd * Rmax;
+      int* kidsE = score ? p.kidsE + (size_t)slot_e * Rmax : nullptr;
+      int sz = 1;
+      u64 key = s_key ^ edge_hash(pe, 0, ps) ^ data_hash(pn, 0, dpidx);
+      double ways_keep = 0.0;
+      for (int r = 0; r < R; ++r) {
+        if (take >> r & 1ull) {
+          sz += s_sz[r];
+          key ^= edge_hash(s_sl[r], 0, s_gi[r]) ^ edge_hash(s_sl[r], ps, s_gi[r]);
+        }
+      }
+      (void)ways_keep;
+      for (int r = lane; r < R; r += 32) {
+        const u64 below = (r == 0) ? 0ull : (take & ((1ull << r) - 1ull));
+        if (take >> r & 1ull) {
+          const int c = __popcll(below);
+          if (k > 0) {
+            kidsD[c] = s_lr[r];
+            if (pool_ok) p.kid_pool[koff + c] = s_lr[r];
           }
+        } else {
+          const int w = 1 + r - __popcll(below);
+          e_nm[w] = s_nm[r];
+          e_lr[w] = s_lr[r];
+          e_lp[w] = s_lp[r];
+          e_nd[w] = s_nd[r];
+          e_sz[w] = s_sz[r];
+          e_sl[w] = s_sl[r];
+          e_gi[w] = s_gi[r];
+          e_ko[w] = s_ko[r];
+          e_kc[w] = s_kc[r];
+          if (kidsE) kidsE[w] = s_lr[r];
+        }
+      }
+      const double mult = s_mult - tab(p.lfact, R, p.n_tab, true) + tab(p.lfact, R - k + 1, p.n_tab, true) +
+                          tab(p.lfact, k, p.n_tab, true);
+      const double opr = (op != 0.0) ? s_opr + opn : s_opr;
+      if (score) {
+        // priors of the new tree from its roots in order: the new node first, then the roots it left alone
+        const double base = (double)(pn + 1) * p.log_alpha + s_crp;
+        double lp = base - (double)pn * tab(p.logn, pn + 2, p.n_tab, false) - mult;
+        double ways = (double)(sz - 1) * tab(p.logn, sz, p.n_tab, false);
+        for (int r = 0; r < R; ++r)
+          if (!(take >> r & 1ull)) ways += (double)(s_sz[r] - 1) * tab(p.logn, s_sz[r], p.n_tab, false);
+        double lp1 = base + (-ways + p.rterm[Rn]) - mult;
+        const double extra = opr + s_om;
+        lp_new = lp + extra;
+        lp1_new = lp1 + extra;
+      }
+      if (lane == 0) {
+        if (k > 0) put_job(p.jobsD, jd, jd * Rmax, k, sid, lr_new, JOB_SCAN, -1, -1);
         e_nm[0] = pn;
         e_lr[0] = lr_new;
         e_lp[0] = sid;
@@ -529,48 +601,26 @@ __global__ void decide_kernel(const Params p, const int t) {
         e_gi[0] = ps;
         e_ko[0] = koff;
         e_kc[0] = k;
-        sizes[0] = sz;
-        int w = 1;
-        for (int r = 0; r < R; ++r)
-          if (!(take >> r & 1ull)) {
-            e_nm[w] = s_nm[r];
-            e_lr[w] = s_lr[r];
-            e_lp[w] = s_lp[r];
-            e_nd[w] = s_nd[r];
-            e_sz[w] = s_sz[r];
-            e_sl[w] = s_sl[r];
-            e_gi[w] = s_gi[r];
-            e_ko[w] = s_ko[r];
-            e_kc[w] = s_kc[r];
-            sizes[w] = s_sz[r];
-            ++w;
-          }
         eI[0] = Rn;
         eI[1] = pn + 1;
         eI[2] = ps + 1;
         eI[3] = pe + 1;
         eI[4] = po;
-        const double mult = s_mult - tab(p.lfact, R, p.n_tab, true) + tab(p.lfact, R - k + 1, p.n_tab, true) +
-                            tab(p.lfact, k, p.n_tab, true);
-        const double opr = (op != 0.0) ? s_opr + opn : s_opr;
         eD[D_MULT] = mult;
         eD[D_CRP] = s_crp;
         eD[D_OMARG] = s_om;
         eD[D_OPRIOR] = opr;
         p.ext_key[i] = key;
-        if (R > 0) {  // the new tree is scored from its roots (score_new); an empty parent's lone candidate was
-          priors(p, pn + 1, s_crp, mult, sizes, Rn, opr, s_om, lp_new, lp1_new);
-          slot_e = atomicAdd(p.nE, 1);
-          int* kids = p.kidsE + (size_t)slot_e * Rmax;
-          for (int c = 0; c < Rn; ++c) kids[c] = e_lr[c];
+        if (score) {
+          kidsE[0] = lr_new;
           put_job(p.jobsE, slot_e, slot_e * Rmax, Rn, -1, -1, JOB_SCAN | JOB_ADD_PRIOR, slot_e, -1);
-          if (Rn > 1) atomicAdd(p.pairs, (u64)(Rn - 1));
         }
       }
-      name_out = pn;
-      mask_out = take;
     }
-    (void)known;
+    name_out = pn;
+    mask_out = take;
+  }
+  if (lane == 0) {
     p.slotE[i] = slot_e;
     p.dec_kind[i] = kind | (v.ret ? FLAG_RETAINED_PARENT : 0);
     p.dec_name[i] = name_out;
@@ -612,7 +662,6 @@ __global__ void weigh_kernel(const Params p, const int t, const double log_unifo
   __shared__ double sh_w[1024];
   __shared__ int sh_cnt[1024];
   __shared__ int sh_anc[1024];
-  __shared__ int sh_flag;
   const int first = p.conditional ? 1 : 0;
   const int N = p.N, i = threadIdx.x;
   const bool last = t >= p.T - 1;
@@ -677,7 +726,11 @@ __global__ void weigh_kernel(const Params p, const int t, const double log_unifo
   if (threadIdx.x == 0) {
     p.o_ess[t] = ess;
     p.o_resampled[t] = resample ? 1 : 0;
-    sh_flag = 0;
+    // the job counters of the next step's build / decide kernels
+    *p.nB = 0;
+    *p.nAdd = 0;
+    *p.nD = 0;
+    *p.nE = 0;
   }
   if (last) {
     // final pick: p = W / sum(W) once more (utils/math.py:19-21 via particle_gibbs.py:42-48)
@@ -743,21 +796,19 @@ __global__ void weigh_kernel(const Params p, const int t, const double log_unifo
     p.o_anc[(size_t)t * N + i] = sh_anc[i];
     p.lw[i] = resample ? lw_uniform : log_W;
   }
-  // ---- next step's parents: cur[s] = ext[anc[s]]
+  // ---- next step's parents: cur[s] = ext[anc[s]], all slots at once (the unused tail of a field is copied too)
   if (!last) {
-    for (int s = 0; s < N; ++s) {
-      const int a = sh_anc[s];
-      const int* src = p.ext_int + (size_t)a * p.irec;
-      int* dst = p.cur_int + (size_t)s * p.irec;
-      const int R = src[0];
-      // only the live part of each field is copied
-      for (int k = threadIdx.x; k < IHEAD + F_COUNT * p.Rmax; k += blockDim.x) {
-        const int f = (k < IHEAD) ? -1 : (k - IHEAD) % p.Rmax;
-        if (f < R) dst[k] = src[k];
-      }
-      if (threadIdx.x < DREC) p.cur_dbl[(size_t)s * DREC + threadIdx.x] = p.ext_dbl[(size_t)a * DREC + threadIdx.x];
-      if (threadIdx.x == 0) p.cur_key[s] = p.ext_key[a];
+    const int irec = p.irec;
+    const int total = N * irec;
+    for (int k = threadIdx.x; k < total; k += blockDim.x) {
+      const int s = k / irec, f = k - s * irec;
+      p.cur_int[k] = p.ext_int[(size_t)sh_anc[s] * irec + f];
     }
+    for (int k = threadIdx.x; k < N * DREC; k += blockDim.x) {
+      const int s = k / DREC, f = k - s * DREC;
+      p.cur_dbl[k] = p.ext_dbl[(size_t)sh_anc[s] * DREC + f];
+    }
+    if (i < N) p.cur_key[i] = p.ext_key[sh_anc[i]];
   }
 }
 
@@ -772,6 +823,12 @@ __global__ void init_kernel(const Params p, const double lw0) {
     for (int k = 0; k < DREC; ++k) p.cur_dbl[(size_t)i * DREC + k] = 0.0;
     p.cur_key[i] = 0;
     p.lw[i] = lw0;
+  }
+  if (threadIdx.x == 0) {
+    *p.nB = 0;
+    *p.nAdd = 0;
+    *p.nD = 0;
+    *p.nE = 0;
   }
 }
 

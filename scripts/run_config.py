@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--depth", type=int, default=200)
     ap.add_argument("--outlier-prob", type=float, default=0.0)
     ap.add_argument("--profile", action="store_true")
+    ap.add_argument("--sweep", default="host", choices=["host", "device"])
     args = ap.parse_args()
     import torch
 
@@ -52,7 +53,8 @@ def main():
 
     def go():
         return run_phyclone_chain(args.burnin, True, 1.0, data, float("inf"), args.iters, args.particles, 1, 1,
-                                  args.outlier_prob, 10**9, "semi-adapted", 0.5, rng, ["s"], 1, 0, 0.0, on_iteration=on_it)
+                                  args.outlier_prob, 10**9, "semi-adapted", 0.5, rng, ["s"], 1, 0, 0.0, on_iteration=on_it,
+                                  sweep=args.sweep)
 
     t0 = time.time()
     if args.profile:
