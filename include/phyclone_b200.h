@@ -225,12 +225,14 @@ int pcb_resample_host(const double* W, int64_t N, const double* uniforms, int64_
  * standard.py:20-45) and the final pick (mcmc/particle_gibbs.py:42-48).
  * Draws are inverse-CDF transforms of uniforms u(seed, step, slot, draw number) (splitmix64 counter hash); the CPU
  * definition of this mode is oracle/uniform.py.  A particle is the root level of its forest; record layouts:
- *   int record  [5 + 9*Rmax]: R, n_nodes, n_slots, n_edges, n_outliers, then Rmax-strided fields
- *                name, log_r tile, log_p tile, n_data, subtree size, edge slot, graph index, kid offset, kid count
+ *   int record  [5 + 9*Rmax, padded to a multiple of 4]: R, n_nodes, n_slots, n_edges, n_outliers, then Rmax-strided
+ *                fields name, log_r tile, log_p tile, n_data, subtree size, edge slot, graph index, kid offset, kid count
  *   dbl record  [8]: crp sum, multiplicity, outlier prior, outlier marginal, log_p, log_p_one, log_w increment, 0
  * Conditional sweeps take the retained path as T such records per view: `ret_th_*` = the retained particle after
  * step t re-read through Tree.from_dict (what extends it), `ret_ba_*` = the same tree as built (what its proposal's
- * candidates are scored on), `ret_key` = its structure hash, `ret_kids` = the child tile lists its kid offsets index.
+ * candidates are scored on), `ret_key` = its structure hash, `ret_kids` = the child tile lists its kid offsets index,
+ * `ret_kind` / `ret_arg` = the edit that made it (0 attach: node name, 1 new root: number of adopted roots, 2 outlier);
+ * of the dbl record only log_p / log_p_one are read for it (its proposal log-probability is computed on the device).
  * Tiles: [tile_base, tile_base + N*Rmax) is per-step candidate scratch, the rest up to tile_limit is handed out to new
  * root / node tiles.  Small control tables are HOST pointers (copied inside); outputs are HOST buffers filled after the
  * one stream synchronisation at the end.  status: 0 ok, else bit 1 = more than Rmax roots, 2 = tile range exhausted,
@@ -243,10 +245,11 @@ typedef struct {
   const int32_t *dp_idx, *value_id, *single_id; /* [T] */
   const double *dp_op, *dp_opn, *dp_marg;        /* [T] outlier log prob, not-outlier log prob, outlier marginal */
   const double *lfact, *logn, *rterm;            /* [n_tab] log n!, log n, FS-CRP root-count term */
-  const int32_t *ret_th_int, *ret_ba_int;        /* [T][5 + 9*Rmax] */
+  const int32_t *ret_th_int, *ret_ba_int;        /* [T][(5 + 9*Rmax + 3) & ~3] */
   const double *ret_th_dbl, *ret_ba_dbl;         /* [T][8] */
   const uint64_t* ret_key;                       /* [T] */
   const int32_t* ret_kids;                       /* [n_ret_kids] */
+  const int32_t *ret_kind, *ret_arg;             /* [T] */
   int32_t *anc, *kind, *name;                    /* [T][N] ancestor of slot i after step t; decision of particle i */
   uint64_t* mask;                                /* [T][N] adopted roots of a new node (positions in the parent) */
   double *raw, *logp, *logq;                     /* [T][N] unnormalised log weight, log_p, proposal log prob */

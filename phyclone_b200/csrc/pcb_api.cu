@@ -938,7 +938,8 @@ int pcb_smc_sweep_dev(const pcb_arena* a, const pcb_sweep_desc* d, void* stream)
   const int N = d->N, T = d->T, Rmax = d->Rmax, S = a->layout.S;
   if (N < 1 || N > 1024 || T < 1 || Rmax < 1 || Rmax > sw::kMaxRoots)
     return fail(PCB_ERR_ARG, "smc_sweep: need 1 <= N <= 1024, T >= 1, 1 <= Rmax <= 64");
-  if (d->conditional && (N < 2 || !d->ret_th_int || !d->ret_ba_int || !d->ret_th_dbl || !d->ret_ba_dbl || !d->ret_key))
+  if (d->conditional && (N < 2 || !d->ret_th_int || !d->ret_ba_int || !d->ret_th_dbl || !d->ret_ba_dbl || !d->ret_key ||
+                         !d->ret_kind || !d->ret_arg))
     return fail(PCB_ERR_ARG, "smc_sweep: conditional sweep without a retained path (or N < 2)");
   if (!d->dp_idx || !d->value_id || !d->single_id || !d->dp_op || !d->dp_opn || !d->dp_marg || !d->lfact || !d->logn ||
       !d->rterm || d->n_tab < Rmax + 2)
@@ -953,7 +954,7 @@ int pcb_smc_sweep_dev(const pcb_arena* a, const pcb_sweep_desc* d, void* stream)
     if (d->value_id[t] < 0 || d->value_id[t] >= a->capacity || d->single_id[t] < 0 || d->single_id[t] >= a->capacity)
       return fail(PCB_ERR_ARG, "smc_sweep: data tile id outside the arena");
   cudaStream_t st = (cudaStream_t)stream;
-  const int irec = sw::IHEAD + sw::F_COUNT * Rmax;
+  const int irec = (sw::IHEAD + sw::F_COUNT * Rmax + 3) & ~3;  // padded to 16 bytes: records move as int4
   const int n_ret_kids = d->conditional ? d->n_ret_kids : 0;
   const long long maxB = (long long)N * (Rmax + 1);
   const int pool_cap = n_ret_kids + N * T * std::min(Rmax, 16) + 64;
@@ -970,6 +971,8 @@ int pcb_smc_sweep_dev(const pcb_arena* a, const pcb_sweep_desc* d, void* stream)
     P.single_id = ci.take<int>(T);
     P.ret_th_int = ci.take<int>(d->conditional ? (size_t)T * irec : 0);
     P.ret_ba_int = ci.take<int>(d->conditional ? (size_t)T * irec : 0);
+    P.ret_kind = ci.take<int>(d->conditional ? T : 0);
+    P.ret_arg = ci.take<int>(d->conditional ? T : 0);
     P.kid_pool = ci.take<int>(pool_cap);
     P.cur_int = ci.take<int>((size_t)N * irec);
     P.ext_int = ci.take<int>((size_t)N * irec);
@@ -1074,6 +1077,8 @@ int pcb_smc_sweep_dev(const pcb_arena* a, const pcb_sweep_desc* d, void* stream)
     PCB_CUDA(up(P.ret_th_dbl, d->ret_th_dbl, (size_t)T * sw::DREC * 8));
     PCB_CUDA(up(P.ret_ba_dbl, d->ret_ba_dbl, (size_t)T * sw::DREC * 8));
     PCB_CUDA(up(P.ret_key, d->ret_key, (size_t)T * 8));
+    PCB_CUDA(up(P.ret_kind, d->ret_kind, (size_t)T * 4));
+    PCB_CUDA(up(P.ret_arg, d->ret_arg, (size_t)T * 4));
     if (n_ret_kids) PCB_CUDA(up(P.kid_pool, d->ret_kids, (size_t)n_ret_kids * 4));
   }
   const int counters[8] = {0, 0, 0, 0, n_ret_kids, (int)(d->tile_base + scratch), 0, -1};
@@ -1090,9 +1095,8 @@ int pcb_smc_sweep_dev(const pcb_arena* a, const pcb_sweep_desc* d, void* stream)
   sw::init_kernel<<<1, threads1, 0, st>>>(P, d->lw_uniform);
   PCB_LAUNCH_CHECK();
   int64_t launches = 1;
-  const int first = d->conditional ? 1 : 0;
-  const unsigned grid_build = (unsigned)((N - first + sw::kBuildWarps - 1) / sw::kBuildWarps);
-  const unsigned grid_decide = (unsigned)((N - first + sw::kDecideWarps - 1) / sw::kDecideWarps);
+  const unsigned grid_build = (unsigned)((N + sw::kBuildWarps - 1) / sw::kBuildWarps);
+  const unsigned grid_decide = (unsigned)((N + sw::kDecideWarps - 1) / sw::kDecideWarps);
   for (int t = 0; t < T; ++t) {
     sw::build_kernel<<<grid_build, 32 * sw::kBuildWarps, 0, st>>>(P, t);
     PCB_LAUNCH_CHECK();

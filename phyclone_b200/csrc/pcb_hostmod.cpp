@@ -963,6 +963,82 @@ PyObject* FState_export(FState* self, PyObject*) {
                        self->omarg, (unsigned long long)self->skey);
 }
 
+// pack_states(thawed states, as-built states, rmax) -> (th_int, ba_int, th_dbl, ba_dbl, kids) as bytes:
+//   the record layout of pcb_sweep_desc (include/phyclone_b200.h): int record [5 + 9*rmax padded to 4] = R, n_nodes,
+//   n_slots, n_edges, n_out, then rmax-strided name, lr, lp, ndata, size, slot, gidx, kid offset, kid count; double
+//   record [8] = crp, mult, oprior, omarg, 0...; kids = the child tile lists the kid offsets index.
+PyObject* mod_pack_states(PyObject*, PyObject* args) {
+  PyObject *th_o, *ba_o;
+  int rmax;
+  if (!PyArg_ParseTuple(args, "OOi", &th_o, &ba_o, &rmax)) return nullptr;
+  PyObject* lists[2] = {PySequence_Fast(th_o, "expected a sequence of states"), nullptr};
+  if (!lists[0]) return nullptr;
+  lists[1] = PySequence_Fast(ba_o, "expected a sequence of states");
+  if (!lists[1]) {
+    Py_DECREF(lists[0]);
+    return nullptr;
+  }
+  const Py_ssize_t T = PySequence_Fast_GET_SIZE(lists[0]);
+  const int irec = (5 + 9 * rmax + 3) & ~3;
+  std::vector<int32_t> ints[2];
+  std::vector<double> dbls[2];
+  std::vector<int32_t> kids;
+  bool ok = PySequence_Fast_GET_SIZE(lists[1]) == T;
+  if (!ok) PyErr_SetString(PyExc_ValueError, "pack_states: the two lists differ in length");
+  for (int w = 0; ok && w < 2; ++w) {
+    ints[w].assign((size_t)T * irec, 0);
+    dbls[w].assign((size_t)T * 8, 0.0);
+  }
+  for (Py_ssize_t t = 0; ok && t < T; ++t) {
+    for (int w = 0; w < 2 && ok; ++w) {
+      PyObject* o = PySequence_Fast_GET_ITEM(lists[w], t);
+      if (!PyObject_TypeCheck(o, &FStateType)) {
+        PyErr_SetString(PyExc_TypeError, "pack_states: not a ForestState");
+        ok = false;
+        break;
+      }
+      FState* s = (FState*)o;
+      const int R = (int)s->roots->size();
+      if (R > rmax) {
+        PyErr_SetString(PyExc_OverflowError, "pack_states: forest with more roots than rmax");
+        ok = false;
+        break;
+      }
+      int32_t* rec = ints[w].data() + (size_t)t * irec;
+      rec[0] = R;
+      rec[1] = (int32_t)s->n_nodes;
+      rec[2] = (int32_t)s->n_slots;
+      rec[3] = (int32_t)s->n_edges;
+      rec[4] = (int32_t)s->n_out;
+      int32_t* body = rec + 5;
+      for (int r = 0; r < R; ++r) {
+        body[0 * rmax + r] = (int32_t)(*s->roots)[r];
+        body[1 * rmax + r] = (*s->lr)[r];
+        body[2 * rmax + r] = (*s->lp)[r];
+        body[3 * rmax + r] = (*s->ndata)[r];
+        body[4 * rmax + r] = (*s->size)[r];
+        body[5 * rmax + r] = (*s->slot)[r];
+        body[6 * rmax + r] = (*s->gidx)[r];
+        body[7 * rmax + r] = (int32_t)kids.size();
+        body[8 * rmax + r] = (int32_t)(*s->kids)[r].size();
+        kids.insert(kids.end(), (*s->kids)[r].begin(), (*s->kids)[r].end());
+      }
+      double* d = dbls[w].data() + (size_t)t * 8;
+      d[0] = s->crp;
+      d[1] = s->mult;
+      d[2] = s->oprior;
+      d[3] = s->omarg;
+    }
+  }
+  Py_DECREF(lists[0]);
+  Py_DECREF(lists[1]);
+  if (!ok) return nullptr;
+  return Py_BuildValue("(y#y#y#y#y#)", (const char*)ints[0].data(), (Py_ssize_t)(ints[0].size() * 4),
+                       (const char*)ints[1].data(), (Py_ssize_t)(ints[1].size() * 4), (const char*)dbls[0].data(),
+                       (Py_ssize_t)(dbls[0].size() * 8), (const char*)dbls[1].data(), (Py_ssize_t)(dbls[1].size() * 8),
+                       (const char*)kids.data(), (Py_ssize_t)(kids.size() * 4));
+}
+
 PyMethodDef FState_methods[] = {
     {"export", (PyCFunction)FState_export, METH_NOARGS, "all fields as a tuple"},
     {"extend", (PyCFunction)FState_extend, METH_VARARGS, "thawed successor state (None if the arena is full)"},
@@ -1985,6 +2061,7 @@ PyObject* mod_log_sum_exp(PyObject*, PyObject* arg) {
 
 PyMethodDef mod_methods[] = {
     {"forest_state", mod_forest_state, METH_VARARGS, "build a ForestState from Python sequences"},
+    {"pack_states", mod_pack_states, METH_VARARGS, "retained-path records of the device-resident sweep"},
     {"log_sum_exp", mod_log_sum_exp, METH_O, "log sum exp of a float64 buffer, reference summation order"},
     {"particle_log_ws", mod_particle_log_ws, METH_VARARGS, "incremental weights of a list of particles"},
     {"propose_step", mod_propose_step, METH_VARARGS, "draws of one SMC step (pcb_smc_draws) and the particles they make"},

@@ -51,6 +51,7 @@ struct Params {
   const int *ret_th_int, *ret_ba_int;
   const double *ret_th_dbl, *ret_ba_dbl;
   const u64* ret_key;
+  const int *ret_kind, *ret_arg;  // the retained path's own edit at step t: kind; node name (ATTACH) / #children (NEW)
   int *cur_int, *ext_int;
   double *cur_dbl, *ext_dbl;
   u64 *cur_key, *ext_key;
@@ -146,11 +147,25 @@ __device__ inline void put_job(int* jobs, int j, int coff, int C, int base, int 
 constexpr int kBuildWarps = 8;
 
 __global__ void build_kernel(const Params p, const int t) {
-  const int first = p.conditional ? 1 : 0;
+  // slot 0 of a conditional sweep is the retained particle: it builds candidates too (its own proposal probability
+  // is needed for its weight, and every particle equal to it shares them), but its state comes from the path tables
+  const int first = 0;
   const int Rmax = p.Rmax;
   const int lane = threadIdx.x & 31;
   const int i = first + blockIdx.x * kBuildWarps + (threadIdx.x >> 5);
   if (i >= p.N) return;
+  if (t > 0 && !(p.conditional && i == 0)) {
+    // this particle's parent state: the record of the particle it was resampled from (ancestors of step t-1; the keys
+    // were permuted by the weigh kernel already -- every warp's search below reads all of them)
+    const int a = p.o_anc[(size_t)(t - 1) * p.N + i];
+    const int4* src = reinterpret_cast<const int4*>(p.ext_int + (size_t)a * p.irec);
+    int4* dst = reinterpret_cast<int4*>(p.cur_int + (size_t)i * p.irec);
+    const int n4 = p.irec >> 2;
+#pragma unroll 4
+    for (int k = lane; k < n4; k += 32) dst[k] = src[k];
+    if (lane < DREC) p.cur_dbl[(size_t)i * DREC + lane] = p.ext_dbl[(size_t)a * DREC + lane];
+    __syncwarp();
+  }
   const u64 key = p.cur_key[i];
   int rep = i;
   for (int j = first + lane; j < i; j += 32)
@@ -270,7 +285,8 @@ __device__ inline int alloc_tiles(const Params& p, int n) {
 }
 
 constexpr int kMaxRoots = 64;
-constexpr int kDecideWarps = 8;
+constexpr int kDecideWarps = 4;
+constexpr int kRec4 = (IHEAD + F_COUNT * kMaxRoots + 3) / 4;
 
 // ------------------------------------------------------------------------------------------------------------
 // decide: proposal normalisation (a17), the particle's draws, successor state, node / score jobs.
@@ -282,7 +298,8 @@ constexpr int kDecideWarps = 8;
 __global__ void decide_kernel(const Params p, const int t) {
   __shared__ double sh_lp[kDecideWarps][kMaxRoots + 2], sh_lp1[kDecideWarps][kMaxRoots + 2],
       sh_q[kDecideWarps][kMaxRoots + 2];
-  const int first = p.conditional ? 1 : 0;
+  __shared__ int4 sh_rec[kDecideWarps][2][kRec4];
+  const int first = 0;  // slot 0 of a conditional sweep: the retained particle, whose edit is given (see below)
   const int Rmax = p.Rmax;
   const int lane = threadIdx.x & 31, wslot = threadIdx.x >> 5;
   const int i = first + blockIdx.x * kDecideWarps + wslot;
@@ -293,14 +310,29 @@ __global__ void decide_kernel(const Params p, const int t) {
   const int vid = p.value_id[t], sid = p.single_id[t], dpidx = p.dp_idx[t];
   const double op = p.dp_op[t], opn = p.dp_opn[t], marg = p.dp_marg[t];
   const ParentView v = parent_view(p, t, i);
-  const int R = v.bI[0];
+  // the parent's record(s) staged in shared memory: the scalar logic below walks them many times
+  {
+    const int n4 = p.irec >> 2;
+    const int4* gb = reinterpret_cast<const int4*>(v.bI);
+    const int4* gp = reinterpret_cast<const int4*>(v.pI);
+#pragma unroll 4
+    for (int k = lane; k < n4; k += 32) sh_rec[wslot][0][k] = gb[k];
+    if (v.ret) {
+#pragma unroll 4
+      for (int k = lane; k < n4; k += 32) sh_rec[wslot][1][k] = gp[k];
+    }
+    __syncwarp();
+  }
+  const int* bI = reinterpret_cast<const int*>(sh_rec[wslot][0]);
+  const int* pI = v.ret ? reinterpret_cast<const int*>(sh_rec[wslot][1]) : bI;
+  const int R = bI[0];
   const int j0 = p.job_off[p.rep[i]];
   // ---- candidates, scored on the base state (semi_adapted.py:85-141; pcb_hostmod.cpp score_attach_all /
   //      score_outlier / score_new)
-  const int* b_nd = fld(v.bI, F_NDATA, Rmax);
-  const int* b_sz = fld(v.bI, F_SIZE, Rmax);
-  const int* b_nm = fld(v.bI, F_NAME, Rmax);
-  const long bn = v.bI[1];
+  const int* b_nd = fld(bI, F_NDATA, Rmax);
+  const int* b_sz = fld(bI, F_SIZE, Rmax);
+  const int* b_nm = fld(bI, F_NAME, Rmax);
+  const long bn = bI[1];
   const double b_crp = v.bD[D_CRP], b_mult = v.bD[D_MULT], b_opr = v.bD[D_OPRIOR], b_om = v.bD[D_OMARG];
   int n_cand = R;
   {
@@ -369,6 +401,34 @@ __global__ void decide_kernel(const Params p, const int t) {
   for (int c = lane; c < n_cand; c += 32) q[c] /= qs;
   __syncwarp();
 
+  if (p.conditional && i == 0) {
+    // the retained particle: its edit is the one the current tree dictates (conditional.py:19-74); only the proposal's
+    // log-probability of that edit is needed (semi_adapted.py:36-61), for its weight
+    const int rk = p.ret_kind[t], ra = p.ret_arg[t];
+    double lq;
+    if (rk == K_NEW && R > 0) {
+      const double lbin =
+          tab(p.lfact, R, p.n_tab, true) - tab(p.lfact, ra, p.n_tab, true) - tab(p.lfact, R - ra, p.n_tab, true);
+      lq = p.log_half - (tab(p.logn, R + 1, p.n_tab, false) + lbin);
+    } else {
+      int pk;
+      if (rk == K_OUTLIER) {
+        pk = out_idx;
+      } else if (rk == K_NEW) {
+        pk = n_cand - 1;
+      } else {
+        pk = 0;
+        while (pk < R && b_nm[pk] != ra) ++pk;
+      }
+      if (pk < 0 || pk >= n_cand) {
+        if (lane == 0) atomicOr(p.status, ST_NUMERIC);
+        pk = 0;
+      }
+      lq = ((R == 0) ? 0.0 : p.log_half) + (c_lp[pk] - lse);
+    }
+    if (lane == 0) p.dec_logq[0] = lq;
+    return;
+  }
   // ---- the particle's draws (semi_adapted.py:63-83, 165-194; conventions of oracle/uniform.py)
   int kind, pick = -1, k_new = 0;
   u64 taken_base = 0;  // NEW: chosen positions in BASE order (= the parent's tree_roots the reference draws from)
@@ -400,16 +460,16 @@ __global__ void decide_kernel(const Params p, const int t) {
   }
 
   // ---- successor state = extend(thawed parent, edit)   (pcb_hostmod.cpp fstate_extend)
-  const int* s_nm = fld(v.pI, F_NAME, Rmax);
-  const int* s_lr = fld(v.pI, F_LR, Rmax);
-  const int* s_lp = fld(v.pI, F_LP, Rmax);
-  const int* s_nd = fld(v.pI, F_NDATA, Rmax);
-  const int* s_sz = fld(v.pI, F_SIZE, Rmax);
-  const int* s_sl = fld(v.pI, F_SLOT, Rmax);
-  const int* s_gi = fld(v.pI, F_GIDX, Rmax);
-  const int* s_ko = fld(v.pI, F_KOFF, Rmax);
-  const int* s_kc = fld(v.pI, F_KCNT, Rmax);
-  const int pn = v.pI[1], ps = v.pI[2], pe = v.pI[3], po = v.pI[4];
+  const int* s_nm = fld(pI, F_NAME, Rmax);
+  const int* s_lr = fld(pI, F_LR, Rmax);
+  const int* s_lp = fld(pI, F_LP, Rmax);
+  const int* s_nd = fld(pI, F_NDATA, Rmax);
+  const int* s_sz = fld(pI, F_SIZE, Rmax);
+  const int* s_sl = fld(pI, F_SLOT, Rmax);
+  const int* s_gi = fld(pI, F_GIDX, Rmax);
+  const int* s_ko = fld(pI, F_KOFF, Rmax);
+  const int* s_kc = fld(pI, F_KCNT, Rmax);
+  const int pn = pI[1], ps = pI[2], pe = pI[3], po = pI[4];
   const double s_crp = v.pD[D_CRP], s_mult = v.pD[D_MULT], s_opr = v.pD[D_OPRIOR], s_om = v.pD[D_OMARG];
   const u64 s_key = v.ret ? p.ret_key[t - 1] : p.cur_key[i];
   int* eI = p.ext_int + (size_t)i * p.irec;
@@ -687,11 +747,12 @@ __global__ void weigh_kernel(const Params p, const int t, const double log_unifo
       p.o_mask[(size_t)t * N + i] = p.dec_mask[i];
     } else {  // the retained particle of this step
       const double* rd = p.ret_th_dbl + (size_t)t * DREC;
-      double w = rd[D_LOGW];
+      const double plp = (t == 0) ? 0.0 : p.ret_th_dbl[(size_t)(t - 1) * DREC + D_LOGP];
+      double w = (rd[D_LOGP] - plp) - p.dec_logq[0];
       if (last) w = w - rd[D_LOGP] + rd[D_LOGP1];
       raw = (t == 0) ? log_uniform : p.lw[0] + w;
       p.o_logp[(size_t)t * N] = rd[D_LOGP];
-      p.o_logq[(size_t)t * N] = 0.0;
+      p.o_logq[(size_t)t * N] = p.dec_logq[0];
       p.o_kind[(size_t)t * N] = -1;
       p.o_name[(size_t)t * N] = -1;
       p.o_mask[(size_t)t * N] = 0;
@@ -796,20 +857,9 @@ __global__ void weigh_kernel(const Params p, const int t, const double log_unifo
     p.o_anc[(size_t)t * N + i] = sh_anc[i];
     p.lw[i] = resample ? lw_uniform : log_W;
   }
-  // ---- next step's parents: cur[s] = ext[anc[s]], all slots at once (the unused tail of a field is copied too)
-  if (!last) {
-    const int irec = p.irec;
-    const int total = N * irec;
-    for (int k = threadIdx.x; k < total; k += blockDim.x) {
-      const int s = k / irec, f = k - s * irec;
-      p.cur_int[k] = p.ext_int[(size_t)sh_anc[s] * irec + f];
-    }
-    for (int k = threadIdx.x; k < N * DREC; k += blockDim.x) {
-      const int s = k / DREC, f = k - s * DREC;
-      p.cur_dbl[k] = p.ext_dbl[(size_t)sh_anc[s] * DREC + f];
-    }
-    if (i < N) p.cur_key[i] = p.ext_key[sh_anc[i]];
-  }
+  // ---- next step's parents: only the structure hashes move here (the build kernel's search for equal parents reads
+  // all of them); every particle's record is fetched by its own warp of the next build kernel
+  if (!last && i < N) p.cur_key[i] = p.ext_key[sh_anc[i]];
 }
 
 __global__ void init_kernel(const Params p, const double lw0) {

@@ -33,11 +33,13 @@ class ParticleGibbsTreeSampler(object):
         data_sigma = RootPermutationDistribution.sample(tree, self._rng)
         seed = int(self._rng.integers(0, 1 << 62))
         sampler = ConditionalSMCSampler(tree, data_sigma, self.kernel, num_particles=self.num_particles,
-                                        resample_threshold=self.resample_threshold)
+                                        resample_threshold=self.resample_threshold, with_proposals=False)
         try:
-            return self._device.run(data_sigma, seed, sampler.constrained_path)
+            return self._device.run(data_sigma, seed, sampler.constrained_path, sampler.path_edits)
         except SweepFallback:
             self._device.stats["fallbacks"] += 1
+            sampler = ConditionalSMCSampler(tree, data_sigma, self.kernel, num_particles=self.num_particles,
+                                            resample_threshold=self.resample_threshold)
             return self._sample_tree_from_swarm(sampler.sample())
 
     def sample_swarm(self, tree):

@@ -17,7 +17,10 @@ import numpy as np
 
 from .. import _lib
 from ..tree.tree import Tree
+from .._hostmod import load as _load_hostmod
 from .forest_state import ATTACH, NEW, ForestState, host_tuple
+
+_hm = _load_hostmod()
 
 IHEAD, NFIELDS, DREC = 5, 9, 8
 FLAG_RETAINED_PARENT = 8
@@ -37,7 +40,7 @@ class SweepDesc(C.Structure):
         + [("seed", _u64), ("tile_base", C.c_int64), ("tile_limit", C.c_int64)]
         + [(n, C.c_void_p) for n in (
             "dp_idx", "value_id", "single_id", "dp_op", "dp_opn", "dp_marg", "lfact", "logn", "rterm", "ret_th_int",
-            "ret_ba_int", "ret_th_dbl", "ret_ba_dbl", "ret_key", "ret_kids", "anc", "kind", "name", "mask", "raw", "logp",
+            "ret_ba_int", "ret_th_dbl", "ret_ba_dbl", "ret_key", "ret_kids", "ret_kind", "ret_arg", "anc", "kind", "name", "mask", "raw", "logp",
             "logq", "ess", "resampled", "final_idx", "status", "tiles_used", "n_launches", "conv_pairs", "device_ms")]
     )
 
@@ -92,44 +95,31 @@ class DeviceSweep(object):
         self.history = None  # set to a list to keep a copy of every sweep's outputs
 
     # ------------------------------------------------------------------------------------------------ packing
-    def _pack_state(self, state, int_rec, dbl_rec, kids_out, rmax):
-        (roots, lr, lp, kids, ndata, size, slot, gidx, n_nodes, n_slots, n_edges, n_out, crp, mult, oprior, omarg,
-         skey) = state.export()
-        R = len(roots)
-        if R > rmax:
-            raise SweepFallback("retained forest with %d roots" % R)
-        int_rec[:IHEAD] = (R, n_nodes, n_slots, n_edges, n_out)
-        body = int_rec[IHEAD:].reshape(NFIELDS, rmax)
-        for f, vals in enumerate((roots, lr, lp, ndata, size, slot, gidx)):
-            body[f, :R] = vals
-        for r, k in enumerate(kids):
-            body[7, r] = len(kids_out)
-            body[8, r] = len(k)
-            kids_out.extend(k)
-        dbl_rec[:4] = (crp, mult, oprior, omarg)
-        return skey
-
     def _pack_retained(self, path, rmax):
+        """Retained-path tables of pcb_sweep_desc: per step the thawed state (what extends the particle), the as-built
+        state (what its proposal's candidates are scored on), log_p / log_p_one and the structure hash."""
         T = len(path) - 1
-        irec = IHEAD + NFIELDS * rmax
-        th_i = np.zeros((T, irec), dtype=np.int32)
-        ba_i = np.zeros((T, irec), dtype=np.int32)
-        th_d = np.zeros((T, DREC), dtype=np.float64)
-        ba_d = np.zeros((T, DREC), dtype=np.float64)
-        keys = np.zeros(T, dtype=np.uint64)
-        kids = []
+        th, ba = [], []
         for t in range(T):
-            particle = path[t + 1]
-            holder = particle._holder
-            th = holder.thawed_state()
-            ba = ForestState.from_tree(holder._built)
-            if th is None or ba is None:
+            holder = path[t + 1]._holder
+            s_th = holder.thawed_state()
+            s_ba = ForestState.from_tree(holder._built)
+            if s_th is None or s_ba is None:
                 raise SweepFallback("retained tree is not an SMC-grown tree")
-            self._pack_state(th, th_i[t], th_d[t], kids, rmax)
-            self._pack_state(ba, ba_i[t], ba_d[t], kids, rmax)
-            keys[t] = holder.vkey[0]  # "equal particle" exactly as the host sampler tests it (kernels.get_proposal_distribution)
-            th_d[t, 4], th_d[t, 5], th_d[t, 6] = holder.log_p, holder.log_p_one, particle.log_w
-        return th_i, ba_i, th_d, ba_d, keys, np.asarray(kids, dtype=np.int32)
+            th.append(s_th)
+            ba.append(s_ba)
+        try:
+            th_i, ba_i, th_d, ba_d, kids = _hm.pack_states(th, ba, rmax)
+        except OverflowError as e:
+            raise SweepFallback(str(e))
+        th_d = np.frombuffer(th_d, dtype=np.float64).reshape(T, DREC).copy()
+        for t in range(T):
+            holder = path[t + 1]._holder
+            th_d[t, 4], th_d[t, 5] = holder.log_p, holder.log_p_one  # the first read scores the whole path: one flush
+        # "equal particle" exactly as the host sampler tests it (kernels.get_proposal_distribution)
+        keys = np.array([path[t + 1]._holder.vkey[0] for t in range(T)], dtype=np.uint64)
+        return (np.frombuffer(th_i, dtype=np.int32), np.frombuffer(ba_i, dtype=np.int32), th_d,
+                np.frombuffer(ba_d, dtype=np.float64), keys, np.frombuffer(kids, dtype=np.int32))
 
     def _outputs(self, T):
         N = self.N
@@ -145,9 +135,10 @@ class DeviceSweep(object):
         return o
 
     # ------------------------------------------------------------------------------------------------ the sweep
-    def run(self, sigma, seed, path=None):
+    def run(self, sigma, seed, path=None, path_edits=None):
         """Sweep over the data points `sigma`; `path` = the retained path ([None, particle_1 .. particle_T]) of a
-        conditional sweep, None for an unconditional one.  Returns the picked particle's tree."""
+        conditional sweep and `path_edits` its (kind, argument) per data point, None for an unconditional sweep.
+        Returns the picked particle's tree."""
         store, N = self.store, self.N
         T = len(sigma)
         rmax = min(MAX_ROOTS, T + 1)
@@ -187,8 +178,11 @@ class DeviceSweep(object):
         (d.dp_idx, d.value_id, d.single_id, d.dp_op, d.dp_opn, d.dp_marg, d.lfact, d.logn, d.rterm) = [_ptr(a) for a in keep]
         h2d = sum(a.nbytes for a in keep)
         if conditional:
-            ret = [th_i, ba_i, th_d, ba_d, keys, kids]
-            d.ret_th_int, d.ret_ba_int, d.ret_th_dbl, d.ret_ba_dbl, d.ret_key, d.ret_kids = [_ptr(a) for a in ret]
+            edits = np.asarray(path_edits, dtype=np.int32).reshape(T, 2)
+            ret_kind, ret_arg = np.ascontiguousarray(edits[:, 0]), np.ascontiguousarray(edits[:, 1])
+            ret = [th_i, ba_i, th_d, ba_d, keys, kids, ret_kind, ret_arg]
+            (d.ret_th_int, d.ret_ba_int, d.ret_th_dbl, d.ret_ba_dbl, d.ret_key, d.ret_kids, d.ret_kind,
+             d.ret_arg) = [_ptr(a) if a.size else None for a in ret]
             h2d += sum(a.nbytes for a in ret)
         (d.anc, d.kind, d.name, d.mask, d.raw, d.logp, d.logq, d.ess, d.resampled, d.final_idx, d.status, d.tiles_used,
          d.n_launches, d.conv_pairs, d.device_ms) = [_ptr(o[k]) for k in (

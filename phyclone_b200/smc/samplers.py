@@ -143,11 +143,14 @@ class SMCSampler(AbstractSMCSampler):
 class ConditionalSMCSampler(AbstractSMCSampler):
     """smc/samplers/conditional.py"""
 
-    def __init__(self, current_tree, data_points, kernel, num_particles, resample_threshold=0.5):
+    def __init__(self, current_tree, data_points, kernel, num_particles, resample_threshold=0.5, with_proposals=True):
+        """`with_proposals=False` (the device-resident sweep): only the retained trees are built; their proposal
+        log-probabilities -- hence the particles' weights -- are computed on the device, from `path_edits`."""
         super().__init__(data_points, kernel, num_particles, resample_threshold=resample_threshold)
-        self.constrained_path = self._get_constrained_path(current_tree)
+        self.path_edits = []  # per data point: (kind, node name | number of adopted roots) of the retained path
+        self.constrained_path = self._get_constrained_path(current_tree, with_proposals)
 
-    def _get_constrained_path(self, tree):
+    def _get_constrained_path(self, tree, with_proposals=True):
         """conditional.py:19-74.  All T retained trees and their proposals are built first (they do not
         depend on any score), the proposal probabilities are read afterwards: one flush for the whole path."""
         kernel = self.kernel
@@ -169,9 +172,11 @@ class ConditionalSMCSampler(AbstractSMCSampler):
             if old_node == outlier_node_name:
                 new_tree.add_data_point_to_outliers(data_point)
                 thawed.add_data_point_to_outliers(data_point)
+                self.path_edits.append((2, 0))
             elif old_node in node_map:
                 new_tree.add_data_point_to_node(data_point, node_map[old_node])
                 thawed.add_data_point_to_node(data_point, node_map[old_node])
+                self.path_edits.append((0, int(node_map[old_node])))
             else:
                 children = [node_map[child] for child in tree.get_children(old_node)]
                 new_node = new_tree.create_root_node(children)
@@ -180,12 +185,17 @@ class ConditionalSMCSampler(AbstractSMCSampler):
                 twin = thawed.create_root_node(children)
                 assert twin == new_node
                 thawed.add_data_point_to_node(data_point, new_node)
+                self.path_edits.append((1, len(children)))
             thawed.outliers  # noqa: B018 -- same key-creation side effect as scoring the as-built tree
             thawed = thawed.thawed_copy()
             holder = TreeHolder(new_tree, kernel.tree_dist)
             holder._thawed = thawed
             holders.append(holder)
         constrained_path = [None]
+        if not with_proposals:
+            for holder in holders:
+                constrained_path.append(kernel.create_particle(None, constrained_path[-1], holder))
+            return constrained_path
         parent_tree = None
         pending = []
         for data_point, holder in zip(self.data_points, holders):
