@@ -377,6 +377,7 @@ def run_ours(args):
     snap = chain.snapshot()
     ops.timing_begin(2000 * args.steps + 4096)
     s0 = dict(chain.stats)
+    plan0 = ops.plan_stats()
     launches0 = ops.launch_count()
     staged0 = store.arena.staged_bytes
     with ClockSampler(local) as clocks:
@@ -384,6 +385,18 @@ def run_ours(args):
     value_per_rank_ms = list(per_rank_ms)
     launches = ops.launch_count() - launches0
     s1 = dict(chain.stats)
+    plan1 = ops.plan_stats()
+    # where a step's time goes on this rank: device-resident sweep (CUDA-event time), waiting for flushes of the tile
+    # store (host blocked on the stream), everything else = host sampler logic
+    sweep_ms = (s1.get("sweep", {}).get("device_ms", 0.0) - s0.get("sweep", {}).get("device_ms", 0.0)) / args.steps
+    wait_ms = 1e3 * (plan1[1] - plan0[1]) / args.steps
+    split = torch.tensor([sweep_ms, wait_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        splits = [torch.zeros_like(split) for _ in range(world)]
+        dist.all_gather(splits, split)
+    else:
+        splits = [split]
+    splits = [[float(x) for x in t.tolist()] for t in splits]
     kernel_ms, n_timed = ops.timing_end()
     def all_pairs(st):  # pair convolutions folded by flushes of the tile store + by device-resident sweeps
         return st["conv_pairs"] + sum(st.get(k, {}).get("conv_pairs", 0) for k in ("sweep", "burnin_sweep"))
@@ -396,20 +409,50 @@ def run_ours(args):
 
     # ---- timed region 2: end to end through the host-facing API, inputs re-sent from pinned host memory
     chain.restore(snap)
-    staged = lambda: store.arena.staged_bytes + 4 * chain.stats["staged_ints"]  # noqa: E731 -- id lists / job tables sent
-    d2h0, st0 = chain.stats["d2h_bytes"], staged()
+    def sweep_bytes(which):  # control tables up / genealogy down of the device-resident sweeps
+        st = chain.stats
+        return sum(st.get(k, {}).get(which, 0) for k in ("sweep", "burnin_sweep"))
+
+    staged = lambda: (store.arena.staged_bytes + 4 * chain.stats["staged_ints"]  # noqa: E731 -- id lists / job tables sent
+                      + sweep_bytes("h2d_bytes"))
+    d2h_all = lambda: chain.stats["d2h_bytes"] + sweep_bytes("d2h_bytes")  # noqa: E731
+    d2h0, st0 = d2h_all(), staged()
     sink = []
     ms_e2e = timed(args.steps, before_step=lambda: store.upload_values(values),
                    after_step=lambda: sink.append(chain.log_p_one()))
     e2e_value = world * args.steps / (ms_e2e * 1e-3)
     h2d = values.nbytes + (staged() - st0) / args.steps
-    d2h = (chain.stats["d2h_bytes"] - d2h0) / args.steps
+    d2h = (d2h_all() - d2h0) / args.steps
 
     # ---- the same iterations once more with nothing attached (no kernel events, no transfers): what the event pairs
     # of region 1 cost
     chain.restore(snap)
     ms_plain = timed(args.steps)
     value_plain = world * args.steps / (ms_plain * 1e-3)
+
+    # ---- the same workload with the sweeps on the host (NumPy Generator draws: RNG-identical to the reference)
+    other = None
+    if rank == 0 and world == 1 and not args.no_other_sweep:
+        which = "host" if args.sweep == "device" else "device"
+        try:
+            store2 = TileStore(values, device=dev, variant=TileStore.LATENCY_LAYOUT)
+            chain2 = Chain(data, chain_rng(rank, world), num_particles=CFG["particles"], proposal=CFG["proposal"],
+                           resample_threshold=CFG["resample_threshold"], outlier_prob=CFG["outlier_prob"], store=store2,
+                           sweep=which)
+            chain2.burnin_step()
+            for _ in range(args.warmup):
+                chain2.step()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                chain2.step()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            other = {"sweep": which, "value": args.steps / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / args.steps,
+                     "how": "second chain object, same data / seed / iteration window, wall clock around the timed steps"}
+            del chain2, store2
+        except Exception as e:  # noqa: BLE001
+            other = {"sweep": which, "error": "%s: %s" % (type(e).__name__, e)}
 
     # ---- saturated-batch figure for the same kernel (how far the kernel itself goes when a launch is big)
     sat = None
@@ -444,7 +487,8 @@ def run_ours(args):
             n_chains = max(2, min(8, (os.cpu_count() or 2) // 2))
             with MpsServer() as server:
                 if server.started:
-                    rate = run_chains_once(n_chains, args.steps, args.warmup, timeout=300)
+                    rate = run_chains_once(n_chains, args.steps, args.warmup, timeout=300, config=CFG["config_number"],
+                                           sweep=args.sweep)
                     mps_chains = {"chains": n_chains, "value": rate, "unit": UNIT, "per_chain": rate / n_chains,
                                   "how": "one host process per chain, all on GPU 0 through an MPS daemon started for this "
                                          "leg (run.MpsServer / run.run_chains_local); same config, chain seeds spawned"}
@@ -490,6 +534,11 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "per_rank_ms_per_step": [round(x, 2) for x in value_per_rank_ms],
+            "per_rank_split_ms_per_step": [
+                {"device_sweep": round(sw, 2), "flush_wait": round(fw, 2), "host": round(max(t - sw - fw, 0.0), 2)}
+                for t, (sw, fw) in zip(value_per_rank_ms, splits)],
+            "limiter": "host sampler logic (one Python thread per chain) + serial device latency: see "
+                       "per_rank_split_ms_per_step; chains never exchange data",
             "cpu_pinning": pinned,
             "roofline": {"bound": "fp64", "kernel": "node_jobs_kernel", "achieved": achieved / 1e12,
                          "peak": fp64_peak / 1e12, "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": traffic, "traffic_source": traffic_src,
@@ -506,6 +555,10 @@ def run_ours(args):
                              **({"sweep_" + k: (s1["sweep"][k] - s0["sweep"][k]) / args.steps for k in s1["sweep"]}
                                 if "sweep" in s1 else {})),
             "sweep": args.sweep,
+            "sweep_note": "device = conditional-SMC sweeps device-resident with uniform-driven draws (csrc/pcb_sweep.cuh; "
+                          "pinned decision for decision against oracle/uniform.py); host = NumPy Generator draws, "
+                          "RNG-identical to the reference",
+            "other_sweep": other,
         }
         print(json.dumps(line))
     if world > 1:
@@ -520,6 +573,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mps-chains", action="store_true", help="skip the 8-chains-on-one-GPU (MPS) leg")
+    ap.add_argument("--no-other-sweep", action="store_true", help="skip the comparison leg with the other sweep mode")
     ap.add_argument("--sweep", default="device", choices=["host", "device"],
                     help="SMC sweeps on the host (NumPy Generator draws, RNG-identical to the reference) or device-resident "
                          "(uniform-driven draws, csrc/pcb_sweep.cuh)")
