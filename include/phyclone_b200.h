@@ -111,10 +111,12 @@ int pcb_tile_add_dev(const pcb_arena* arena, const int32_t* a_ids, const int32_t
  *   [2] base tile id (log_p) or -1         [3] output tile id or -1 (scores only)
  *   [4] flags (PCB_JOB_*)                  [5] score slot or -1
  *   [6] second base tile id + 1, or 0: log_p = tile(base) + tile(base2) formed on the fly (a node refresh right after
- *       `log_p += value`, tree/tree_node.py:42-52 then :61-71)          [7] reserved (0)
+ *       `log_p += value`, tree/tree_node.py:42-52 then :61-71)          [7] number of second-stage children (PCB_JOB_THEN_SCORE), else 0
  */
 #define PCB_JOB_SCAN 1      /* apply the prefix log-sum-exp (log_S); without it the job yields log_D */
 #define PCB_JOB_ADD_PRIOR 2 /* add the scalar `prior` (the dummy root's log_p = -log G) */
+#define PCB_JOB_THEN_SCORE 4 /* device-resident sweep only: after the node tile is written, fold record[7] more children
+                              * onto it as a dummy root (prior added) and emit that tree's scores into `score slot` */
 #define PCB_JOB_INTS 8
 
 int pcb_node_jobs_dev(const pcb_arena* arena, const int32_t* jobs_dev, const int32_t* children_dev, int64_t n_jobs,

@@ -127,18 +127,31 @@ int pool_ctas() {
   return v;
 }
 
-template <int L>
-int launch_jobs_L(const pcb::JobKernelParams& kp, long long n_jobs, int threads, size_t smem, cudaStream_t st) {
+template <int L, bool FUSE>
+int launch_jobs_LF(const pcb::JobKernelParams& kp, long long n_jobs, int threads, size_t smem, cudaStream_t st) {
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
-    PCB_CUDA(cudaFuncSetAttribute(pcb::node_jobs_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PCB_CUDA(cudaFuncSetAttribute(pcb::node_jobs_kernel<L, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   const long long grid = kp.n_jobs_dev ? std::min<long long>(n_jobs * kp.row_blocks, pool_ctas()) : n_jobs * kp.row_blocks;
   if (grid > 2147483647ll) return fail(PCB_ERR_ARG, "too many jobs for one launch");
-  pcb::node_jobs_kernel<L><<<(unsigned)grid, threads, smem, st>>>(kp);
+  pcb::node_jobs_kernel<L, FUSE><<<(unsigned)grid, threads, smem, st>>>(kp);
   PCB_LAUNCH_CHECK();
   return PCB_OK;
+}
+
+// `fused`: the table may hold PCB_JOB_THEN_SCORE jobs (only the strips the latency / throughput layouts use are built)
+template <int L>
+int launch_jobs_L(const pcb::JobKernelParams& kp, long long n_jobs, int threads, size_t smem, cudaStream_t st,
+                  bool fused = false) {
+  if (fused) {
+    if constexpr (L == 7 || L == 13 || L == 17)
+      return launch_jobs_LF<L, true>(kp, n_jobs, threads, smem, st);
+    else
+      return fail(PCB_ERR_ARG, "node_jobs: fused jobs are not built for this strip width");
+  }
+  return launch_jobs_LF<L, false>(kp, n_jobs, threads, smem, st);
 }
 
 template <int L>
@@ -427,13 +440,14 @@ int pcb_timing_end(double* total_ms, int64_t* n_launches) {
 
 static int node_jobs_launch(const pcb_arena* a, const int32_t* jobs_dev, const int32_t* children_dev, int64_t n_jobs,
                             double prior, double* rows_lse, double* rows_last, void* stream,
-                            const int* n_jobs_dev = nullptr);
+                            const int* n_jobs_dev = nullptr, bool fused = false);
 
 static int jobs_launch_timed(const pcb_arena* a, const int32_t* jobs_dev, const int32_t* children_dev, int64_t n_jobs,
-                             double prior, double* rows_lse, double* rows_last, void* stream, const int* n_jobs_dev) {
+                             double prior, double* rows_lse, double* rows_last, void* stream, const int* n_jobs_dev,
+                             bool fused = false) {
   const bool timed = g_timing.on && n_jobs > 0 && g_timing.used + 2 <= g_timing.cap;
   if (timed) PCB_CUDA(cudaEventRecord(g_timing.ev[g_timing.used], (cudaStream_t)stream));
-  const int rc = node_jobs_launch(a, jobs_dev, children_dev, n_jobs, prior, rows_lse, rows_last, stream, n_jobs_dev);
+  const int rc = node_jobs_launch(a, jobs_dev, children_dev, n_jobs, prior, rows_lse, rows_last, stream, n_jobs_dev, fused);
   if (timed && rc == PCB_OK) {
     PCB_CUDA(cudaEventRecord(g_timing.ev[g_timing.used + 1], (cudaStream_t)stream));
     g_timing.used += 2;
@@ -449,7 +463,8 @@ int pcb_node_jobs_dev(const pcb_arena* a, const int32_t* jobs_dev, const int32_t
 // n_jobs_dev != NULL: `n_jobs` is only an upper bound, the count is read on the device (tables written by a kernel
 // earlier in the stream)
 static int node_jobs_launch(const pcb_arena* a, const int32_t* jobs_dev, const int32_t* children_dev, int64_t n_jobs,
-                            double prior, double* rows_lse, double* rows_last, void* stream, const int* n_jobs_dev) {
+                            double prior, double* rows_lse, double* rows_last, void* stream, const int* n_jobs_dev,
+                            bool fused) {
   int rc = check_arena(a);
   if (rc) return rc;
   if (n_jobs <= 0) return PCB_OK;
@@ -478,6 +493,7 @@ static int node_jobs_launch(const pcb_arena* a, const int32_t* jobs_dev, const i
   kp.n_jobs = n_jobs;
   kp.n_jobs_dev = n_jobs_dev;
   if (l.kernel == 1) {
+    if (fused) return fail(PCB_ERR_ARG, "node_jobs: the unit-per-warp kernel has no fused jobs");
     const size_t wsmem = wide_smem_bytes(l.lanes_per_row, l.pitch);
     cudaStream_t wst = (cudaStream_t)stream;
     switch (l.strip) {
@@ -495,17 +511,17 @@ static int node_jobs_launch(const pcb_arena* a, const int32_t* jobs_dev, const i
   cudaStream_t st = (cudaStream_t)stream;
   switch (l.strip) {
     case 3:
-      return launch_jobs_L<3>(kp, n_jobs, threads, smem, st);
+      return launch_jobs_L<3>(kp, n_jobs, threads, smem, st, fused);
     case 5:
-      return launch_jobs_L<5>(kp, n_jobs, threads, smem, st);
+      return launch_jobs_L<5>(kp, n_jobs, threads, smem, st, fused);
     case 7:
-      return launch_jobs_L<7>(kp, n_jobs, threads, smem, st);
+      return launch_jobs_L<7>(kp, n_jobs, threads, smem, st, fused);
     case 9:
-      return launch_jobs_L<9>(kp, n_jobs, threads, smem, st);
+      return launch_jobs_L<9>(kp, n_jobs, threads, smem, st, fused);
     case 13:
-      return launch_jobs_L<13>(kp, n_jobs, threads, smem, st);
+      return launch_jobs_L<13>(kp, n_jobs, threads, smem, st, fused);
     case 17:
-      return launch_jobs_L<17>(kp, n_jobs, threads, smem, st);
+      return launch_jobs_L<17>(kp, n_jobs, threads, smem, st, fused);
   }
   return fail(PCB_ERR_ARG, "node_jobs: unsupported strip");
 }
@@ -1056,6 +1072,11 @@ int pcb_smc_sweep_dev(const pcb_arena* a, const pcb_sweep_desc* d, void* stream)
   P.pool_cap = pool_cap;
   P.tile_limit = (int)d->tile_limit;
   P.scratch0 = (int)d->tile_base;
+  {
+    const char* e = getenv("PCB_SWEEP_FUSE");
+    P.fuse = (a->layout.kernel == 0 && (a->layout.strip == 7 || a->layout.strip == 13 || a->layout.strip == 17) &&
+              !(e && atoi(e) == 0)) ? 1 : 0;
+  }
 
   // ---- inputs: host -> device
   auto up = [&](const void* dst, const void* src, size_t bytes) -> cudaError_t {
@@ -1115,9 +1136,14 @@ int pcb_smc_sweep_dev(const pcb_arena* a, const pcb_sweep_desc* d, void* stream)
     PCB_LAUNCH_CHECK();
     launches += 3;
     if (t > 0) {
-      if ((rc = jobs_launch_timed(a, P.jobsD, P.kidsD, N, d->prior, nullptr, nullptr, stream, P.nD))) return rc;
-      if ((rc = jobs_launch_timed(a, P.jobsE, P.kidsE, 2ll * N, d->prior, P.scE_lse, P.scE_last, stream, P.nE))) return rc;
-      launches += 2;
+      if (!P.fuse) {
+        if ((rc = jobs_launch_timed(a, P.jobsD, P.kidsD, N, d->prior, nullptr, nullptr, stream, P.nD))) return rc;
+        ++launches;
+      }
+      if ((rc = jobs_launch_timed(a, P.jobsE, P.kidsE, 2ll * N, d->prior, P.scE_lse, P.scE_last, stream, P.nE,
+                                  P.fuse != 0)))
+        return rc;
+      ++launches;
     }
     sw::weigh_kernel<<<1, 1024, 0, st>>>(P, t, d->log_uniform, d->lw_uniform);
     PCB_LAUNCH_CHECK();

@@ -1036,7 +1036,7 @@ PyObject* mod_pack_states(PyObject*, PyObject* args) {
   return Py_BuildValue("(y#y#y#y#y#)", (const char*)ints[0].data(), (Py_ssize_t)(ints[0].size() * 4),
                        (const char*)ints[1].data(), (Py_ssize_t)(ints[1].size() * 4), (const char*)dbls[0].data(),
                        (Py_ssize_t)(dbls[0].size() * 8), (const char*)dbls[1].data(), (Py_ssize_t)(dbls[1].size() * 8),
-                       (const char*)kids.data(), (Py_ssize_t)(kids.size() * 4));
+                       kids.empty() ? "" : (const char*)kids.data(), (Py_ssize_t)(kids.size() * 4));
 }
 
 PyMethodDef FState_methods[] = {

@@ -239,8 +239,10 @@ __device__ __forceinline__ void row_prefix_lse(const double* x, double* out, int
 constexpr int kSmemHead = 256;
 constexpr int kSmemTail = 256;
 
-template <int L>
-__global__ void __launch_bounds__(32, (L == 13) ? 12 : 1) node_jobs_kernel(const JobKernelParams p) {
+// FUSE: the launch may contain PCB_JOB_THEN_SCORE jobs (a separate instantiation: the extra live state of the second
+// stage costs registers the plain kernel cannot spare at 12 warps per SM)
+template <int L, bool FUSE = false>
+__global__ void __launch_bounds__(32, (L == 13 && !FUSE) ? 12 : 1) node_jobs_kernel(const JobKernelParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
   const int rows_elems = p.RB * p.pitch;
@@ -281,11 +283,16 @@ __global__ void __launch_bounds__(32, (L == 13) ? 12 : 1) node_jobs_kernel(const
   const bool scan = flags & 1;
   const double addc = (flags & 2) ? p.prior : 0.0;
   const bool shortcut = scan && base < 0 && outt < 0;
+  // PCB_JOB_THEN_SCORE: after the node tile is written, the SAME work item goes on folding jr[7] more children onto
+  // it as a dummy root and emits that tree's scores -- the node refresh and the tree score it feeds are one serial
+  // chain anyway, and as two jobs they were two dependent launches (csrc/pcb_sweep.cuh)
+  const int C2 = (FUSE && (flags & 4)) ? jr[7] : 0;
+  const int Ctot = C + C2;
 
   // child tile ids: one coalesced load per 32 children, handed out by shuffles.  (Reading children[coff + j] when
   // step j needs it put two dependent global loads -- id, then row maximum / TMA source -- on the serial path of
   // every fold step: ~1 us of the ~3.3 us a lone warp spends per step.)
-  int my_child = (tid < C) ? p.children[coff + tid] : 0;
+  int my_child = (tid < Ctot) ? p.children[coff + tid] : 0;
   const int c0 = __shfl_sync(0xffffffffu, my_child, 0);
   const int c1_id = __shfl_sync(0xffffffffu, my_child, 1);
   if (tid == 0) {
@@ -313,13 +320,17 @@ __global__ void __launch_bounds__(32, (L == 13) ? 12 : 1) node_jobs_kernel(const
 
   // ---- left fold over the children (tree/utils.py:33-47) --------------------------
   const bool db = p.double_b;
-  for (int j = 1; j < C; ++j) {
-    if ((j & 31) == 0) my_child = (j + tid < C) ? p.children[coff + j + tid] : 0;  // next 32 ids
+  bool sc = shortcut;      // this stage ends in the score-only epilogue
+  double add = addc;
+  int jb = 1, je = C;      // children folded by this stage
+  for (int stage = 0;; ++stage) {
+  for (int j = jb; j < je; ++j) {
+    if ((j & 31) == 0) my_child = (j + tid < Ctot) ? p.children[coff + j + tid] : 0;  // next 32 ids
     const int cj = __shfl_sync(0xffffffffu, my_child, j & 31);
     // id of the child after this one (the refill issued during this step) and this child's row maximum: both are
     // requested here, a whole convolution before they are needed
     int cnext = 0;
-    if (j + 1 < C) cnext = ((j + 1) & 31) ? __shfl_sync(0xffffffffu, my_child, (j + 1) & 31) : p.children[coff + j + 1];
+    if (j + 1 < je) cnext = ((j + 1) & 31) ? __shfl_sync(0xffffffffu, my_child, (j + 1) & 31) : p.children[coff + j + 1];
     const double mB = row_ok ? p.rmax[(size_t)cj * p.S + row] : 0.0;
     const bool first_buf = !db || (j & 1);
     double* Bcur = first_buf ? bufB0 : bufB1;
@@ -330,7 +341,7 @@ __global__ void __launch_bounds__(32, (L == 13) ? 12 : 1) node_jobs_kernel(const
       mbar_wait(&bars[2], ph2 & 1);
       ++ph2;
     }
-    if (db && j + 1 < C && tid == 0) {  // prefetch the next operand into the buffer step j-1 released
+    if (db && j + 1 < je && tid == 0) {  // prefetch the next operand into the buffer step j-1 released
       double* Bnext = (j & 1) ? bufB1 : bufB0;
       uint64_t* nbar = (j & 1) ? &bars[2] : &bars[1];
       mbar_expect_tx(nbar, bytes);
@@ -339,7 +350,7 @@ __global__ void __launch_bounds__(32, (L == 13) ? 12 : 1) node_jobs_kernel(const
     const double* b_row = Bcur + lrow * pitch + lead;
     double y1[L], y2[L];
     conv_unit<L>(a_row, b_row, u, Q, lane_ok, y1, y2);
-    if (!db && j + 1 < C) {  // single operand buffer: refill it as soon as every lane is done with it
+    if (!db && j + 1 < je) {  // single operand buffer: refill it as soon as every lane is done with it
       __syncwarp();
       if (tid == 0) {
         fence_proxy_async();
@@ -368,7 +379,7 @@ __global__ void __launch_bounds__(32, (L == 13) ? 12 : 1) node_jobs_kernel(const
     const double ymax = group_max(mx[0], P);
     double scale = 1.0;
     bool tiny = false;
-    if (j < C - 1) {
+    if (j < je - 1) {
       // re-normalise the running product exactly where the reference re-max-shifts it
       M += mB + log(ymax);
       tiny = !(ymax >= 1e-290);
@@ -400,7 +411,7 @@ __global__ void __launch_bounds__(32, (L == 13) ? 12 : 1) node_jobs_kernel(const
   double* yrow = a_row;
 
   // ---- epilogue 1: dummy-root scoring without materialising the tile --------------
-  if (shortcut) {
+  if (sc) {
     double t1 = 0.0, t2 = 0.0;
     if (row_ok)
       for (int k = lir; k < G; k += P) {
@@ -411,10 +422,10 @@ __global__ void __launch_bounds__(32, (L == 13) ? 12 : 1) node_jobs_kernel(const
     t1 = group_sum(t1, P);
     t2 = group_sum(t2, P);
     if (row_ok && lir == 0 && slot >= 0) {
-      p.sc_lse[(size_t)slot * p.S + row] = (M + addc) + log(t2);
-      p.sc_last[(size_t)slot * p.S + row] = (M + addc) + log(t1);
+      p.sc_lse[(size_t)slot * p.S + row] = (M + add) + log(t2);
+      p.sc_last[(size_t)slot * p.S + row] = (M + add) + log(t1);
     }
-    continue;
+    break;
   }
 
   // ---- epilogue 2: elementwise log_D / log_S, + log_p, store tile, optional scores --
@@ -493,17 +504,35 @@ __global__ void __launch_bounds__(32, (L == 13) ? 12 : 1) node_jobs_kernel(const
         olg[k] = v;
         olin[k] = e;
       }
+      if (C2 > 0) yrow[k] = e;  // the tile in the linear domain: first operand of the dummy-root fold below
     }
   }
   esum = group_sum(esum, P);
   __syncwarp();
   if (row_ok && lir == 0) {
     if (outt >= 0) p.rmax[(size_t)outt * p.S + row] = vmax;
-    if (slot >= 0) {
+    if (slot >= 0 && C2 == 0) {
       p.sc_lse[(size_t)slot * p.S + row] = (vmax == -INFINITY) ? -INFINITY : vmax + log(esum);
       p.sc_last[(size_t)slot * p.S + row] = yrow[G - 1];
     }
   }
+  if (C2 == 0 || stage == 1) break;
+  // ---- second stage: the tile just written is the first root of a dummy-root fold over children C .. Ctot-1
+  M = vmax;
+  if (tid == 0) {
+    const int cfirst = p.children[coff + C];
+    fence_proxy_async();
+    const bool fb = !db || (C & 1);
+    mbar_expect_tx(fb ? &bars[1] : &bars[2], bytes);
+    tma_load_1d(fb ? bufB0 : bufB1, p.lin + (size_t)cfirst * p.tile_elems + (size_t)r0 * pitch, bytes,
+                fb ? &bars[1] : &bars[2]);
+  }
+  if ((C & 31) != 0 && C >= 32) my_child = ((C & ~31) + tid < Ctot) ? p.children[coff + (C & ~31) + tid] : 0;
+  sc = true;
+  add = p.prior;
+  jb = C;
+  je = Ctot;
+  }  // stages
   }  // work items
 }
 

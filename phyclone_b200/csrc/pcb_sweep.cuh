@@ -43,6 +43,7 @@ enum { ST_OK = 0, ST_ROOTS = 1, ST_TILES = 2, ST_POOL = 4, ST_NUMERIC = 8 };
 
 struct Params {
   int N, T, Rmax, conditional, outliers, S, irec, n_tab;
+  int fuse;  // 1: a new node's tile and the score of its tree are ONE two-stage job (PCB_JOB_THEN_SCORE)
   double log_alpha, threshold, log_half;
   u64 seed;
   const int *dp_idx, *value_id, *single_id;
@@ -124,7 +125,9 @@ __device__ inline ParentView parent_view(const Params& p, int t, int i) {
   return v;
 }
 
-__device__ inline void put_job(int* jobs, int j, int coff, int C, int base, int out, int flags, int slot, int base2) {
+constexpr int JOB_THEN_SCORE = 4;
+__device__ inline void put_job(int* jobs, int j, int coff, int C, int base, int out, int flags, int slot, int base2,
+                               int more = 0) {
   int* r = jobs + (size_t)j * 8;
   r[0] = coff;
   r[1] = C;
@@ -133,7 +136,7 @@ __device__ inline void put_job(int* jobs, int j, int coff, int C, int base, int 
   r[4] = flags;
   r[5] = slot;
   r[6] = base2 + 1;
-  r[7] = 0;
+  r[7] = more;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -583,11 +586,12 @@ __global__ void decide_kernel(const Params p, const int t) {
     } else {
       int lr_new = sid, koff = 0, jd = 0;
       const bool score = R > 0;  // an empty parent's lone candidate already is this tree
+      const bool fused = p.fuse && k > 0 && score;  // node tile and tree score as one two-stage job in table E
       if (lane == 0) {
         if (k > 0) {
           lr_new = alloc_tiles(p, 1);
           koff = atomicAdd(p.pool_top, k);
-          jd = atomicAdd(p.nD, 1);
+          if (!fused) jd = atomicAdd(p.nD, 1);
           if (koff + k > p.pool_cap) atomicOr(p.status, ST_POOL);
           if (k > 1) atomicAdd(p.pairs, (u64)(k - 1));
         }
@@ -601,8 +605,10 @@ __global__ void decide_kernel(const Params p, const int t) {
       jd = __shfl_sync(0xffffffffu, jd, 0);
       slot_e = __shfl_sync(0xffffffffu, slot_e, 0);
       const bool pool_ok = koff + k <= p.pool_cap;
-      int* kidsD = p.kidsD + (size_t)jd * Rmax;
       int* kidsE = score ? p.kidsE + (size_t)slot_e * Rmax : nullptr;
+      // fused: [adopted roots (stage 1) | roots left alone (stage 2)] in one child list; else the node job's list
+      int* kidsD = fused ? kidsE : p.kidsD + (size_t)jd * Rmax;
+      const int e_shift = fused ? k - 1 : 0;  // stage-2 children start at index k of the fused list
       int sz = 1;
       u64 key = s_key ^ edge_hash(pe, 0, ps) ^ data_hash(pn, 0, dpidx);
       double ways_keep = 0.0;
@@ -632,7 +638,7 @@ __global__ void decide_kernel(const Params p, const int t) {
           e_gi[w] = s_gi[r];
           e_ko[w] = s_ko[r];
           e_kc[w] = s_kc[r];
-          if (kidsE) kidsE[w] = s_lr[r];
+          if (kidsE) kidsE[w + e_shift] = s_lr[r];
         }
       }
       const double mult = s_mult - tab(p.lfact, R, p.n_tab, true) + tab(p.lfact, R - k + 1, p.n_tab, true) +
@@ -651,7 +657,7 @@ __global__ void decide_kernel(const Params p, const int t) {
         lp1_new = lp1 + extra;
       }
       if (lane == 0) {
-        if (k > 0) put_job(p.jobsD, jd, jd * Rmax, k, sid, lr_new, JOB_SCAN, -1, -1);
+        if (k > 0 && !fused) put_job(p.jobsD, jd, jd * Rmax, k, sid, lr_new, JOB_SCAN, -1, -1);
         e_nm[0] = pn;
         e_lr[0] = lr_new;
         e_lp[0] = sid;
@@ -671,7 +677,9 @@ __global__ void decide_kernel(const Params p, const int t) {
         eD[D_OMARG] = s_om;
         eD[D_OPRIOR] = opr;
         p.ext_key[i] = key;
-        if (score) {
+        if (fused) {
+          put_job(p.jobsE, slot_e, slot_e * Rmax, k, sid, lr_new, JOB_SCAN | JOB_THEN_SCORE, slot_e, -1, Rn - 1);
+        } else if (score) {
           kidsE[0] = lr_new;
           put_job(p.jobsE, slot_e, slot_e * Rmax, Rn, -1, -1, JOB_SCAN | JOB_ADD_PRIOR, slot_e, -1);
         }
