@@ -286,7 +286,8 @@ __global__ void __launch_bounds__(32, (L == 13 && !FUSE) ? 12 : 1) node_jobs_ker
   // PCB_JOB_THEN_SCORE: after the node tile is written, the SAME work item goes on folding jr[7] more children onto
   // it as a dummy root and emits that tree's scores -- the node refresh and the tree score it feeds are one serial
   // chain anyway, and as two jobs they were two dependent launches (csrc/pcb_sweep.cuh)
-  const int C2 = (FUSE && (flags & 4)) ? jr[7] : 0;
+  const bool then_score = FUSE && (flags & 4);
+  const int C2 = then_score ? jr[7] : 0;  // may be 0: the new node adopted every root and is the only one left
   const int Ctot = C + C2;
 
   // child tile ids: one coalesced load per 32 children, handed out by shuffles.  (Reading children[coff + j] when
@@ -504,22 +505,22 @@ __global__ void __launch_bounds__(32, (L == 13 && !FUSE) ? 12 : 1) node_jobs_ker
         olg[k] = v;
         olin[k] = e;
       }
-      if (C2 > 0) yrow[k] = e;  // the tile in the linear domain: first operand of the dummy-root fold below
+      if (then_score) yrow[k] = e;  // the tile in the linear domain: first operand of the dummy-root fold below
     }
   }
   esum = group_sum(esum, P);
   __syncwarp();
   if (row_ok && lir == 0) {
     if (outt >= 0) p.rmax[(size_t)outt * p.S + row] = vmax;
-    if (slot >= 0 && C2 == 0) {
+    if (slot >= 0 && !then_score) {
       p.sc_lse[(size_t)slot * p.S + row] = (vmax == -INFINITY) ? -INFINITY : vmax + log(esum);
       p.sc_last[(size_t)slot * p.S + row] = yrow[G - 1];
     }
   }
-  if (C2 == 0 || stage == 1) break;
+  if (!then_score || stage == 1) break;
   // ---- second stage: the tile just written is the first root of a dummy-root fold over children C .. Ctot-1
   M = vmax;
-  if (tid == 0) {
+  if (tid == 0 && C2 > 0) {
     const int cfirst = p.children[coff + C];
     fence_proxy_async();
     const bool fb = !db || (C & 1);
