@@ -565,6 +565,70 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_chains_job(args):
+    """--chains C: BASELINE configs[2] as written -- the C chains of one run (spawned generators, run.py:87-113) on the
+    N GPUs of the job, chain c on GPU c % N, one worker process per chain (the reference's ProcessPoolExecutor,
+    run.py:111-149); the workers of a GPU share it through an MPS daemon.  The same C chains run whatever N is, so the
+    per-N values are the same work.  Timed on the device (CUDA events around each worker's steps), max over all workers
+    of all ranks; no data-path collective."""
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    from multi_chain_bench import run_chains_once
+
+    from phyclone_b200.run import MpsServer
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world != args.gpus:
+        raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    C = args.chains
+    mine = [c for c in range(C) if c % world == rank]
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        cores = sorted(os.sched_getaffinity(0))
+        block = len(cores) // world
+        if block >= 1 and not os.environ.get("PCB_NO_PIN"):
+            os.sched_setaffinity(0, cores[local * block:(local + 1) * block])  # inherited by this rank's workers
+    os.environ["CUDA_VISIBLE_DEVICES"] = os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")[local] \
+        if os.environ.get("CUDA_VISIBLE_DEVICES") else str(local)  # workers and the MPS daemon see this rank's GPU only
+
+    def go():
+        if world > 1:
+            dist.barrier()
+
+    with MpsServer(enable=len(mine) > 1) as server:
+        rate, ev_ms, splits = run_chains_once(len(mine), args.steps, args.warmup, timeout=900, config=CFG["config_number"],
+                                              sweep=args.sweep, device=0, chains=mine, n_chains=C, before_go=go,
+                                              details=True)
+        mps = server.started
+    ms = torch.tensor([ev_ms], dtype=torch.float64, device="cuda" if world > 1 else "cpu")
+    per_rank = [ev_ms]
+    if world > 1:
+        every = [torch.zeros_like(ms) for _ in range(world)]
+        dist.all_gather(every, ms)
+        per_rank = [float(t.item()) for t in every]
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    job_ms = float(ms.item())
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": C * args.steps / (job_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": job_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": dict(CFG, chains=C),
+            "sweep": args.sweep, "chains_per_gpu": [len([c for c in range(C) if c % world == r]) for r in range(world)],
+            "mps": mps, "per_rank_ms_per_step": [round(x / args.steps, 2) for x in per_rank],
+            "rank0_worker_split_ms_per_step": splits,
+            "how": "one worker process per chain, chain c on GPU c % N, CUDA events around each worker's timed steps, max "
+                   "over workers and ranks; strong scaling: the same %d chains at every N" % C,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -587,6 +651,8 @@ def main():
     set_config(args.config)
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.chains is not None:
+        run_chains_job(args)
     else:
         run_ours(args)
 
