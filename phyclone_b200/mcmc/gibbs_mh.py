@@ -13,11 +13,14 @@ _hm = _load_hostmod()
 
 
 class DataPointSampler(object):
+    LOOKAHEAD = 8  # moves scored per device round trip (see sample_tree)
+
     def __init__(self, tree_dist, rng, outliers=False):
         self.tree_dist = tree_dist
         self.outliers = outliers
         self._rng = rng
         self._flat = None  # (graph, flattened structure) of the tree the current sweep edits in place
+        self.moves = self.stays = self.lookahead_hits = 0
 
     def sample_tree(self, tree):
         """gibbs_mh.py:17-33: one Gibbs move per data point whose node holds more than one point, in shuffled order.
@@ -29,13 +32,49 @@ class DataPointSampler(object):
         self._rng.shuffle(data_idxs)
         self._flat = None
         by_idx = None
-        for data_idx in data_idxs:
-            old_node = tree_labels[data_idx]
-            if tree.get_data_len(old_node) > 1:
-                if by_idx is None:
-                    tree = tree.copy()
-                    by_idx = {dp.idx: dp for lst in tree._data.values() for dp in lst}
-                tree_labels[data_idx] = self._move(by_idx[data_idx], tree, old_node)
+        # A move is one synchronising device round trip, and most moves put the point back where it was.  So the
+        # candidates of the next LOOKAHEAD moves are recorded at once, each against the tree its predecessors leave
+        # behind IF they stay put (tile ops are lazy and memoised: recording costs no arithmetic, and "remove + add
+        # back" yields the same tile ids on the look-ahead copy as later on the real tree); one flush scores them
+        # all.  The moves are then drawn one by one exactly as before -- same scores, same RNG calls -- and the first
+        # point that really moves throws the rest of the look-ahead away.
+        ahead = []  # [(position in data_idxs, pending scores | None)]
+        k, n = 0, len(data_idxs)
+        while k < n:
+            if not ahead:
+                t = tree
+                for j in range(k, min(k + self.LOOKAHEAD, n)):
+                    old = tree_labels[data_idxs[j]]
+                    if t.get_data_len(old) <= 1:
+                        ahead.append((j, None))
+                        continue
+                    if by_idx is None:
+                        t = tree = tree.copy()
+                        by_idx = {dp.idx: dp for lst in tree._data.values() for dp in lst}
+                    dp = by_idx[data_idxs[j]]
+                    ahead.append((j, self._score_candidates(t, dp, old)))
+                    if j + 1 < min(k + self.LOOKAHEAD, n):
+                        t = t.copy()
+                        t.remove_data_point_from_node(dp, old)
+                        if old == t.outlier_node_name:
+                            t.add_data_point_to_outliers(dp)
+                        else:
+                            t.add_data_point_to_node(dp, old)
+            j, pending = ahead.pop(0)
+            assert j == k
+            data_idx = data_idxs[k]
+            if pending is not None:
+                old_node = tree_labels[data_idx]
+                new_node = self._move(by_idx[data_idx], tree, old_node, pending)
+                tree_labels[data_idx] = new_node
+                self.moves += 1
+                if new_node == old_node:
+                    self.stays += 1
+                    self.lookahead_hits += 1 if ahead else 0
+                else:
+                    ahead = []
+                    self._flat = None
+            k += 1
         return tree
 
     def _sample_tree(self, data_idx, tree, old_node):
@@ -46,12 +85,13 @@ class DataPointSampler(object):
         self._move(data_point, new_tree, old_node)
         return new_tree
 
-    def _move(self, data_point, tree, old_node):
+    def _move(self, data_point, tree, old_node, pending=None):
         """Draw the node `data_point` moves to and apply the move to `tree` IN PLACE; returns the node's name.
         Every candidate is scored from the one tree by recording the tile ops its two path refreshes would perform
         (remove from `old_node`: refresh old_node..root; add to the new node: log_r += value, refresh its parents up
         to the root); only the candidate that is drawn gets built."""
-        pending = self._score_candidates(tree, data_point, old_node)
+        if pending is None:
+            pending = self._score_candidates(tree, data_point, old_node)
         log_q = np.array([p.resolve()[1] for p in pending])
         log_q = log_normalize(log_q)
         q = np.exp(log_q)
