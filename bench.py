@@ -621,7 +621,7 @@ def run_chains_job(args):
             "sweep": args.sweep, "chains_per_gpu": [len([c for c in range(C) if c % world == r]) for r in range(world)],
             "mps": mps, "per_rank_ms_per_step": [round(x / args.steps, 2) for x in per_rank],
             "rank0_worker_split_ms_per_step": splits,
-            "how": "one worker process per chain, chain c on GPU c % N, CUDA events around each worker's timed steps, max "
+            "how": "one worker process per chain, chain c on GPU c mod N, CUDA events around each worker's timed steps, max "
                    "over workers and ranks; strong scaling: the same %d chains at every N" % C,
         }
         print(json.dumps(line))
