@@ -240,7 +240,9 @@ int pcb_resample_host(const double* W, int64_t N, const double* uniforms, int64_
  * one stream synchronisation at the end.  status: 0 ok, else bit 1 = more than Rmax roots, 2 = tile range exhausted,
  * 4 = kid pool exhausted, 8 = non-finite weights (the sweep's outputs are then void). */
 typedef struct {
-  int32_t N, T, Rmax, conditional, outliers, n_tab, n_ret_kids, reserved;
+  int32_t N, T, Rmax, conditional, outliers, n_tab, n_ret_kids;
+  int32_t perm_dist; /* 1: particle weights carry the root-permutation density (smc/kernels/base.py:49-55,
+                      * smc/utils.py:18-66); the dbl record's 7th entry is then the retained tree's log_pdf */
   double log_alpha, threshold, log_half, log_uniform, lw_uniform, prior;
   uint64_t seed;
   int64_t tile_base, tile_limit;
@@ -252,6 +254,8 @@ typedef struct {
   const uint64_t* ret_key;                       /* [T] */
   const int32_t* ret_kids;                       /* [n_ret_kids] */
   const int32_t *ret_kind, *ret_arg;             /* [T] */
+  const int32_t* ret_subtree_data;               /* [T][Rmax] perm_dist: data points under each root (thawed order) */
+  const double* ret_subtree_log_count;           /* [T][Rmax] perm_dist: log #compatible orders of each root's subtree */
   int32_t *anc, *kind, *name;                    /* [T][N] ancestor of slot i after step t; decision of particle i */
   uint64_t* mask;                                /* [T][N] adopted roots of a new node (positions in the parent) */
   double *raw, *logp, *logq;                     /* [T][N] unnormalised log weight, log_p, proposal log prob */

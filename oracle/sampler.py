@@ -1202,12 +1202,12 @@ def alpha_move(joint, tree, rng, a=0.01, b=0.01):  # concentration.py:29-60, run
 def run_chain(data, rng, num_iters, burnin=1, num_particles=100, proposal="semi-adapted", resample_threshold=0.5,
               outlier_prob=0.0, concentration_value=1.0, concentration_update=True, num_samples_data_point=1,
               num_samples_prune_regraph=1, use_tile_caches=False, on_iteration=None, sweep_log=None,
-              subtree_update_prob=0.0):
+              subtree_update_prob=0.0, perm_dist=False):
     """Returns {"trace": [...], "extensions": int, "convs": int}; trace entry =
     {"iter", "alpha", "log_p_one", "tree": frozen dict, "clades", "outliers"} (run.py:293-302).
     `sweep_log`: a list that receives the step / resample / pick records of every SMC sweep (see `_note`)."""
     tm = TileMath(use_tile_caches)
-    joint = Joint(concentration_value)
+    joint = Joint(concentration_value, perm_dist=perm_dist)
     kernel = KERNELS[proposal](joint, rng, tm, outlier_proposal_prob=0.1 if outlier_prob > 0 else 0.0)
     if sweep_log is not None:
         kernel.sweep_log = sweep_log

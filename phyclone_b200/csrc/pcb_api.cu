@@ -987,6 +987,9 @@ int pcb_smc_sweep_dev(const pcb_arena* a, const pcb_sweep_desc* d, void* stream)
     P.single_id = ci.take<int>(T);
     P.ret_th_int = ci.take<int>(d->conditional ? (size_t)T * irec : 0);
     P.ret_ba_int = ci.take<int>(d->conditional ? (size_t)T * irec : 0);
+    P.cur_dl = ci.take<int>(d->perm_dist ? (size_t)N * Rmax : 0);
+    P.ext_dl = ci.take<int>(d->perm_dist ? (size_t)N * Rmax : 0);
+    P.ret_th_dl = ci.take<int>(d->perm_dist && d->conditional ? (size_t)T * Rmax : 0);
     P.ret_kind = ci.take<int>(d->conditional ? T : 0);
     P.ret_arg = ci.take<int>(d->conditional ? T : 0);
     P.kid_pool = ci.take<int>(pool_cap);
@@ -1032,6 +1035,10 @@ int pcb_smc_sweep_dev(const pcb_arena* a, const pcb_sweep_desc* d, void* stream)
     P.dec_logq = cd.take<double>(N);
     P.dec_lp = cd.take<double>(N);
     P.dec_lp1 = cd.take<double>(N);
+    P.dec_lpdf = cd.take<double>(N);
+    P.cur_lc = cd.take<double>(d->perm_dist ? (size_t)N * Rmax : 0);
+    P.ext_lc = cd.take<double>(d->perm_dist ? (size_t)N * Rmax : 0);
+    P.ret_th_lc = cd.take<double>(d->perm_dist && d->conditional ? (size_t)T * Rmax : 0);
     P.o_raw = cd.take<double>(TN);
     P.o_logp = cd.take<double>(TN);
     P.o_logq = cd.take<double>(TN);
@@ -1068,6 +1075,7 @@ int pcb_smc_sweep_dev(const pcb_arena* a, const pcb_sweep_desc* d, void* stream)
   P.log_alpha = d->log_alpha;
   P.threshold = d->threshold;
   P.log_half = d->log_half;
+  P.perm = d->perm_dist ? 1 : 0;
   P.seed = d->seed;
   P.pool_cap = pool_cap;
   P.tile_limit = (int)d->tile_limit;
@@ -1099,6 +1107,11 @@ int pcb_smc_sweep_dev(const pcb_arena* a, const pcb_sweep_desc* d, void* stream)
     PCB_CUDA(up(P.ret_ba_dbl, d->ret_ba_dbl, (size_t)T * sw::DREC * 8));
     PCB_CUDA(up(P.ret_key, d->ret_key, (size_t)T * 8));
     PCB_CUDA(up(P.ret_kind, d->ret_kind, (size_t)T * 4));
+    if (d->perm_dist) {
+      if (!d->ret_subtree_data || !d->ret_subtree_log_count) return fail(PCB_ERR_ARG, "smc_sweep: perm_dist tables missing");
+      PCB_CUDA(up(P.ret_th_dl, d->ret_subtree_data, (size_t)T * Rmax * 4));
+      PCB_CUDA(up(P.ret_th_lc, d->ret_subtree_log_count, (size_t)T * Rmax * 8));
+    }
     PCB_CUDA(up(P.ret_arg, d->ret_arg, (size_t)T * 4));
     if (n_ret_kids) PCB_CUDA(up(P.kid_pool, d->ret_kids, (size_t)n_ret_kids * 4));
   }

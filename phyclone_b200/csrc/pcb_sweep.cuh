@@ -44,6 +44,12 @@ enum { ST_OK = 0, ST_ROOTS = 1, ST_TILES = 2, ST_POOL = 4, ST_NUMERIC = 8 };
 struct Params {
   int N, T, Rmax, conditional, outliers, S, irec, n_tab;
   int fuse;  // 1: a new node's tile and the score of its tree are ONE two-stage job (PCB_JOB_THEN_SCORE)
+  int perm;  // 1: weights carry the root-permutation density (smc/kernels/base.py:49-55, smc/utils.py:18-66)
+  // per root: data points in its subtree, log number of compatible orders of the subtree   [slot][Rmax]
+  int *cur_dl, *ext_dl;
+  double *cur_lc, *ext_lc, *dec_lpdf;
+  const int* ret_th_dl;
+  const double* ret_th_lc;
   double log_alpha, threshold, log_half;
   u64 seed;
   const int *dp_idx, *value_id, *single_id;
@@ -108,6 +114,8 @@ __device__ inline const int* fld(const int* rec, int f, int Rmax) { return rec +
 struct ParentView {
   const int *pI, *bI;
   const double *pD, *bD;
+  const int* pDl;     // subtree data counts of the roots (thawed order), perm mode only
+  const double* pLc;  // log order counts of the roots' subtrees
   bool ret;
 };
 __device__ inline ParentView parent_view(const Params& p, int t, int i) {
@@ -118,9 +126,13 @@ __device__ inline ParentView parent_view(const Params& p, int t, int i) {
     v.bI = p.ret_ba_int + (size_t)(t - 1) * p.irec;
     v.pD = p.ret_th_dbl + (size_t)(t - 1) * DREC;
     v.bD = p.ret_ba_dbl + (size_t)(t - 1) * DREC;
+    v.pDl = p.perm ? p.ret_th_dl + (size_t)(t - 1) * p.Rmax : nullptr;
+    v.pLc = p.perm ? p.ret_th_lc + (size_t)(t - 1) * p.Rmax : nullptr;
   } else {
     v.pI = v.bI = p.cur_int + (size_t)i * p.irec;
     v.pD = v.bD = p.cur_dbl + (size_t)i * DREC;
+    v.pDl = p.perm ? p.cur_dl + (size_t)i * p.Rmax : nullptr;
+    v.pLc = p.perm ? p.cur_lc + (size_t)i * p.Rmax : nullptr;
   }
   return v;
 }
@@ -167,6 +179,11 @@ __global__ void build_kernel(const Params p, const int t) {
 #pragma unroll 4
     for (int k = lane; k < n4; k += 32) dst[k] = src[k];
     if (lane < DREC) p.cur_dbl[(size_t)i * DREC + lane] = p.ext_dbl[(size_t)a * DREC + lane];
+    if (p.perm)
+      for (int k = lane; k < Rmax; k += 32) {
+        p.cur_dl[(size_t)i * Rmax + k] = p.ext_dl[(size_t)a * Rmax + k];
+        p.cur_lc[(size_t)i * Rmax + k] = p.ext_lc[(size_t)a * Rmax + k];
+      }
     __syncwarp();
   }
   const u64 key = p.cur_key[i];
@@ -278,6 +295,8 @@ __device__ inline int inv_cdf(const double* q, int n, double u) {
   return n - 1;
 }
 
+__device__ inline int eI_R_after(int kind, int R, int k_new) { return kind == K_NEW ? R - k_new + 1 : R; }
+
 __device__ inline int alloc_tiles(const Params& p, int n) {
   const int t0 = atomicAdd(p.tile_top, n);
   if (t0 + n > p.tile_limit) {
@@ -285,6 +304,23 @@ __device__ inline int alloc_tiles(const Params& p, int n) {
     return p.scratch0;  // in bounds; the sweep is void and the host reruns it with a larger arena
   }
   return t0;
+}
+
+// -log(number of root permutations) of a forest from its roots' (log order count, subtree data count), n_all data
+// points of which n_out are outliers: RootPermutationDistribution.log_pdf (smc/utils.py:18-66)
+__device__ inline double perm_log_pdf(const Params& p, const double* lc, const int* dl, int R, int n_all, int n_out) {
+  double count = 0.0;
+  int total = 0;
+  for (int r = 0; r < R; ++r) count += lc[r];
+  if (R > 0) {
+    for (int r = 0; r < R; ++r) total += dl[r];
+    double multi = tab(p.lfact, total, p.n_tab, true);
+    for (int r = 0; r < R; ++r) multi -= tab(p.lfact, dl[r], p.n_tab, true);
+    count += multi;
+  }
+  count += tab(p.lfact, n_all, p.n_tab, true) - tab(p.lfact, n_out, p.n_tab, true) -
+           tab(p.lfact, n_all - n_out, p.n_tab, true);
+  return -count;
 }
 
 constexpr int kMaxRoots = 64;
@@ -688,6 +724,49 @@ __global__ void decide_kernel(const Params p, const int t) {
     name_out = pn;
     mask_out = take;
   }
+  if (p.perm) {
+    // root-permutation density of the new forest minus the parent's (both from the thawed state: the density does not
+    // depend on the order of the roots)
+    int* e_dl = p.ext_dl + (size_t)i * Rmax;
+    double* e_lc = p.ext_lc + (size_t)i * Rmax;
+    const int Rn = eI_R_after(kind, R, k_new);
+    if (lane == 0) {
+      if (kind == K_NEW) {
+        int dsum = 0, w = 1;
+        double csum = 0.0, multi = 0.0;
+        for (int r = 0; r < R; ++r) {
+          if (mask_out >> r & 1ull) {
+            dsum += v.pDl[r];
+            csum += v.pLc[r];
+            multi -= tab(p.lfact, v.pDl[r], p.n_tab, true);
+          } else {
+            e_dl[w] = v.pDl[r];
+            e_lc[w] = v.pLc[r];
+            ++w;
+          }
+        }
+        if (k_new > 0) multi += tab(p.lfact, dsum, p.n_tab, true);
+        e_dl[0] = 1 + dsum;
+        e_lc[0] = csum + multi;  // + log 1! for the node's own single data point
+      } else {
+        for (int r = 0; r < R; ++r) {
+          e_dl[r] = v.pDl[r];
+          e_lc[r] = v.pLc[r];
+        }
+        if (kind == K_ATTACH) {
+          int j = 0;
+          while (j < R && s_nm[j] != name_out) ++j;
+          const int own = s_nd[j];
+          e_dl[j] = v.pDl[j] + 1;
+          e_lc[j] = v.pLc[j] + (tab(p.lfact, own + 1, p.n_tab, true) - tab(p.lfact, own, p.n_tab, true));
+        }
+      }
+      const int out_new = po + (kind == K_OUTLIER ? 1 : 0);
+      const double lpdf_new = perm_log_pdf(p, e_lc, e_dl, Rn, t + 1, out_new);
+      const double lpdf_par = (t == 0) ? 0.0 : perm_log_pdf(p, v.pLc, v.pDl, R, t, po);
+      p.dec_lpdf[i] = lpdf_new - lpdf_par;
+    }
+  }
   if (lane == 0) {
     p.slotE[i] = slot_e;
     p.dec_kind[i] = kind | (v.ret ? FLAG_RETAINED_PARENT : 0);
@@ -744,6 +823,7 @@ __global__ void weigh_kernel(const Params p, const int t, const double log_unifo
       }
       const double plp = p.cur_dbl[(size_t)i * DREC + D_LOGP];  // 0 for the empty start (parent None)
       double w = (lp - plp) - p.dec_logq[i];
+      if (p.perm) w = ((lp - plp) + p.dec_lpdf[i]) - p.dec_logq[i];
       if (last) w = w - lp + lp1;
       p.ext_dbl[(size_t)i * DREC + D_LOGP] = lp;
       p.ext_dbl[(size_t)i * DREC + D_LOGP1] = lp1;
@@ -757,6 +837,10 @@ __global__ void weigh_kernel(const Params p, const int t, const double log_unifo
       const double* rd = p.ret_th_dbl + (size_t)t * DREC;
       const double plp = (t == 0) ? 0.0 : p.ret_th_dbl[(size_t)(t - 1) * DREC + D_LOGP];
       double w = (rd[D_LOGP] - plp) - p.dec_logq[0];
+      if (p.perm) {
+        const double ppdf = (t == 0) ? 0.0 : p.ret_th_dbl[(size_t)(t - 1) * DREC + D_LOGW];
+        w = ((rd[D_LOGP] - plp) + (rd[D_LOGW] - ppdf)) - p.dec_logq[0];  // D_LOGW holds the retained tree's log_pdf
+      }
       if (last) w = w - rd[D_LOGP] + rd[D_LOGP1];
       raw = (t == 0) ? log_uniform : p.lw[0] + w;
       p.o_logp[(size_t)t * N] = rd[D_LOGP];
@@ -773,6 +857,11 @@ __global__ void weigh_kernel(const Params p, const int t, const double log_unifo
     for (int k = threadIdx.x; k < p.irec; k += blockDim.x) p.ext_int[k] = ri[k];
     if (threadIdx.x < DREC) p.ext_dbl[threadIdx.x] = p.ret_th_dbl[(size_t)t * DREC + threadIdx.x];
     if (threadIdx.x == 0) p.ext_key[0] = p.ret_key[t];
+    if (p.perm)
+      for (int k = threadIdx.x; k < p.Rmax; k += blockDim.x) {
+        p.ext_dl[k] = p.ret_th_dl[(size_t)t * p.Rmax + k];
+        p.ext_lc[k] = p.ret_th_lc[(size_t)t * p.Rmax + k];
+      }
   }
   // ---- log_Z, log_W, W, ESS
   const double m = block_max(raw, sh_red);

@@ -39,10 +39,10 @@ class Timer(object):
         self._start = None
 
 
-def setup_kernel(outlier_prob, proposal, rng, tree_dist, store):
+def setup_kernel(outlier_prob, proposal, rng, tree_dist, store, perm_dist=None):
     """run.py:403-417"""
     outlier_proposal_prob = 0.1 if outlier_prob > 0 else 0
-    return KERNELS[proposal](tree_dist, rng, store, outlier_proposal_prob=outlier_proposal_prob)
+    return KERNELS[proposal](tree_dist, rng, store, outlier_proposal_prob=outlier_proposal_prob, perm_dist=perm_dist)
 
 
 class Chain(object):
@@ -51,7 +51,8 @@ class Chain(object):
 
     def __init__(self, data, rng, num_particles=100, proposal="semi-adapted", resample_threshold=0.5, outlier_prob=0.0,
                  concentration_value=1.0, concentration_update=True, num_samples_data_point=1,
-                 num_samples_prune_regraph=1, device=None, store=None, sweep="host", subtree_update_prob=0.0):
+                 num_samples_prune_regraph=1, device=None, store=None, sweep="host", subtree_update_prob=0.0,
+                 perm_dist=None):
         self.data = data
         self.rng = rng
         # the tree walks recurse once per level and a forest over T data points can be T deep
@@ -61,7 +62,7 @@ class Chain(object):
             store = TileStore(np.array([dp.value for dp in data]), device=device, variant=TileStore.LATENCY_LAYOUT)
         self.store = store
         self.tree_dist = TreeJointDistribution(FSCRPDistribution(concentration_value))
-        self.kernel = setup_kernel(outlier_prob, proposal, rng, self.tree_dist, store)
+        self.kernel = setup_kernel(outlier_prob, proposal, rng, self.tree_dist, store, perm_dist=perm_dist)
         self.dp_sampler = DataPointSampler(self.tree_dist, rng, outliers=(outlier_prob > 0))
         self.prg_sampler = PruneRegraphSampler(self.tree_dist, rng)
         self.conc_sampler = GammaPriorConcentrationSampler(0.01, 0.01, rng=rng)

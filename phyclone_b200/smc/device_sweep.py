@@ -35,12 +35,13 @@ class SweepDesc(C.Structure):
     """include/phyclone_b200.h: pcb_sweep_desc"""
 
     _fields_ = (
-        [(n, C.c_int32) for n in ("N", "T", "Rmax", "conditional", "outliers", "n_tab", "n_ret_kids", "reserved")]
+        [(n, C.c_int32) for n in ("N", "T", "Rmax", "conditional", "outliers", "n_tab", "n_ret_kids", "perm_dist")]
         + [(n, C.c_double) for n in ("log_alpha", "threshold", "log_half", "log_uniform", "lw_uniform", "prior")]
         + [("seed", _u64), ("tile_base", C.c_int64), ("tile_limit", C.c_int64)]
         + [(n, C.c_void_p) for n in (
             "dp_idx", "value_id", "single_id", "dp_op", "dp_opn", "dp_marg", "lfact", "logn", "rterm", "ret_th_int",
-            "ret_ba_int", "ret_th_dbl", "ret_ba_dbl", "ret_key", "ret_kids", "ret_kind", "ret_arg", "anc", "kind", "name", "mask", "raw", "logp",
+            "ret_ba_int", "ret_th_dbl", "ret_ba_dbl", "ret_key", "ret_kids", "ret_kind", "ret_arg", "ret_subtree_data",
+            "ret_subtree_log_count", "anc", "kind", "name", "mask", "raw", "logp",
             "logq", "ess", "resampled", "final_idx", "status", "tiles_used", "n_launches", "conv_pairs", "device_ms")]
     )
 
@@ -87,6 +88,7 @@ class DeviceSweep(object):
         self.store = kernel.store
         self.N = int(num_particles)
         self.threshold = float(resample_threshold)
+        self.perm = kernel.perm_dist is not None  # weights carry the root-permutation density (kernels/base.py:49-55)
         self.lib = _lib.require_device()
         self.stats = {"sweeps": 0, "fallbacks": 0, "launches": 0, "device_ms": 0.0, "conv_pairs": 0, "tiles": 0,
                       "h2d_bytes": 0, "d2h_bytes": 0}
@@ -118,8 +120,22 @@ class DeviceSweep(object):
             th_d[t, 4], th_d[t, 5] = holder.log_p, holder.log_p_one  # the first read scores the whole path: one flush
         # "equal particle" exactly as the host sampler tests it (kernels.get_proposal_distribution)
         keys = np.array([path[t + 1]._holder.vkey[0] for t in range(T)], dtype=np.uint64)
+        sub_n = sub_c = None
+        if self.perm:
+            # root-permutation density (smc/utils.py:18-66): the retained trees' log_pdf and, per root of the thawed
+            # state, the data points below it and the log number of compatible orders of its subtree
+            from .utils import RootPermutationDistribution as RPD
+
+            sub_n = np.zeros((T, rmax), dtype=np.int32)
+            sub_c = np.zeros((T, rmax), dtype=np.float64)
+            for t in range(T):
+                holder = path[t + 1]._holder
+                th_d[t, 6] = RPD.log_pdf(holder._built)
+                tree = holder._thawed
+                for r, node in enumerate(th[t].roots):
+                    sub_c[t, r], sub_n[t, r] = RPD.subtree_terms(tree, node)
         return (np.frombuffer(th_i, dtype=np.int32), np.frombuffer(ba_i, dtype=np.int32), th_d,
-                np.frombuffer(ba_d, dtype=np.float64), keys, np.frombuffer(kids, dtype=np.int32))
+                np.frombuffer(ba_d, dtype=np.float64), keys, np.frombuffer(kids, dtype=np.int32), sub_n, sub_c)
 
     def _outputs(self, T):
         N = self.N
@@ -147,7 +163,7 @@ class DeviceSweep(object):
         lfact, logn, rterm = _prior_tables(prior, n_tab)
         conditional = path is not None
         if conditional:
-            th_i, ba_i, th_d, ba_d, keys, kids = self._pack_retained(path, rmax)
+            th_i, ba_i, th_d, ba_d, keys, kids, sub_n, sub_c = self._pack_retained(path, rmax)
         store.flush()  # every tile the retained path refers to must exist before the sweep reads it
         tuples = [host_tuple(store, dp) for dp in sigma]
         dp_idx = np.array([t[0] for t in tuples], dtype=np.int32)
@@ -167,6 +183,7 @@ class DeviceSweep(object):
         d = SweepDesc()
         d.N, d.T, d.Rmax, d.conditional = N, T, rmax, 1 if conditional else 0
         d.outliers = 1 if self.kernel.outlier_proposal_prob > 0 else 0
+        d.perm_dist = 1 if self.perm else 0
         d.n_tab, d.n_ret_kids = n_tab, (len(kids) if conditional else 0)
         d.log_alpha, d.threshold, d.log_half = float(prior.log_alpha), self.threshold, float(self.kernel.log_half)
         # swarm.log_weights of N particles at the uniform weight: lu - (log(sum of N exp(0)) + lu)  (swarm.py:33-44)
@@ -183,6 +200,9 @@ class DeviceSweep(object):
             ret = [th_i, ba_i, th_d, ba_d, keys, kids, ret_kind, ret_arg]
             (d.ret_th_int, d.ret_ba_int, d.ret_th_dbl, d.ret_ba_dbl, d.ret_key, d.ret_kids, d.ret_kind,
              d.ret_arg) = [_ptr(a) if a.size else None for a in ret]
+            if self.perm:
+                ret += [sub_n, sub_c]
+                d.ret_subtree_data, d.ret_subtree_log_count = _ptr(sub_n), _ptr(sub_c)
             h2d += sum(a.nbytes for a in ret)
         (d.anc, d.kind, d.name, d.mask, d.raw, d.logp, d.logq, d.ess, d.resampled, d.final_idx, d.status, d.tiles_used,
          d.n_launches, d.conv_pairs, d.device_ms) = [_ptr(o[k]) for k in (

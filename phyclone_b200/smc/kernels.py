@@ -78,7 +78,9 @@ class Kernel(object):
         return self._dist_cache.get(key, lambda: self._make_proposal(data_point, parent_particle, parent_tree))
 
     def create_particle(self, log_q, parent_particle, tree_holder):
-        """base.py:38-57; log_w = log_p - parent.log_p - log_q is finalised lazily by `Particle.log_w`."""
+        """base.py:38-57; log_w = log_p - parent.log_p - log_q is finalised lazily by `Particle.log_w`.  The
+        root-permutation density (`perm_dist`, base.py:49-55; None in production, run.py:403-417) enters the weights
+        of the device-resident sweep only (smc/device_sweep.py): the retained path built here never reads them."""
         return Particle(log_q, parent_particle, tree_holder)
 
     def propose_particle(self, data_point, parent_particle):

@@ -44,6 +44,8 @@ class AbstractSMCSampler(object):
         self._rng = kernel.rng
 
     def sample(self):
+        if self.kernel.perm_dist is not None:
+            raise NotImplementedError("perm_dist is implemented by the device-resident sweep only (sweep='device')")
         self._init_swarm()
         self._resample_swarm()
         while self.iteration < self.num_iterations:

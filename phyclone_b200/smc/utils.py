@@ -26,7 +26,57 @@ def _subtree_order(tree, rng, node):
     return below
 
 
+def _log_factorial(n):
+    from ..utils.math import cached_log_factorial
+
+    return cached_log_factorial(n)
+
+
+def _log_multinomial(sizes):
+    """utils/math.py:159-177"""
+    if len(sizes) == 0:
+        return 0
+    result = _log_factorial(sum(sizes))
+    for x in sizes:
+        result -= _log_factorial(x)
+    return result
+
+
 class RootPermutationDistribution(object):
+    @staticmethod
+    def subtree_terms(tree, node):
+        """(log number of compatible orders of the subtree under `node`, data points in it): smc/utils.py:41-62"""
+        count, sizes = 0, []
+        for child in tree.get_children(node):
+            c, n = RootPermutationDistribution.subtree_terms(tree, child)
+            count += c
+            sizes.append(n)
+        own = tree.get_data_len(node)
+        count += _log_multinomial(sizes)
+        count += _log_factorial(own)
+        return count, own + sum(sizes)
+
+    @staticmethod
+    def log_count(tree, source=None):
+        """smc/utils.py:18-62"""
+        if source is not None:
+            return RootPermutationDistribution.subtree_terms(tree, source)[0]
+        from ..utils.math import log_binomial_coefficient
+
+        count, sizes = 0, []
+        for node in tree.roots:
+            c, n = RootPermutationDistribution.subtree_terms(tree, node)
+            count += c
+            sizes.append(n)
+        count += _log_multinomial(sizes)
+        count += log_binomial_coefficient(len(tree.data), len(tree.outliers))
+        return count
+
+    @staticmethod
+    def log_pdf(tree):
+        """smc/utils.py:64-66"""
+        return -RootPermutationDistribution.log_count(tree)
+
     @staticmethod
     def sample(tree, rng, source=None):
         if source is not None:

@@ -44,7 +44,7 @@ def _close(a, b, what, tol=1e-9):
     return float(err.max())
 
 
-def _compare_chain(vals, probs, particles, outlier_prob, burnin, iters, seed, what):
+def _compare_chain(vals, probs, particles, outlier_prob, burnin, iters, seed, what, perm_dist=False):
     from phyclone_b200.data.base import make_data_points
     from phyclone_b200.run import Chain
 
@@ -54,10 +54,13 @@ def _compare_chain(vals, probs, particles, outlier_prob, burnin, iters, seed, wh
         odata = [osm.Datum(i, v, outlier_prob=probs[i][0], outlier_prob_not=probs[i][1]) for i, v in enumerate(vals)]
     log = []
     want = osm.run_chain(odata, SweepRNG(np.random.default_rng(seed)), iters, burnin=burnin, num_particles=particles,
-                         outlier_prob=outlier_prob, sweep_log=log)
+                         outlier_prob=outlier_prob, sweep_log=log, perm_dist=perm_dist)
     sweeps = _sweeps(log)
+    from phyclone_b200.smc.utils import RootPermutationDistribution
+
     chain = Chain(make_data_points(vals, outlier_probs=probs), np.random.default_rng(seed), num_particles=particles,
-                  outlier_prob=outlier_prob, sweep="device")
+                  outlier_prob=outlier_prob, sweep="device",
+                  perm_dist=RootPermutationDistribution() if perm_dist else None)
     hist_b, hist_m = [], []
     chain.burnin_sampler._device.history = hist_b
     chain.tree_sampler._device.history = hist_m
@@ -116,6 +119,49 @@ def test_device_sweep_matches_uniform_oracle(name, particles, iters):
     if float(g["outlier_prob_run"]) > 0:
         probs = [(float(g["outlier_prob"][i]), float(g["outlier_prob_not"][i])) for i in range(len(vals))]
     _compare_chain(vals, probs, particles, float(g["outlier_prob_run"]), 1, iters, 11, name)
+
+
+@pytest.mark.parametrize("name,particles,iters", [("syn12", 16, 6), ("syn8_outliers", 12, 6)])
+def test_device_sweep_with_root_permutation_density(name, particles, iters):
+    """The same comparison with `perm_dist` on: particle weights carry the root-permutation density
+    (smc/kernels/base.py:49-55, smc/utils.py:18-66), as in the reference's posterior tests."""
+    g = load_chain(name)
+    vals = g["values"]
+    probs = None
+    if float(g["outlier_prob_run"]) > 0:
+        probs = [(float(g["outlier_prob"][i]), float(g["outlier_prob_not"][i])) for i in range(len(vals))]
+    _compare_chain(vals, probs, particles, float(g["outlier_prob_run"]), 1, iters, 13, name + " + perm_dist", perm_dist=True)
+
+
+def test_device_mode_samples_the_exact_posterior():
+    """The reference's own statistical check of its particle-Gibbs sampler (tests/test_pg_posterior.py:15-158: kernel
+    with the root-permutation density, 10 particles, delta 0.03) run on the device-resident sweep: clade-set
+    frequencies of 2000 PG sweeps against the exact FS-CRP posterior obtained by enumeration."""
+    from collections import Counter
+
+    from phyclone_b200.data.base import make_data_points
+    from phyclone_b200.run import Chain
+    from phyclone_b200.smc.utils import RootPermutationDistribution
+    from tests.posterior_utils import CASES, exact_posterior
+
+    for name in ("two_points_non_informative", "two_points_two_clusters", "three_points_non_informative",
+                 "two_points_2d_two_clusters"):
+        data = CASES[name](np.random.default_rng(12345))
+        truth = exact_posterior(data)
+        chain = Chain(make_data_points(np.array([d.value for d in data])), np.random.default_rng(7), num_particles=10,
+                      sweep="device", perm_dist=RootPermutationDistribution())
+        tree = chain.tree
+        counts = Counter()
+        for it in range(-100, 2000):
+            chain.kernel.clear_proposal_dist_caches()
+            chain.store.reset()
+            tree = chain.tree_sampler.sample_tree(tree)
+            if it > 0:
+                counts[_clades(tree)] += 1
+        total = sum(counts.values())
+        err = max(abs(counts[k] / total - p) for k, p in truth.items())
+        print("%s: %d forests, max |device frequency - exact posterior| = %.4f" % (name, len(truth), err))
+        assert err <= 0.03, (name, err)
 
 
 def test_device_sweep_at_bench_config():
