@@ -516,8 +516,8 @@ def run_ours(args):
         ext = (s1["extensions"] - s0["extensions"]) * world
         traffic, traffic_src = None, None
         try:  # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture of this command
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_node_jobs_traffic.json")))
-            traffic, traffic_src = tj["dram_bytes_per_launch"], "profiles/r1_node_jobs_traffic.json (ncu --set full)"
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r2_node_jobs_traffic.json")))
+            traffic, traffic_src = tj["dram_bytes_per_launch"], "profiles/r2_node_jobs_traffic.json (ncu --set full)"
         except Exception:  # noqa: BLE001
             pass
         line = {
