@@ -601,6 +601,10 @@ def run_chains_job(args):
             dist.barrier()
 
     with MpsServer(enable=len(mine) > 1) as server:
+        if server.started:
+            # the daemon was started seeing this rank's GPU only and exposes it as ITS device 0: clients index into the
+            # server's enumeration, not the machine's
+            os.environ["CUDA_VISIBLE_DEVICES"] = "0"
         rate, ev_ms, splits = run_chains_once(len(mine), args.steps, args.warmup, timeout=900, config=CFG["config_number"],
                                               sweep=args.sweep, device=0, chains=mine, n_chains=C, before_go=go,
                                               details=True)
