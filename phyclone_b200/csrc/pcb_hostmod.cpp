@@ -808,6 +808,163 @@ FState* fstate_extend(FState* self, Book* book, int kind, const DataPt& dp, PyOb
   }
 }
 
+// extend_built(book, kind, dp, arg) -> AS-BUILT successor state, or None if the arena is full.
+// The state of the tree the reference builds by editing in place (no from_dict round trip), as the retained path of a
+// conditional sweep does (smc/samplers/conditional.py:19-74): `arg` = node name (ATTACH) or the children in ADOPTION
+// order (NEW).  Differences from `extend` (the re-read tree): a new node's children fold in reversed adoption order
+// (every adopted edge goes to the head of the adjacency list), the node is created empty and then takes the data point,
+// and a node that takes a data point gets `log_r += value` instead of a re-fold (tree/tree_node.py:42-52).
+FState* fstate_extend_built(FState* self, Book* book, int kind, const DataPt& dp, PyObject* arg, int* status) {
+  *status = -1;
+  if (kind == K_OUTLIER) return fstate_extend(self, book, kind, dp, arg, status);
+  const size_t R = self->roots->size();
+  if (kind == K_ATTACH) {
+    const long node = PyLong_AsLong(arg);
+    if (node == -1 && PyErr_Occurred()) return nullptr;
+    const int j = index_of(self, node);
+    if (j < 0) {
+      PyErr_SetString(PyExc_KeyError, "node is not a root of this state");
+      return nullptr;
+    }
+    const int lp_old = (*self->lp)[j], lr_old = (*self->lr)[j];
+    const int lp_new = lp_old == book->prior_id ? dp.single_id : book_add(book, lp_old, dp.value_id, false);
+    if (lp_new < 0) {
+      *status = 1;
+      return nullptr;
+    }
+    const int lr_new = lr_old == lp_old ? lp_new : book_add(book, lr_old, dp.value_id, false);
+    if (lr_new < 0) {
+      *status = 1;
+      return nullptr;
+    }
+    // everything but the two tiles is what `extend` computes
+    FState* s = fstate_alloc();
+    if (!s) return nullptr;
+    const int n = (*self->ndata)[j];
+    *s->roots = *self->roots;
+    *s->kids = *self->kids;
+    *s->size = *self->size;
+    *s->slot = *self->slot;
+    *s->gidx = *self->gidx;
+    *s->lp = *self->lp;
+    *s->lr = *self->lr;
+    *s->ndata = *self->ndata;
+    (*s->lp)[j] = lp_new;
+    (*s->lr)[j] = lr_new;
+    (*s->ndata)[j] = n + 1;
+    s->n_nodes = self->n_nodes;
+    s->n_slots = self->n_slots;
+    s->n_edges = self->n_edges;
+    s->n_out = self->n_out;
+    s->omarg = self->omarg;
+    s->oprior = (dp.op != 0.0) ? self->oprior + dp.opn : self->oprior;
+    s->mult = self->mult;
+    s->crp = self->crp + (n >= 1 ? lf(n) - lf(n - 1) : 0.0);
+    s->skey = self->skey ^ data_hash(node, n, dp.idx);
+    s->last_added = node;
+    s->has_last = 1;
+    *status = 0;
+    return s;
+  }
+  // NEW
+  std::vector<long> adopted;
+  if (!longs_of(arg, adopted)) return nullptr;
+  std::vector<int> order;
+  for (long c : adopted) {
+    const int j = index_of(self, c);
+    if (j < 0) {
+      PyErr_SetString(PyExc_KeyError, "child is not a root of this state");
+      return nullptr;
+    }
+    order.push_back(j);
+  }
+  std::vector<int> nk;
+  for (size_t i = order.size(); i-- > 0;) nk.push_back((*self->lr)[order[i]]);
+  // the node is created without data (log_p = the prior tile, log_r = log_p + log_S(children) or log_p itself) ...
+  const int lr_empty = nk.empty() ? book->prior_id : book_node(book, book->prior_id, nk);
+  if (lr_empty < 0) {
+    *status = 1;
+    return nullptr;
+  }
+  // ... and then takes the point: log_p becomes the singleton tile, log_r += value (its own tile even for a leaf)
+  const int lr_new = book_add(book, lr_empty, dp.value_id, false);
+  if (lr_new < 0) {
+    *status = 1;
+    return nullptr;
+  }
+  std::vector<char> taken(R, 0);
+  for (int j : order) taken[(size_t)j] = 1;
+  FState* s = fstate_alloc();
+  if (!s) return nullptr;
+  const long name = self->n_nodes, gi = self->n_slots, root_gi = 0;
+  int sz = 1;
+  for (int j : order) sz += (*self->size)[j];
+  s->roots->push_back(name);
+  s->lr->push_back(lr_new);
+  s->lp->push_back(dp.single_id);
+  s->kids->push_back(nk);
+  s->ndata->push_back(1);
+  s->size->push_back(sz);
+  s->slot->push_back((int)self->n_edges);
+  s->gidx->push_back((int)gi);
+  for (size_t j = 0; j < R; ++j)
+    if (!taken[j]) {
+      s->roots->push_back((*self->roots)[j]);
+      s->lr->push_back((*self->lr)[j]);
+      s->lp->push_back((*self->lp)[j]);
+      s->kids->push_back((*self->kids)[j]);
+      s->ndata->push_back((*self->ndata)[j]);
+      s->size->push_back((*self->size)[j]);
+      s->slot->push_back((*self->slot)[j]);
+      s->gidx->push_back((*self->gidx)[j]);
+    }
+  const long k = (long)order.size();
+  s->n_nodes = self->n_nodes + 1;
+  s->n_slots = self->n_slots + 1;
+  s->n_edges = self->n_edges + 1;
+  s->n_out = self->n_out;
+  s->omarg = self->omarg;
+  s->oprior = (dp.op != 0.0) ? self->oprior + dp.opn : self->oprior;
+  s->mult = self->mult - lf((long)R) + lf((long)R - k + 1) + lf(k);
+  s->crp = self->crp;
+  uint64_t key = self->skey ^ edge_hash(self->n_edges, root_gi, gi) ^ data_hash(name, 0, dp.idx);
+  for (int j : order) {
+    const long e = (*self->slot)[j], c = (*self->gidx)[j];
+    key ^= edge_hash(e, root_gi, c) ^ edge_hash(e, gi, c);
+  }
+  s->skey = key;
+  s->last_added = name;
+  s->has_last = 1;
+  *status = 0;
+  return s;
+}
+
+PyObject* FState_extend_built(FState* self, PyObject* args) {
+  Book* book;
+  int kind;
+  PyObject *dpo, *arg;
+  if (!PyArg_ParseTuple(args, "O!iOO", &BookType, &book, &kind, &dpo, &arg)) return nullptr;
+  DataPt dp;
+  if (!parse_dp(dpo, dp)) return nullptr;
+  int status = 0;
+  FState* s = fstate_extend_built(self, book, kind, dp, arg, &status);
+  if (status == 1) Py_RETURN_NONE;
+  return (PyObject*)s;
+}
+
+// score_self(book, log_alpha) -> (prior_p, prior_one, sid or -1): the state's own tree score
+// (tree/distributions.py:186-206), the data terms as a lazy score handle
+PyObject* FState_score_self(FState* self, PyObject* args) {
+  Book* book;
+  double log_alpha;
+  if (!PyArg_ParseTuple(args, "O!d", &BookType, &book, &log_alpha)) return nullptr;
+  double lp, lp1;
+  priors(log_alpha, self->n_nodes, self->crp, self->mult, self->size->data(), self->size->size(), self->oprior,
+         self->omarg, lp, lp1);
+  const int sid = self->lr->empty() ? -1 : book_score(book, *self->lr);
+  return Py_BuildValue("(ddi)", lp, lp1, sid);
+}
+
 // score_attach_all(book, dp, nodes, log_alpha) -> [(prior_p, prior_one, score id, n children of node)] | None
 PyObject* FState_score_attach_all(FState* self, PyObject* args) {
   Book* book;
@@ -1042,6 +1199,8 @@ PyObject* mod_pack_states(PyObject*, PyObject* args) {
 PyMethodDef FState_methods[] = {
     {"export", (PyCFunction)FState_export, METH_NOARGS, "all fields as a tuple"},
     {"extend", (PyCFunction)FState_extend, METH_VARARGS, "thawed successor state (None if the arena is full)"},
+    {"extend_built", (PyCFunction)FState_extend_built, METH_VARARGS, "as-built successor state (None if the arena is full)"},
+    {"score_self", (PyCFunction)FState_score_self, METH_VARARGS, "(prior_p, prior_one, score id | -1) of the state's own tree"},
     {"score_attach_all", (PyCFunction)FState_score_attach_all, METH_VARARGS, ""},
     {"score_new", (PyCFunction)FState_score_new, METH_VARARGS, ""},
     {"score_outlier", (PyCFunction)FState_score_outlier, METH_VARARGS, ""},

@@ -28,14 +28,17 @@ class ParticleGibbsTreeSampler(object):
         """The same move with the sweep itself on the device (smc/device_sweep.py): sigma and the retained path are
         built here, one seed is drawn from the chain's Generator, everything between the first proposal and the
         final pick happens in `pcb_smc_sweep_dev`."""
-        from ..smc.device_sweep import SweepFallback
+        from ..smc.device_sweep import RetainedPath, SweepFallback
 
         data_sigma = RootPermutationDistribution.sample(tree, self._rng)
         seed = int(self._rng.integers(0, 1 << 62))
-        sampler = ConditionalSMCSampler(tree, data_sigma, self.kernel, num_particles=self.num_particles,
-                                        resample_threshold=self.resample_threshold, with_proposals=False)
         try:
-            return self._device.run(data_sigma, seed, sampler.constrained_path, sampler.path_edits)
+            if self._device.perm:
+                # the root-permutation density is a function of whole trees: build the retained trees
+                sampler = ConditionalSMCSampler(tree, data_sigma, self.kernel, num_particles=self.num_particles,
+                                                resample_threshold=self.resample_threshold, with_proposals=False)
+                return self._device.run(data_sigma, seed, sampler.constrained_path, sampler.path_edits)
+            return self._device.run(data_sigma, seed, RetainedPath(tree, data_sigma, self.kernel))
         except SweepFallback:
             self._device.stats["fallbacks"] += 1
             sampler = ConditionalSMCSampler(tree, data_sigma, self.kernel, num_particles=self.num_particles,

@@ -69,6 +69,90 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+class RetainedPath(object):
+    """The retained path of a conditional sweep (smc/samplers/conditional.py:19-74) as root-level states, without
+    building the T trees: per data point the edit the current tree dictates, the as-built state (the tree the
+    reference grows by editing in place: what the path's own proposals are scored on) and the thawed state (that tree
+    re-read through `Tree.from_dict`: what extends a particle), both kept by the host extension
+    (`ForestState.extend_built` / `extend`), plus the as-built tree's score.  A `Tree` is replayed only where the
+    picked lineage touches the path (`tree(t)`)."""
+
+    def __init__(self, tree, sigma, kernel):
+        from .forest_state import OUTLIER, ensure_tables
+
+        store = kernel.store
+        book = store.book
+        prior = kernel.tree_dist.prior
+        ensure_tables(prior, store.T + 2)
+        log_alpha = float(prior.log_alpha)
+        labels = tree.labels
+        outlier = tree.outlier_node_name
+        node_map = {}
+        th = ba = ForestState.empty(store)
+        self.store, self.sigma, self.grid_size = store, sigma, sigma[0].grid_size
+        self.thawed, self.built, self.edits, self.args, self._scores = [], [], [], [], []
+        for dp in sigma:
+            t = host_tuple(store, dp)
+            old = labels[dp.idx]
+            if old == outlier:
+                kind, arg, edit = OUTLIER, None, (2, 0)
+            elif old in node_map:
+                kind, arg = ATTACH, node_map[old]
+                edit = (0, int(arg))
+            else:
+                arg = tuple(node_map[c] for c in tree.get_children(old))  # adoption order (conditional.py:55-58)
+                kind, edit = NEW, (1, len(arg))
+                node_map[old] = th.n_nodes
+            th = self._step(th.extend, kind, t, arg)
+            ba = self._step(ba.extend_built, kind, t, arg)
+            self.thawed.append(th)
+            self.built.append(ba)
+            self.edits.append(edit)
+            self.args.append((kind, arg))
+            self._scores.append(ba.score_self(book, log_alpha))
+        self._replayed = (0, None)  # (data points replayed, thawed tree)
+
+    def _step(self, fn, kind, t, arg):
+        book = self.store.book
+        s = fn(book, kind, t, arg)
+        if s is None:  # arena full: grow it and record again (ops already recorded are memoised)
+            self.store._grow()
+            s = fn(book, kind, t, arg)
+        return s
+
+    def scores(self):
+        """[(log_p, log_p_one)] of the T retained trees; the first read flushes the store (one batched evaluation)."""
+        out = []
+        for pp, p1, sid in self._scores:
+            if sid >= 0:
+                lse_sum, last_sum = self.store.value(sid)
+                pp, p1 = pp + lse_sum, p1 + last_sum
+            out.append((pp, p1))
+        return out
+
+    def tree(self, t):
+        """The retained particle after `t` data points as the reference's `particle.tree` (a from_dict round trip of
+        the as-built tree): the path's edits replayed on a `Tree`, re-read after every edit."""
+        done, tree = self._replayed
+        if tree is None or done > t:
+            done, tree = 0, Tree(self.grid_size, self.store)
+        for k in range(done, t):
+            dp = self.sigma[k]
+            kind, arg = self.args[k]
+            tree = tree.copy()
+            if kind == ATTACH:
+                tree.add_data_point_to_node(dp, arg)
+            elif kind == NEW:
+                node = tree.create_root_node(arg)
+                tree.add_data_point_to_node(dp, node)
+            else:
+                tree.add_data_point_to_outliers(dp)
+            tree.outliers  # noqa: B018 -- same key-creation side effect as scoring the as-built tree
+            tree = tree.thawed_copy()
+        self._replayed = (t, tree)
+        return tree.copy()
+
+
 class SweepFallback(Exception):
     """The sweep cannot run on the device (a forest with more than 64 roots, a tree with graph vacancies ...):
     the caller runs the host sampler instead."""
@@ -137,6 +221,19 @@ class DeviceSweep(object):
         return (np.frombuffer(th_i, dtype=np.int32), np.frombuffer(ba_i, dtype=np.int32), th_d,
                 np.frombuffer(ba_d, dtype=np.float64), keys, np.frombuffer(kids, dtype=np.int32), sub_n, sub_c)
 
+    def _pack_states(self, rp, rmax):
+        """The same tables from a `RetainedPath` (no trees involved)."""
+        T = len(rp.thawed)
+        try:
+            th_i, ba_i, th_d, ba_d, kids = _hm.pack_states(rp.thawed, rp.built, rmax)
+        except OverflowError as e:
+            raise SweepFallback(str(e))
+        th_d = np.frombuffer(th_d, dtype=np.float64).reshape(T, DREC).copy()
+        th_d[:, 4:6] = rp.scores()
+        keys = np.array([s.skey for s in rp.thawed], dtype=np.uint64)
+        return (np.frombuffer(th_i, dtype=np.int32), np.frombuffer(ba_i, dtype=np.int32), th_d,
+                np.frombuffer(ba_d, dtype=np.float64), keys, np.frombuffer(kids, dtype=np.int32), None, None)
+
     def _outputs(self, T):
         N = self.N
         o = self._out
@@ -162,7 +259,10 @@ class DeviceSweep(object):
         n_tab = max(T + 3, rmax + 3, 8)
         lfact, logn, rterm = _prior_tables(prior, n_tab)
         conditional = path is not None
-        if conditional:
+        if isinstance(path, RetainedPath):
+            th_i, ba_i, th_d, ba_d, keys, kids, sub_n, sub_c = self._pack_states(path, rmax)
+            path_edits = path.edits
+        elif conditional:
             th_i, ba_i, th_d, ba_d, keys, kids, sub_n, sub_c = self._pack_retained(path, rmax)
         store.flush()  # every tile the retained path refers to must exist before the sweep reads it
         tuples = [host_tuple(store, dp) for dp in sigma]
@@ -237,14 +337,15 @@ class DeviceSweep(object):
         anc, kind, name, mask = o["anc"], o["kind"], o["name"], o["mask"]
         i = int(o["final"][0])
         edits, tree, t = [], None, T - 1
+        retained = (lambda n: path.tree(n)) if isinstance(path, RetainedPath) else (lambda n: path[n].tree)
         while True:
             if path is not None and i == 0:
-                tree = path[t + 1].tree
+                tree = retained(t + 1)
                 break
             k = int(kind[t, i])
             edits.append((t, k & 7, int(name[t, i]), int(mask[t, i])))
             if k & FLAG_RETAINED_PARENT:
-                tree = path[t].tree
+                tree = retained(t)
                 break
             if t == 0:
                 tree = Tree(sigma[0].grid_size, self.store)
