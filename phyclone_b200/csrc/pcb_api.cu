@@ -48,9 +48,12 @@ int jobs_double_b() {
   }
   return v;
 }
-size_t jobs_smem_bytes(int RB, int pitch) {
-  return pcb::kSmemHead + (jobs_double_b() ? 3ull : 2ull) * RB * pitch * 8 + pcb::kSmemTail;
+// A, B (+ a second operand buffer with PCB_NBUF=3, or the output buffer O of the multi-round kernel)
+size_t jobs_smem_bytes(int RB, int pitch, bool multi = false) {
+  return pcb::kSmemHead + ((jobs_double_b() || multi) ? 3ull : 2ull) * RB * pitch * 8 + pcb::kSmemTail;
 }
+
+constexpr int kMaxGrid = 8192;  // three rows of a tile in shared memory
 
 size_t wide_smem_bytes(int P, int pitch) {
   return pcb::kSmemHead + 2ull * 32 * pitch * 8 + (size_t)P * 32 * 8 + 32 * 8 + pcb::kSmemTail;
@@ -84,19 +87,23 @@ int fill_layout_wide(int S, int G, int L, pcb_layout* out) {
 }
 
 int fill_layout(int S, int G, int L, int P, pcb_layout* out) {
-  if (S < 1 || G < 1 || G > 1088) return fail(PCB_ERR_ARG, "layout: need S >= 1 and 1 <= G <= 1088");
+  if (S < 1 || G < 1 || G > kMaxGrid) return fail(PCB_ERR_ARG, "layout: need S >= 1 and 1 <= G <= 8192");
   bool okL = false;
   for (int l : kStrips) okL |= (l == L);
   if (!okL || (P != 4 && P != 8 && P != 16 && P != 32)) return fail(PCB_ERR_ARG, "layout: unsupported strip/lanes");
   const int Q = (G + L - 1) / L;
-  if ((Q + 1) / 2 > P) return fail(PCB_ERR_ARG, "layout: lanes_per_row must cover ceil(Q/2) strip pairs");
+  // more strip pairs than lanes: only the widest configuration walks several pairs per lane (grids beyond 1088)
+  const int rounds = ((Q + 1) / 2 + P - 1) / P;
+  if (rounds > 1 && !(L == 17 && P == 32))
+    return fail(PCB_ERR_ARG, "layout: lanes_per_row must cover ceil(Q/2) strip pairs (several pairs per lane: L=17, P=32 only)");
   // lead zeros | Q strips | one spare strip (the operand refill of a body that never runs stays in the row)
   int pitch = L + (Q + 1) * L;
   int want = (P == 4) ? 4 : 8;  // bank rule: rows sharing a half-warp must not collide
   if (const char* e = getenv("PCB_PITCH_MOD")) want = atoi(e);  // tuning knob
   while (pitch % 16 != want) ++pitch;
   const int RB = 32 / P;  // one warp per CTA
-  if (jobs_smem_bytes(RB, pitch) > 200 * 1024) return fail(PCB_ERR_ARG, "layout: grid too large for shared memory");
+  if (jobs_smem_bytes(RB, pitch, rounds > 1) > 200 * 1024)
+    return fail(PCB_ERR_ARG, "layout: grid too large for shared memory");
   out->S = S;
   out->G = G;
   out->strip = L;
@@ -106,7 +113,7 @@ int fill_layout(int S, int G, int L, int P, pcb_layout* out) {
   out->lead = L;
   out->rows_per_cta = RB;
   out->kernel = 0;
-  out->reserved = 0;
+  out->reserved = rounds > 1 ? rounds : 0;  // strip pairs per lane and fold step when more than one
   out->tile_elems = (int64_t)S * pitch;
   return PCB_OK;
 }
@@ -127,16 +134,17 @@ int pool_ctas() {
   return v;
 }
 
-template <int L, bool FUSE>
+template <int L, bool FUSE, bool MULTI = false>
 int launch_jobs_LF(const pcb::JobKernelParams& kp, long long n_jobs, int threads, size_t smem, cudaStream_t st) {
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
-    PCB_CUDA(cudaFuncSetAttribute(pcb::node_jobs_kernel<L, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PCB_CUDA(cudaFuncSetAttribute(pcb::node_jobs_kernel<L, FUSE, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
     configured = smem;
   }
   const long long grid = kp.n_jobs_dev ? std::min<long long>(n_jobs * kp.row_blocks, pool_ctas()) : n_jobs * kp.row_blocks;
   if (grid > 2147483647ll) return fail(PCB_ERR_ARG, "too many jobs for one launch");
-  pcb::node_jobs_kernel<L, FUSE><<<(unsigned)grid, threads, smem, st>>>(kp);
+  pcb::node_jobs_kernel<L, FUSE, MULTI><<<(unsigned)grid, threads, smem, st>>>(kp);
   PCB_LAUNCH_CHECK();
   return PCB_OK;
 }
@@ -145,6 +153,14 @@ int launch_jobs_LF(const pcb::JobKernelParams& kp, long long n_jobs, int threads
 template <int L>
 int launch_jobs_L(const pcb::JobKernelParams& kp, long long n_jobs, int threads, size_t smem, cudaStream_t st,
                   bool fused = false) {
+  if (kp.rounds > 1) {
+    if constexpr (L == 17) {
+      if (fused) return fail(PCB_ERR_ARG, "node_jobs: no fused jobs on grids beyond 1088");
+      return launch_jobs_LF<L, false, true>(kp, n_jobs, threads, smem, st);
+    } else {
+      return fail(PCB_ERR_ARG, "node_jobs: several strip pairs per lane need the 17-wide strip");
+    }
+  }
   if (fused) {
     if constexpr (L == 7 || L == 13 || L == 17)
       return launch_jobs_LF<L, true>(kp, n_jobs, threads, smem, st);
@@ -327,6 +343,7 @@ int pcb_make_layout(int32_t S, int32_t G, int32_t variant, pcb_layout* out) {
   }
   if (variant >= 10000) return fill_layout_wide(S, G, (variant - 10000) / 100, out);
   if (variant >= 0) return fill_layout(S, G, variant / 100, variant % 100, out);
+  if (variant < 0 && G > 1088) return fill_layout(S, G, 17, 32, out);  // several strip pairs per lane
   if (variant == -2) {
     // latency-optimised: a single chain launches a handful of jobs at a time, so the device is empty and the
     // time of a launch is the time of ONE lane's strip pair; take the narrowest strip whose pairs fit a row group
@@ -489,7 +506,8 @@ static int node_jobs_launch(const pcb_arena* a, const int32_t* jobs_dev, const i
   kp.lead = l.lead;
   kp.RB = l.rows_per_cta;
   kp.row_blocks = (l.S + l.rows_per_cta - 1) / l.rows_per_cta;
-  kp.double_b = jobs_double_b();
+  kp.rounds = l.reserved > 1 ? l.reserved : 1;
+  kp.double_b = kp.rounds > 1 ? 0 : jobs_double_b();
   kp.n_jobs = n_jobs;
   kp.n_jobs_dev = n_jobs_dev;
   if (l.kernel == 1) {
@@ -507,7 +525,7 @@ static int node_jobs_launch(const pcb_arena* a, const int32_t* jobs_dev, const i
     return fail(PCB_ERR_ARG, "node_jobs: unsupported strip for the wide kernel");
   }
   const int threads = 32;
-  const size_t smem = jobs_smem_bytes(l.rows_per_cta, l.pitch);
+  const size_t smem = jobs_smem_bytes(l.rows_per_cta, l.pitch, kp.rounds > 1);
   cudaStream_t st = (cudaStream_t)stream;
   switch (l.strip) {
     case 3:

@@ -31,6 +31,7 @@ struct JobKernelParams {
                           // stream, pcb_sweep.cuh) and the grid is only an upper bound / a persistent pool of CTAs
   int S, G, Q, U, P, pitch, lead, RB, row_blocks;
   int double_b;  // 1: two operand buffers (next child prefetched during the fold step), 0: one
+  int rounds;    // strip pairs a lane walks per fold step (1 unless the grid is wider than 2 * P strips)
 };
 
 // ---------------------------------------------------------------------------------
@@ -241,14 +242,17 @@ constexpr int kSmemTail = 256;
 
 // FUSE: the launch may contain PCB_JOB_THEN_SCORE jobs (a separate instantiation: the extra live state of the second
 // stage costs registers the plain kernel cannot spare at 12 warps per SM)
-template <int L, bool FUSE = false>
-__global__ void __launch_bounds__(32, (L == 13 && !FUSE) ? 12 : 1) node_jobs_kernel(const JobKernelParams p) {
+// MULTI: grids wider than 2 * 32 strips (G > 1088): a lane walks `p.rounds` strip pairs per fold step, the raw outputs
+// of a step go to a third row buffer O that then swaps roles with A (the single-pair kernel updates A in place, which
+// is only safe once every lane has read all of it)
+template <int L, bool FUSE = false, bool MULTI = false>
+__global__ void __launch_bounds__(32, (L == 13 && !FUSE && !MULTI) ? 12 : 1) node_jobs_kernel(const JobKernelParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
   const int rows_elems = p.RB * p.pitch;
   double* bufA = reinterpret_cast<double*>(smem_raw + kSmemHead);
   double* bufB0 = bufA + rows_elems;
-  double* bufB1 = bufB0 + rows_elems;
+  double* bufB1 = bufB0 + rows_elems;  // second operand buffer (double_b) or, for MULTI, the output buffer O
 
   const int P = p.P, G = p.G, pitch = p.pitch, lead = p.lead, Q = p.Q;
   const int tid = threadIdx.x;
@@ -314,7 +318,12 @@ __global__ void __launch_bounds__(32, (L == 13 && !FUSE) ? 12 : 1) node_jobs_ker
   ++ph0;
 
   double* a_row = bufA + lrow * pitch + lead;
-  const int u = lir;  // the layout guarantees ceil(Q/2) <= P: one unit (strip pair) per lane
+  double* o_row = bufB1 + lrow * pitch + lead;
+  if (MULTI) {  // O's pads must be zero like a tile's: it becomes the next step's A
+    for (int k = tid; k < rows_elems; k += 32) bufB1[k] = 0.0;
+    __syncwarp();
+  }
+  const int u = lir;  // the layout guarantees ceil(Q/2) <= P: one unit (strip pair) per lane (MULTI: per round)
   const bool lane_ok = row_ok && u < p.U;
   const int k1 = u * L, k2 = (Q - 1 - u) * L;
   const bool two = k2 != k1;
@@ -349,6 +358,70 @@ __global__ void __launch_bounds__(32, (L == 13 && !FUSE) ? 12 : 1) node_jobs_ker
       tma_load_1d(Bnext, p.lin + (size_t)cnext * p.tile_elems + (size_t)r0 * pitch, bytes, nbar);
     }
     const double* b_row = Bcur + lrow * pitch + lead;
+    if constexpr (MULTI) {
+      double lmax = 0.0;
+      for (int rd = 0; rd < p.rounds; ++rd) {
+        const int uu = lir + rd * P;
+        const bool ok = row_ok && uu < p.U;
+        const int kk1 = uu * L, kk2 = (Q - 1 - uu) * L;
+        const bool tw = kk2 != kk1;
+        double y1[L], y2[L];
+        conv_unit<L>(a_row, b_row, uu, Q, ok, y1, y2);
+        const int nv2 = ok ? min(L, G - kk2) : 0;
+        const bool v1 = ok && tw;
+        const double fl1 = v1 ? kFloor : 0.0;
+#pragma unroll
+        for (int i = 0; i < L; ++i) {
+          y2[i] = select_f64(y2[i] > 0.0 && i < nv2, y2[i], (i < nv2) ? kFloor : 0.0);
+          y1[i] = select_f64(y1[i] > 0.0 && v1, y1[i], fl1);
+          lmax = fmax(lmax, fmax(y1[i], y2[i]));
+        }
+        if (ok) {
+#pragma unroll
+          for (int i = 0; i < L; ++i) o_row[kk2 + i] = y2[i];
+          if (tw) {
+#pragma unroll
+            for (int i = 0; i < L; ++i) o_row[kk1 + i] = y1[i];
+          }
+        }
+      }
+      if (j + 1 < je) {  // every lane is done with the operand: refill it
+        __syncwarp();
+        if (tid == 0) {
+          fence_proxy_async();
+          mbar_expect_tx(&bars[1], bytes);
+          tma_load_1d(bufB0, p.lin + (size_t)cnext * p.tile_elems + (size_t)r0 * pitch, bytes, &bars[1]);
+        }
+      }
+      const double ymax = group_max(lmax, P);
+      double scale = 1.0;
+      bool tiny = false;
+      if (j < je - 1) {
+        M += mB + log(ymax);
+        tiny = !(ymax >= 1e-290);
+        scale = 1.0 / ymax;
+      } else {
+        M += mB;
+      }
+      __syncwarp();
+      if (j < je - 1) {
+        for (int rd = 0; rd < p.rounds; ++rd) {
+          const int uu = lir + rd * P;
+          if (!(row_ok && uu < p.U)) continue;
+          const int kk1 = uu * L, kk2 = (Q - 1 - uu) * L;
+#pragma unroll
+          for (int i = 0; i < L; ++i) o_row[kk2 + i] = tiny ? o_row[kk2 + i] / ymax : o_row[kk2 + i] * scale;
+          if (kk2 != kk1) {
+#pragma unroll
+            for (int i = 0; i < L; ++i) o_row[kk1 + i] = tiny ? o_row[kk1 + i] / ymax : o_row[kk1 + i] * scale;
+          }
+        }
+      }
+      double* t_row = a_row;
+      a_row = o_row;
+      o_row = t_row;
+      __syncwarp();
+    } else {
     double y1[L], y2[L];
     conv_unit<L>(a_row, b_row, u, Q, lane_ok, y1, y2);
     if (!db && j + 1 < je) {  // single operand buffer: refill it as soon as every lane is done with it
@@ -407,6 +480,7 @@ __global__ void __launch_bounds__(32, (L == 13 && !FUSE) ? 12 : 1) node_jobs_ker
       }
     }
     __syncwarp();
+    }
   }
 
   double* yrow = a_row;

@@ -25,7 +25,7 @@ def _np_conv_dims(child_1, child_2):
 def _convolve_two_children(child_1, child_2):
     """reference tree/utils.py:50-57.  The reference switches to an FFT at G >= 1000 (utils/math.py:241-263,
     same max-shift / floor contract, plus FFT round-off of ~1e-16 of the row maximum); the device kernel evaluates
-    the direct sum for every supported grid (G <= 1088), so large grids get the exact value of that contract."""
+    the direct sum for every supported grid (G <= 8192; several strip pairs per lane beyond 1088), so large grids get the exact value of that contract."""
     return ops.np_conv_dims(child_1, child_2)
 
 

@@ -85,7 +85,7 @@ def conv_log(log_x, log_y, ans=None):
 def fft_convolve_two_children(child_1, child_2):
     """utils/math.py:241-263: the reference's FFT evaluation of the `_np_conv_dims` contract (per-row max shift,
     truncation to G terms, `<= 0 -> 1e-100` floor) for G >= 1000.  Here the same contract is evaluated by the
-    direct-sum kernel, i.e. without the FFT's round-off noise; G <= 1088."""
+    direct-sum kernel, i.e. without the FFT's round-off noise; G <= 8192."""
     from .. import ops
 
     return ops.np_conv_dims(child_1, child_2)

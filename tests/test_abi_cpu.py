@@ -50,8 +50,15 @@ def test_layout_struct_mirrors_the_header():
         assert lay.pitch >= lay.lead + (lay.n_strips + 1) * lay.strip
         assert lay.tile_elems == S * lay.pitch and (lay.tile_elems * 8) % 16 == 0  # TMA: 16-byte multiples
         assert (lay.n_strips + 1) // 2 <= lay.lanes_per_row
+    # grids beyond 1088: the 17-wide strip with several strip pairs per lane (`reserved` = pairs per lane)
+    for G in (1089, 2001, 5000):
+        lay = _lib.Layout()
+        _lib.check(lib.pcb_make_layout(8, G, -1, ctypes.byref(lay)))
+        assert (lay.strip, lay.lanes_per_row, lay.kernel) == (17, 32, 0)
+        assert lay.reserved == -(-((lay.n_strips + 1) // 2) // 32) and lay.reserved >= 2
+        assert lay.pitch >= lay.lead + (lay.n_strips + 1) * lay.strip and (lay.tile_elems * 8) % 16 == 0
     bad = _lib.Layout()
-    assert lib.pcb_make_layout(8, 5000, -1, ctypes.byref(bad)) != 0
+    assert lib.pcb_make_layout(8, 9000, -1, ctypes.byref(bad)) != 0
     assert b"layout" in lib.pcb_last_error()
 
 

@@ -51,11 +51,42 @@ def test_large_grid_direct_sum_vs_reference_fft(G):
     assert_close(tu.compute_log_S(kids), onum.log_s(kids), 1e-9, "log_S at G=%d" % G)
 
 
+@pytest.mark.parametrize("S,G", [(2, 1089), (3, 1500), (4, 2001), (2, 4096), (1, 8192)])
+def test_grids_beyond_1088(S, G):
+    """Grids wider than 2 x 32 strips: lanes walk several strip pairs per fold step (node_jobs_kernel<17, false, true>).
+    Pair convolution, three-child fold + scan and the node update against the oracle (1e-9); at G = 2001 also
+    against scipy's FFT evaluation, which is what the reference runs there (utils/math.py:241-263), up to the FFT's
+    own round-off; peaked rows exercise the 1e-100 floor."""
+    from phyclone_b200 import ops
+    from phyclone_b200.tree import utils as tu
+
+    rng = np.random.default_rng(G)
+    a = np.log(rng.uniform(0.1, 1000, size=(S, G)))
+    b = np.log(rng.uniform(0.1, 1000, size=(S, G)))
+    c = np.log(rng.uniform(0.1, 1000, size=(S, G)))
+    peaked = -0.5 * ((np.arange(G) - G * 0.3) / 3.0) ** 2 + np.zeros((S, 1))  # rows spanning >> 745 nats
+    got = ops.np_conv_dims(a, b)
+    assert_close(got, onum.conv_pair(a, b), 1e-9, "pair conv at G=%d" % G)
+    assert_close_bucketed(ops.np_conv_dims(peaked, peaked + 1.0), onum.conv_pair(peaked, peaked + 1.0),
+                          what="peaked pair at G=%d" % G, max_boundary=8)
+    kids = [a, b, c, peaked]
+    assert_close_bucketed(tu.compute_log_S(kids), onum.log_s(kids), what="log_S at G=%d" % G, max_boundary=8)
+    log_p = np.log(rng.uniform(0.1, 10, size=(1, S, G)))
+    upd = ops.node_update_batch(log_p, [np.stack([a, b, c])])[0]
+    assert_close(upd, onum.node_log_r(log_p[0], [a, b, c]), 1e-9, "node update at G=%d" % G)
+    if G == 2001:
+        from scipy.signal import fftconvolve
+
+        shift = a.max(1, keepdims=True) + b.max(1, keepdims=True)
+        fft = np.stack([fftconvolve(np.exp(b[s] - b[s].max()), np.exp(a[s] - a[s].max()))[:G] for s in range(S)])
+        assert np.abs(np.exp(got - shift) - fft).max() <= 1e-11 * fft.max()
+
+
 def test_grid_beyond_supported_size_is_an_error():
     from phyclone_b200 import ops
 
     with pytest.raises(RuntimeError):
-        ops.np_conv_dims(np.zeros((1, 1100)), np.zeros((1, 1100)))
+        ops.np_conv_dims(np.zeros((1, 8300)), np.zeros((1, 8300)))
 
 
 def test_tree_node_dropin(golden):
