@@ -194,6 +194,9 @@ int check_arena(const pcb_arena* a) {
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
+  ~DevBuf() {  // per-thread scratch goes away with its thread (a chain = one host thread)
+    if (p) cudaFree(p);
+  }
   int ensure(size_t bytes) {
     if (bytes <= cap) return PCB_OK;
     if (p) cudaFree(p);
@@ -201,8 +204,12 @@ struct DevBuf {
     cap = 0;
     size_t want = bytes + bytes / 4 + 256;
     cudaError_t e = cudaMalloc(&p, want);
-    if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? PCB_ERR_NOMEM : PCB_ERR_CUDA,
-                                      std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    if (e != cudaSuccess) {
+      cudaGetLastError();  // do not leave the failure for the next launch check to report as its own
+      p = nullptr;
+      return fail(e == cudaErrorMemoryAllocation ? PCB_ERR_NOMEM : PCB_ERR_CUDA,
+                  std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    }
     cap = want;
     return PCB_OK;
   }
@@ -410,6 +417,7 @@ int pcb_tile_add_dev(const pcb_arena* a, const int32_t* a_ids, const int32_t* b_
   if (n <= 0) return PCB_OK;
   const pcb_layout& l = a->layout;
   const long long warps = n * l.S;
+  if ((warps + 3) / 4 > 2147483647ll) return fail(PCB_ERR_ARG, "tile_add: too many tiles for one launch");
   const int wpb = 4;
   pcb::tile_add_kernel<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
       a_ids, b_ids, out_ids, n, b_sign, addend, a->lg, a->lin, a->rmax, l.S, l.G, l.pitch, l.lead, l.tile_elems);
@@ -424,7 +432,7 @@ struct JobTiming {
   std::vector<cudaEvent_t> ev;  // 2 per recorded launch
   size_t used = 0, cap = 0;
 };
-JobTiming g_timing;
+thread_local JobTiming g_timing;  // a chain is one host thread: its kernel timing is its own
 
 int pcb_timing_begin(int32_t max_launches) {
   if (max_launches < 1) return fail(PCB_ERR_ARG, "timing: max_launches must be positive");
@@ -552,8 +560,8 @@ int pcb_reduce_rows_dev(const double* rows_dev, int64_t n_slots, int32_t S, doub
   return PCB_OK;
 }
 
-double g_plan_enqueue_s = 0.0, g_plan_sync_s = 0.0;
-int64_t g_plan_flushes = 0;
+thread_local double g_plan_enqueue_s = 0.0, g_plan_sync_s = 0.0;  // per host thread (= per chain)
+thread_local int64_t g_plan_flushes = 0;
 
 // One flush of the host's tile store in ONE call: stage the packed id lists / job tables (pinned host -> device),
 // run every launch of the plan in dependency order, reduce the score rows and copy the sums back.
@@ -570,12 +578,34 @@ int pcb_run_plan_dev(const pcb_arena* a, const int32_t* packed_host, int64_t n_i
     return fail(PCB_ERR_ARG, "run_plan: score buffers missing");
   cudaStream_t st = (cudaStream_t)stream;
   const auto t_begin = std::chrono::steady_clock::now();
+  // every tile id / score slot of the plan must lie inside the arena / the score buffers: a stale plan (ids from before
+  // a reset or grow) would otherwise write into neighbouring allocations
+  for (int r = 0; r < n_rec; ++r) {
+    const int32_t* rec = plan + 6 * r;
+    const int64_t off = rec[1], n = rec[2];
+    if (off < 0 || n < 0 || rec[3] < 0 || off + (rec[0] == 0 ? 3 * n : 8 * n + rec[3]) > n_ints)
+      return fail(PCB_ERR_ARG, "run_plan: record outside the packed buffer");
+    const int32_t* q = packed_host + off;
+    const int64_t cap = a->capacity;
+    if (rec[0] == 0) {
+      for (int64_t i = 0; i < 3 * n; ++i)
+        if (q[i] < 0 || q[i] >= cap) return fail(PCB_ERR_ARG, "run_plan: tile id outside the arena");
+    } else {
+      const int32_t* kids = q + 8 * n;
+      for (int64_t i = 0; i < n; ++i) {
+        const int32_t* j = q + 8 * i;
+        if (j[0] < 0 || j[1] < 1 || (int64_t)j[0] + j[1] > rec[3] || j[2] < -1 || j[2] >= cap || j[3] < -1 || j[3] >= cap ||
+            j[5] < -1 || j[5] >= n_slots || j[6] < 0 || j[6] > cap)
+          return fail(PCB_ERR_ARG, "run_plan: job record outside the arena / score buffers");
+      }
+      for (int64_t i = 0; i < rec[3]; ++i)
+        if (kids[i] < 0 || kids[i] >= cap) return fail(PCB_ERR_ARG, "run_plan: child tile id outside the arena");
+    }
+  }
   PCB_CUDA(cudaMemcpyAsync(packed_dev, packed_host, (size_t)n_ints * 4, cudaMemcpyHostToDevice, st));
   for (int r = 0; r < n_rec; ++r) {
     const int32_t* rec = plan + 6 * r;
     const int64_t off = rec[1], n = rec[2];
-    if (off < 0 || n < 0 || off + (rec[0] == 0 ? 3 * n : 8 * n + rec[3]) > n_ints)
-      return fail(PCB_ERR_ARG, "run_plan: record outside the packed buffer");
     const int32_t* p0 = packed_dev + off;
     if (rec[0] == 0) {
       if ((rc = pcb_tile_add_dev(a, p0, p0 + n, p0 + 2 * n, n, rec[4] ? -1.0 : 1.0, 0.0, stream))) return rc;
