@@ -105,10 +105,14 @@ class Chain(object):
     def step(self):
         """run.py:261-288: PG sweep, data-point Gibbs, prune-regraph, relabel, concentration update."""
         self.kernel.clear_proposal_dist_caches()
-        self.store.reset()
         if self.rng.random() < self.subtree_update_prob:  # run.py:268-271 (the coin is drawn even at probability 0)
-            tree = self.subtree_sampler.sample_tree(self.tree)
+            # the subtree move edits the carried tree itself: its tiles must survive into the new arena generation
+            carried = self.tree.copy()
+            self.store.flush()
+            self.store.rebase(carried)
+            tree = self.subtree_sampler.sample_tree(carried)
         else:
+            self.store.reset()  # new arena generation: the carried tree is only read structurally from here on
             tree = self.tree_sampler.sample_tree(self.tree)
         tree = self.tree = self._local_moves(tree)
         if self.concentration_update:

@@ -92,6 +92,28 @@ class TileStore:
         self.arena.alloc.reset()
         self.book.reset()
 
+    def rebase(self, tree):
+        """Start a new arena generation that still holds `tree`'s tiles: they are copied to the bottom of the new
+        generation and the tree's ids are rewritten in place.  A plain `reset()` leaves a carried tree's ids pointing
+        at slots the new generation will overwrite, which is fine as long as the tree is only read structurally (the
+        particle-Gibbs sweep, the Gibbs moves on the tree it returns) -- the subtree move prunes and re-grafts the
+        carried tree itself, i.e. reads its tiles."""
+        al = self.arena.alloc
+        ids = sorted({i for i in list(tree._lp.values()) + list(tree._lr.values()) if i >= al.permanent})
+        dense = self.arena.export_tiles(ids) if ids else None  # flushes nothing: a carried tree has no pending ops
+        self.reset()
+        if not ids:
+            return
+        base = self.book.reserve(len(ids))
+        while base < 0:
+            self._grow()
+            base = self.book.reserve(len(ids))
+        new_ids = list(range(base, base + len(ids)))
+        self.arena.import_tiles(dense, new_ids)
+        remap = dict(zip(ids, new_ids))
+        tree._lp = {k: remap.get(v, v) for k, v in tree._lp.items()}
+        tree._lr = {k: remap.get(v, v) for k, v in tree._lr.items()}
+
     def _grow(self):
         al = self.arena.alloc
         if al.capacity >= self.max_capacity:

@@ -11,13 +11,27 @@ from phyclone_b200.engine import JOB_ADD_PRIOR, JOB_SCAN, TileAllocator
 from phyclone_b200.tiles import TileStore
 
 
+class _ForgetfulAllocator(TileAllocator):
+    """A new arena generation really forgets the old tiles here (the device arena merely overwrites them later): a
+    tree that reads tile ids of a previous generation fails loudly in the CPU tests instead of working by luck."""
+
+    def __init__(self, capacity, arena):
+        super().__init__(capacity)
+        self._arena = arena
+
+    def reset(self):
+        super().reset()
+        for i in [i for i in self._arena.tiles if i >= self.permanent]:
+            del self._arena.tiles[i]
+
+
 class FakeArena:
     def __init__(self, S, G, capacity):
         self.S, self.G = S, G
         self.capacity = int(capacity)
-        self.alloc = TileAllocator(self.capacity)
-        self.prior = -float(np.log(G))
         self.tiles = {}
+        self.alloc = _ForgetfulAllocator(self.capacity, self)
+        self.prior = -float(np.log(G))
         self.staged_bytes = 0
 
     def grow(self, new_capacity):
