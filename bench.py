@@ -65,9 +65,11 @@ def workload_values_gpu(ops):
 
 
 def chain_rng(rank, world):
-    """run.py:87-139: a single chain uses the main Generator itself, several chains use its spawned children."""
-    main = np.random.default_rng(1)
-    return main if world == 1 else main.spawn(world)[rank]
+    """Chain `rank` of the job: child `rank` of `default_rng(1).spawn(max(8, world))` (run.py:87-113 spawns one child
+    per chain).  The same children at every N -- also for one chain, where the reference would use the main Generator
+    itself -- so that rank r runs the SAME chain whatever the number of GPUs: per-N values are then comparable and
+    `--gpus N`, `--chains 8` and the reference arm all draw from one family of eight chains."""
+    return np.random.default_rng(1).spawn(max(8, world))[rank]
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -465,8 +467,12 @@ def run_ours(args):
             live_variant = (10000 if lay.kernel else 0) + 100 * lay.strip + (0 if lay.kernel else lay.lanes_per_row)
             r = bench_variant(CFG["samples"], CFG["grid"], -1, 32768, 8, 4096, 5)
             r2 = bench_variant(CFG["samples"], CFG["grid"], live_variant, 32768, 8, 4096, 5)
+            r3 = bench_variant(CFG["samples"], CFG["grid"], -1, 16384, 8, 4096, 5, score_only=False)
             sat = {"achieved": r["tflops"], "unit": "TFLOP/s", "frac": r["tflops"] * 1e12 / fp64_peak,
-                   "launch": "32768 jobs x 8 children",
+                   "launch": "32768 score-only jobs x 8 children (dummy-root folds: no tile written, no log_p read)",
+                   "full_node_jobs": {"launch": "16384 node refreshes x 8 children, each reading a log_p tile and "
+                                                "writing its log_r tile (log + linear + row maxima)",
+                                      "achieved": r3["tflops"], "frac": r3["tflops"] * 1e12 / fp64_peak},
                    "layout": "throughput layout (L=%d, P=%d): what a saturated batch would run with" % (r["L"], r["P"]),
                    "chain_layout": {"layout": "latency layout (L=%d, P=%d): what the timed chain runs with, its launches "
                                               "being ~20 jobs" % (r2["L"], r2["P"]),

@@ -17,7 +17,9 @@ from phyclone_b200 import engine, ops  # noqa: E402
 
 
 def bench_variant(S, G, variant, n_jobs, C, n_tiles, reps, score_only=True):
-    ar = engine.DeviceArena(S, G, n_tiles + 1, variant=variant)
+    """score_only=True: dummy-root jobs (scores, no tile written, no log_p read).  score_only=False: full node
+    refreshes -- every job reads a log_p tile and writes its log_r tile (log + lin + row maxima) to its own slot."""
+    ar = engine.DeviceArena(S, G, n_tiles + 1 + (0 if score_only else n_jobs), variant=variant)
     rng = np.random.default_rng(0)
     dense = torch.log(torch.rand((n_tiles, S, G), dtype=torch.float64, device=ar.device) * 999.9 + 0.1)
     ar.import_tiles(dense, np.arange(n_tiles))
@@ -25,10 +27,16 @@ def bench_variant(S, G, variant, n_jobs, C, n_tiles, reps, score_only=True):
     jobs = np.zeros((n_jobs, 8), dtype=np.int32)
     jobs[:, 0] = np.arange(n_jobs) * C
     jobs[:, 1] = C
-    jobs[:, 2] = -1
-    jobs[:, 3] = -1
-    jobs[:, 4] = engine.JOB_SCAN | engine.JOB_ADD_PRIOR
-    jobs[:, 5] = np.arange(n_jobs)
+    if score_only:
+        jobs[:, 2] = -1
+        jobs[:, 3] = -1
+        jobs[:, 4] = engine.JOB_SCAN | engine.JOB_ADD_PRIOR
+        jobs[:, 5] = np.arange(n_jobs)
+    else:
+        jobs[:, 2] = rng.integers(0, n_tiles, size=n_jobs)
+        jobs[:, 3] = n_tiles + 1 + np.arange(n_jobs)
+        jobs[:, 4] = engine.JOB_SCAN
+        jobs[:, 5] = -1
     for _ in range(3):
         ar.run_jobs(jobs, kids, n_slots=n_jobs)
     torch.cuda.synchronize()
@@ -54,7 +62,7 @@ def bench_variant(S, G, variant, n_jobs, C, n_tiles, reps, score_only=True):
     lay = ar.layout
     return {
         "variant": variant, "L": lay.strip, "P": lay.lanes_per_row, "pitch": lay.pitch, "RB": lay.rows_per_cta,
-        "S": S, "G": G, "jobs": n_jobs, "children": C, "ms": ms,
+        "S": S, "G": G, "jobs": n_jobs, "children": C, "ms": ms, "score_only": bool(score_only),
         "tflops": 2 * fma / (ms * 1e-3) / 1e12, "convs_per_s": n_jobs * (C - 1) / (ms * 1e-3),
     }
 

@@ -30,7 +30,7 @@ def worker(rank, n, steps, warmup, barrier, q, config=2, sweep="host", device=0,
     cfg = bench.set_config(config)
     values = bench.workload_values_gpu(ops)
     data = make_data_points(values, outlier_probs=workloads.outlier_log_probs(cfg))
-    rng = np.random.default_rng(1).spawn(n_chains)[chain] if n_chains > 1 else np.random.default_rng(1)  # run.py:87-113
+    rng = np.random.default_rng(1).spawn(max(8, n_chains))[chain]  # bench.chain_rng: the same family of chains
     ch = Chain(data, rng, num_particles=cfg["particles"], outlier_prob=cfg["outlier_prob"], sweep=sweep)
     ch.burnin_step()
     for _ in range(warmup):
