@@ -63,6 +63,7 @@ class TileStore:
         self.book = load_hostmod().TileBook(al.permanent, self.arena.capacity, self.prior_id)
         self._stats = {"flushes": 0, "launches": 0, "d2h_bytes": 0, "flush_s": 0.0, "device_wait_s": 0.0}
         self._ctx = None
+        self.generation = 0  # bumped by reset(): trees remember which generation their tile ids belong to
         self.reset()
 
     @property
@@ -91,6 +92,7 @@ class TileStore:
         """Start a new arena generation: everything but the permanent tiles is forgotten."""
         self.arena.alloc.reset()
         self.book.reset()
+        self.generation += 1
 
     def rebase(self, tree):
         """Start a new arena generation that still holds `tree`'s tiles: they are copied to the bottom of the new
@@ -102,6 +104,7 @@ class TileStore:
         ids = sorted({i for i in list(tree._lp.values()) + list(tree._lr.values()) if i >= al.permanent})
         dense = self.arena.export_tiles(ids) if ids else None  # flushes nothing: a carried tree has no pending ops
         self.reset()
+        tree._gen = self.generation
         if not ids:
             return
         base = self.book.reserve(len(ids))
@@ -113,6 +116,7 @@ class TileStore:
         remap = dict(zip(ids, new_ids))
         tree._lp = {k: remap.get(v, v) for k, v in tree._lp.items()}
         tree._lr = {k: remap.get(v, v) for k, v in tree._lr.items()}
+        tree._gen = self.generation
 
     def _grow(self):
         al = self.arena.alloc

@@ -25,7 +25,7 @@ class Tree(object):
     _ROOT_NODE_NAME = "root"
     _OUTLIER_NODE_NAME = -1
     __slots__ = ("grid_size", "store", "_data", "_graph", "_node_indices", "_node_indices_rev", "_last_node_added_to",
-                 "_lp", "_lr", "_dirty", "_skey", "_pt")
+                 "_lp", "_lr", "_dirty", "_skey", "_pt", "_gen")
 
     def __init__(self, grid_size, store):
         self.grid_size = grid_size
@@ -45,6 +45,9 @@ class Tree(object):
         self._skey = 0  # running structure hash (see structure_key); None = recompute
         # running integer/scalar statistics behind the FS-CRP prior (see prior_terms); None = recompute
         self._pt = [0.0, 0.0, {}, 0.0, 0.0]  # crp_sum, multiplicity, subtree node counts, outlier prior, outlier marginals
+        # arena generation the tile ids belong to: a tree carried across `store.reset()` may still be read structurally
+        # (labels, children, sigma), but recording tile ops on its ids would read slots the new generation reuses
+        self._gen = getattr(store, "generation", 0)
         self._add_node(self._ROOT_NODE_NAME)
 
     # ------------------------------------------------------------------ identity
@@ -267,6 +270,7 @@ class Tree(object):
     def score_handle(self):
         """Lazy (sum_s LSE_g, sum_s last column) of the dummy root's log_r, or None for an empty forest
         (tree/distributions.py:197-200)."""
+        self._live()
         kids = self.root_children_tiles()
         return self.store.score(kids) if kids else None
 
@@ -291,8 +295,15 @@ class Tree(object):
         self._node_indices_rev[i] = node
         return i
 
+    def _live(self):
+        if self._gen != getattr(self.store, "generation", self._gen):
+            raise RuntimeError("this Tree's tiles belong to arena generation %d, the store is at %d: re-read it with "
+                               "Tree.from_dict(tree.to_dict(), store) or keep its tiles with store.rebase(tree)"
+                               % (self._gen, self.store.generation))
+
     def _absorb(self, i, data_points):
         """TreeNode.add_data_point(_list) (tree/tree_node.py:34-52): log_p += value; log_r += value."""
+        self._live()
         st = self.store
         lp, lr = self._lp[i], self._lr[i]
         for dp in data_points:
@@ -414,6 +425,7 @@ class Tree(object):
         new._skey = self._skey
         pt = self._pt
         new._pt = None if pt is None else pt.copy()  # the size dict is replaced, never mutated, on edit
+        new._gen = self._gen
         return new
 
     def thawed_copy(self):
@@ -457,6 +469,7 @@ class Tree(object):
         kids = tuple(lr[c] for c in g.successor_indices(i))
         if self._node_indices_rev[i] == self._ROOT_NODE_NAME:
             return  # the dummy root's tile is only ever reduced: see score_handle()
+        self._live()
         lr[i] = self.store.node(self._lp[i], kids) if kids else self._lp[i]
 
     def _update_path_to_root(self, source):
@@ -511,6 +524,7 @@ class Tree(object):
         new._dirty = set()
         new._skey = None
         new._pt = None
+        new._gen = getattr(store, "generation", 0)  # every tile is re-derived below: the tree belongs to the store's now
         r = g.add_node(cls._ROOT_NODE_NAME)
         new._lp[r], new._lr[r] = store.prior_id, NO_TILE
         if len(tree_dict["graph"]) > 0:

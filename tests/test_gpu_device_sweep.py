@@ -164,6 +164,26 @@ def test_device_mode_samples_the_exact_posterior():
         assert err <= 0.03, (name, err)
 
 
+def test_sweep_falls_back_to_the_host_sampler(monkeypatch):
+    """Forests wider than the device sweep's root limit (64; forced down to 2 here) make a sweep fall back to the host
+    sampler -- either before the call (the retained path does not fit) or after it (a particle overflowed: the
+    sweep's outputs are void) -- and the chain carries on."""
+    import phyclone_b200.smc.device_sweep as ds
+    from phyclone_b200.data.base import make_data_points
+    from phyclone_b200.run import Chain
+
+    monkeypatch.setattr(ds, "MAX_ROOTS", 2)
+    g = load_chain("syn12")
+    chain = Chain(make_data_points(g["values"]), np.random.default_rng(4), num_particles=12, sweep="device")
+    chain.burnin_step()
+    for _ in range(4):
+        chain.step()
+    st = chain.stats
+    assert st["sweep"]["fallbacks"] + st["burnin_sweep"]["fallbacks"] >= 1
+    assert np.isfinite(chain.log_p_one())
+    assert sorted(dp.idx for dp in chain.tree.data) == list(range(len(g["values"])))
+
+
 def test_device_sweep_at_bench_config():
     """BASELINE configs[1] at full size (50 x 8 x 101, 100 particles): burn-in sweep + two PG iterations."""
     from oracle.synthetic import make_synthetic
