@@ -38,7 +38,7 @@ class DataPointSampler(object):
         # back" yields the same tile ids on the look-ahead copy as later on the real tree); one flush scores them
         # all.  The moves are then drawn one by one exactly as before -- same scores, same RNG calls -- and the first
         # point that really moves throws the rest of the look-ahead away.
-        ahead = []  # [(position in data_idxs, pending scores | None)]
+        ahead = []  # [(position in data_idxs, pending scores | None, the tree after this point stays put | None)]
         k, n = 0, len(data_idxs)
         while k < n:
             if not ahead:
@@ -46,26 +46,30 @@ class DataPointSampler(object):
                 for j in range(k, min(k + self.LOOKAHEAD, n)):
                     old = tree_labels[data_idxs[j]]
                     if t.get_data_len(old) <= 1:
-                        ahead.append((j, None))
+                        ahead.append((j, None, None))
                         continue
                     if by_idx is None:
                         t = tree = tree.copy()
                         by_idx = {dp.idx: dp for lst in tree._data.values() for dp in lst}
                     dp = by_idx[data_idxs[j]]
-                    ahead.append((j, self._score_candidates(t, dp, old)))
+                    pending = self._score_candidates(t, dp, old)
+                    stay = None
                     if j + 1 < min(k + self.LOOKAHEAD, n):
-                        t = t.copy()
+                        t = stay = t.copy()
                         t.remove_data_point_from_node(dp, old)
                         if old == t.outlier_node_name:
                             t.add_data_point_to_outliers(dp)
                         else:
                             t.add_data_point_to_node(dp, old)
-            j, pending = ahead.pop(0)
+                    ahead.append((j, pending, stay))
+            j, pending, stay = ahead.pop(0)
             assert j == k
             data_idx = data_idxs[k]
             if pending is not None:
                 old_node = tree_labels[data_idx]
-                new_node = self._move(by_idx[data_idx], tree, old_node, pending)
+                # a point that stays put: the look-ahead already built exactly that tree (the next points were
+                # scored on it) -- adopt it instead of applying "remove + add back" a second time
+                new_node, tree = self._move(by_idx[data_idx], tree, old_node, pending, stay)
                 tree_labels[data_idx] = new_node
                 self.moves += 1
                 if new_node == old_node:
@@ -82,11 +86,11 @@ class DataPointSampler(object):
         data_point = tree.data[data_idx]
         assert data_point.idx == data_idx
         new_tree = tree.copy()
-        self._move(data_point, new_tree, old_node)
-        return new_tree
+        return self._move(data_point, new_tree, old_node)[1]
 
-    def _move(self, data_point, tree, old_node, pending=None):
-        """Draw the node `data_point` moves to and apply the move to `tree` IN PLACE; returns the node's name.
+    def _move(self, data_point, tree, old_node, pending=None, stay=None):
+        """Draw the node `data_point` moves to and apply the move to `tree` IN PLACE (or, if the point stays where it
+        is and the caller already holds that tree as `stay`, take that one); returns (node name, tree).
         Every candidate is scored from the one tree by recording the tile ops its two path refreshes would perform
         (remove from `old_node`: refresh old_node..root; add to the new node: log_r += value, refresh its parents up
         to the root); only the candidate that is drawn gets built."""
@@ -98,14 +102,15 @@ class DataPointSampler(object):
         q = q / sum(q)
         tree_idx = self._rng.multinomial(1, q).argmax()
         nodes = tree.nodes
+        new_node = nodes[tree_idx] if tree_idx < len(nodes) else tree.outlier_node_name
+        if stay is not None and new_node == old_node:
+            return new_node, stay
         tree.remove_data_point_from_node(data_point, old_node)
         if tree_idx < len(nodes):
-            new_node = nodes[tree_idx]
             tree.add_data_point_to_node(data_point, new_node)
         else:
-            new_node = tree.outlier_node_name
             tree.add_data_point_to_outliers(data_point)
-        return new_node
+        return new_node, tree
 
     def _score_candidates(self, tree, data_point, old_node):
         """Scores of `tree` with `data_point` moved to every node (in `tree.nodes` order) and, with outlier
