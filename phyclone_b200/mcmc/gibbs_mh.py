@@ -20,6 +20,7 @@ class DataPointSampler(object):
         self.outliers = outliers
         self._rng = rng
         self._flat = None  # (graph, flattened structure) of the tree the current sweep edits in place
+        self._one_shape = False  # True while sample_tree runs: all its trees are copies of one shape
         self.moves = self.stays = self.lookahead_hits = 0
 
     def sample_tree(self, tree):
@@ -31,6 +32,7 @@ class DataPointSampler(object):
         data_idxs = list(tree_labels.keys())
         self._rng.shuffle(data_idxs)
         self._flat = None
+        self._one_shape = True
         by_idx = None
         # A move is one synchronising device round trip, and most moves put the point back where it was.  So the
         # candidates of the next LOOKAHEAD moves are recorded at once, each against the tree its predecessors leave
@@ -77,14 +79,16 @@ class DataPointSampler(object):
                     self.lookahead_hits += 1 if ahead else 0
                 else:
                     ahead = []
-                    self._flat = None
             k += 1
+        self._one_shape = False
+        self._flat = None
         return tree
 
     def _sample_tree(self, data_idx, tree, old_node):
         """gibbs_mh.py:35-70 with the reference's signature: returns a new tree, the input is left alone."""
         data_point = tree.data[data_idx]
         assert data_point.idx == data_idx
+        self._one_shape = False
         new_tree = tree.copy()
         return self._move(data_point, new_tree, old_node)[1]
 
@@ -125,7 +129,8 @@ class DataPointSampler(object):
         ensure_tables(prior, st.T + 2)
         # the shape of the tree does not change during a Gibbs sweep (points move, nodes stay): flatten it once
         flat = self._flat
-        if flat is None or flat[0] is not g:
+        # inside one sweep every tree handed in (the tree being edited and its look-ahead copies) has the same shape
+        if flat is None or (flat[0] is not g and not self._one_shape):
             n_slots = len(g.payload)
             parent, kids = [-1] * n_slots, [()] * n_slots
             succ, pred = g.successor_indices, g.predecessor_indices
