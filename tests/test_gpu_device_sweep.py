@@ -201,6 +201,27 @@ def test_device_sweep_wide_layout_many_particles():
     _compare_chain(syn["values"], None, 200, 0.0, 1, 2, 3, "40 points x 4 samples, 200 particles")
 
 
+def test_device_sweep_500_particles():
+    """BASELINE configs[4]'s swarm size (500 particles) on a reduced data set: 60 unclustered points x 4 samples."""
+    from oracle.synthetic import make_synthetic
+
+    syn = make_synthetic(60, 4, 101, 1, 200, seed=0, density="beta-binomial", precision=400)
+    _compare_chain(syn["values"], None, 500, 0.0, 1, 1, 7, "60 points x 4 samples, 500 particles")
+
+
+def test_device_sweep_at_config4_shape():
+    """BASELINE configs[3]'s tile shape and outlier modelling on a reduced data set: 20 clusters x 20 samples, grid 201,
+    outlier_prob 1e-3, 40 particles."""
+    from oracle.synthetic import make_synthetic
+    from phyclone_b200 import workloads
+
+    cfg = workloads.config_dict(4, clusters=20)
+    syn = make_synthetic(20, cfg["samples"], cfg["grid"], cfg["muts_per_cluster"], cfg["depth"], seed=0,
+                         density=cfg["density"], precision=cfg["precision"])
+    _compare_chain(syn["values"], workloads.outlier_log_probs(cfg), 40, cfg["outlier_prob"], 1, 1, 9,
+                   "20 clusters x 20 samples x grid 201, outliers")
+
+
 def test_device_mode_has_the_host_samplers_stationary_distribution():
     """Statistical pin of the uniform-driven mode on the device, after the reference's own check of its particle-Gibbs
     sampler (tests/test_pg_posterior.py:15-158, delta 0.03).  That test gives the kernel the root-permutation
