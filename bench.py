@@ -464,7 +464,7 @@ def run_ours(args):
             from kernel_bench import bench_variant
 
             lay = store.arena.layout
-            live_variant = (10000 if lay.kernel else 0) + 100 * lay.strip + (0 if lay.kernel else lay.lanes_per_row)
+            live_variant = (10000 if (lay.kernel & 3) else 0) + 100 * lay.strip + (0 if (lay.kernel & 3) else lay.lanes_per_row)
             r = bench_variant(CFG["samples"], CFG["grid"], -1, 32768, 8, 4096, 5)
             r2 = bench_variant(CFG["samples"], CFG["grid"], live_variant, 32768, 8, 4096, 5)
             r3 = bench_variant(CFG["samples"], CFG["grid"], -1, 16384, 8, 4096, 5, score_only=False)

@@ -60,10 +60,13 @@ typedef struct {
   int32_t pitch;         /* doubles per padded row                   */
   int32_t lead;          /* leading zero doubles per row (== L)      */
   int32_t rows_per_cta;  /* rows of one tile handled by one CTA      */
-  int32_t kernel;        /* 0: lane-per-unit job kernel, 1: unit-per-warp ("wide", 32 rows of 32/S jobs per CTA) */
+  int32_t kernel;        /* bits 0-1: 0 lane-per-unit job kernel, 1 unit-per-warp ("wide", 32 rows of 32/S jobs per CTA);
+                            PCB_KERNEL_LATENCY (4), set by the caller: small launches (<= 1024 jobs, sweeps of <= 256
+                            particles) run on the warp-per-row mapping -- same results to rounding, shorter fold chains */
   int32_t reserved;
   int64_t tile_elems;    /* S * pitch                                */
 } pcb_layout;
+#define PCB_KERNEL_LATENCY 4
 
 /* variant = 100*L + P fixes the strip/lane configuration (10000 + 100*L: the unit-per-warp kernel, S an even
  * divisor of 32); -1 picks the throughput-optimal one for (S, G) (saturated

@@ -185,6 +185,64 @@ int launch_wide_L(const pcb::JobKernelParams& kp, long long n_jobs, size_t smem,
   return PCB_OK;
 }
 
+// ---- the latency mapping (node_jobs_rows_kernel): one warp per row, the bodies of a strip pair split over H lanes
+int rows_rb(int S) {  // rows (warps) per CTA: the largest divisor of S up to 4
+  for (int rb = 4; rb > 1; --rb)
+    if (S % rb == 0) return rb;
+  return 1;
+}
+size_t rows_smem_bytes(const pcb_layout& l) { return pcb::kSmemHead + 3ull * rows_rb(l.S) * l.pitch * 8 + pcb::kSmemTail; }
+bool rows_supported(const pcb_layout& l) {
+  return (l.kernel & 3) == 0 && l.reserved <= 1 && (l.strip == 7 || l.strip == 13 || l.strip == 17) &&
+         l.n_strips >= 1 && l.n_strips <= 32 && l.lead >= l.strip - 1 && l.pitch - l.lead >= l.n_strips * l.strip &&
+         rows_smem_bytes(l) <= 200 * 1024;
+}
+// launches of at most this many jobs go to the latency mapping when the store asked for it (PCB_ROWS_MAX_JOBS)
+long long rows_max_jobs() {
+  static long long v = -1;
+  if (v < 0) {
+    const char* env = getenv("PCB_ROWS_MAX_JOBS");
+    v = (env && *env) ? atoll(env) : 1024;
+  }
+  return v;
+}
+template <int L>
+int launch_rows_L(const pcb::JobKernelParams& kp, long long n_jobs, size_t smem, cudaStream_t st) {
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    PCB_CUDA(cudaFuncSetAttribute(pcb::node_jobs_rows_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  // device-counted launches: a pool that covers the device a few times over
+  const long long grid = kp.n_jobs_dev ? std::min<long long>(n_jobs * kp.row_blocks, pool_ctas() / 3) : n_jobs * kp.row_blocks;
+  if (grid > 2147483647ll) return fail(PCB_ERR_ARG, "too many jobs for one launch");
+  pcb::node_jobs_rows_kernel<L><<<(unsigned)grid, 32 * kp.RB, smem, st>>>(kp);
+  PCB_LAUNCH_CHECK();
+  return PCB_OK;
+}
+int launch_rows(pcb::JobKernelParams kp, const pcb_layout& l, long long n_jobs, cudaStream_t st) {
+  kp.RB = rows_rb(l.S);
+  kp.row_blocks = l.S / kp.RB;
+  // bodies per lane: the fewest for which the strips, split over ceil((q+1)/T) lanes each, fit a warp
+  int T = 1;
+  for (;; ++T) {
+    int n = 0;
+    for (int q = 0; q < l.n_strips; ++q) n += (q + T) / T;
+    if (n <= 32) break;
+  }
+  kp.P = T;
+  const size_t smem = rows_smem_bytes(l);
+  switch (l.strip) {
+    case 7:
+      return launch_rows_L<7>(kp, n_jobs, smem, st);
+    case 13:
+      return launch_rows_L<13>(kp, n_jobs, smem, st);
+    case 17:
+      return launch_rows_L<17>(kp, n_jobs, smem, st);
+  }
+  return fail(PCB_ERR_ARG, "node_jobs: unsupported strip for the latency mapping");
+}
+
 int check_arena(const pcb_arena* a) {
   if (!a || !a->lg || !a->lin || !a->rmax || a->capacity < 1) return fail(PCB_ERR_ARG, "arena: null");
   return PCB_OK;
@@ -463,16 +521,18 @@ int pcb_timing_end(double* total_ms, int64_t* n_launches) {
   return PCB_OK;
 }
 
+// mode bits of a launch: the table may hold PCB_JOB_THEN_SCORE jobs / the caller knows the launch is a small one
+constexpr int kJobsFused = 1, kJobsSmall = 2;
 static int node_jobs_launch(const pcb_arena* a, const int32_t* jobs_dev, const int32_t* children_dev, int64_t n_jobs,
                             double prior, double* rows_lse, double* rows_last, void* stream,
-                            const int* n_jobs_dev = nullptr, bool fused = false);
+                            const int* n_jobs_dev = nullptr, int mode = 0);
 
 static int jobs_launch_timed(const pcb_arena* a, const int32_t* jobs_dev, const int32_t* children_dev, int64_t n_jobs,
                              double prior, double* rows_lse, double* rows_last, void* stream, const int* n_jobs_dev,
-                             bool fused = false) {
+                             int mode = 0) {
   const bool timed = g_timing.on && n_jobs > 0 && g_timing.used + 2 <= g_timing.cap;
   if (timed) PCB_CUDA(cudaEventRecord(g_timing.ev[g_timing.used], (cudaStream_t)stream));
-  const int rc = node_jobs_launch(a, jobs_dev, children_dev, n_jobs, prior, rows_lse, rows_last, stream, n_jobs_dev, fused);
+  const int rc = node_jobs_launch(a, jobs_dev, children_dev, n_jobs, prior, rows_lse, rows_last, stream, n_jobs_dev, mode);
   if (timed && rc == PCB_OK) {
     PCB_CUDA(cudaEventRecord(g_timing.ev[g_timing.used + 1], (cudaStream_t)stream));
     g_timing.used += 2;
@@ -489,7 +549,8 @@ int pcb_node_jobs_dev(const pcb_arena* a, const int32_t* jobs_dev, const int32_t
 // earlier in the stream)
 static int node_jobs_launch(const pcb_arena* a, const int32_t* jobs_dev, const int32_t* children_dev, int64_t n_jobs,
                             double prior, double* rows_lse, double* rows_last, void* stream, const int* n_jobs_dev,
-                            bool fused) {
+                            int mode) {
+  const bool fused = mode & kJobsFused;
   int rc = check_arena(a);
   if (rc) return rc;
   if (n_jobs <= 0) return PCB_OK;
@@ -518,7 +579,10 @@ static int node_jobs_launch(const pcb_arena* a, const int32_t* jobs_dev, const i
   kp.double_b = kp.rounds > 1 ? 0 : jobs_double_b();
   kp.n_jobs = n_jobs;
   kp.n_jobs_dev = n_jobs_dev;
-  if (l.kernel == 1) {
+  if ((l.kernel & PCB_KERNEL_LATENCY) && rows_supported(l) && ((mode & kJobsSmall) || (!n_jobs_dev && n_jobs <= rows_max_jobs()))) {
+    return launch_rows(kp, l, n_jobs, (cudaStream_t)stream);
+  }
+  if ((l.kernel & 3) == 1) {
     if (fused) return fail(PCB_ERR_ARG, "node_jobs: the unit-per-warp kernel has no fused jobs");
     const size_t wsmem = wide_smem_bytes(l.lanes_per_row, l.pitch);
     cudaStream_t wst = (cudaStream_t)stream;
@@ -1128,11 +1192,17 @@ int pcb_smc_sweep_dev(const pcb_arena* a, const pcb_sweep_desc* d, void* stream)
   P.pool_cap = pool_cap;
   P.tile_limit = (int)d->tile_limit;
   P.scratch0 = (int)d->tile_base;
+  bool small_jobs = false;
   {
     const char* e = getenv("PCB_SWEEP_FUSE");
-    P.fuse = (a->layout.kernel == 0 && (a->layout.strip == 7 || a->layout.strip == 13 || a->layout.strip == 17) &&
+    const char* e2 = getenv("PCB_ROWS_MAX_PARTICLES");
+    // a sweep of a few hundred particles launches a few hundred fold chains per step: the latency mapping
+    small_jobs = (a->layout.kernel & PCB_KERNEL_LATENCY) && rows_supported(a->layout) && N <= ((e2 && *e2) ? atoi(e2) : 256);
+    P.fuse = ((a->layout.kernel & 3) == 0 &&
+              (small_jobs || a->layout.strip == 7 || a->layout.strip == 13 || a->layout.strip == 17) &&
               !(e && atoi(e) == 0)) ? 1 : 0;
   }
+  const int jobs_mode = small_jobs ? kJobsSmall : 0;
 
   // ---- inputs: host -> device
   auto up = [&](const void* dst, const void* src, size_t bytes) -> cudaError_t {
@@ -1192,17 +1262,19 @@ int pcb_smc_sweep_dev(const pcb_arena* a, const pcb_sweep_desc* d, void* stream)
       ++launches;
     }
     const long long boundB = (long long)N * (std::min(Rmax, t) + 1);
-    if ((rc = jobs_launch_timed(a, P.jobsB, P.kidsB, boundB, d->prior, P.scB_lse, P.scB_last, stream, P.nB))) return rc;
+    if ((rc = jobs_launch_timed(a, P.jobsB, P.kidsB, boundB, d->prior, P.scB_lse, P.scB_last, stream, P.nB, jobs_mode)))
+      return rc;
     sw::decide_kernel<<<grid_decide, 32 * sw::kDecideWarps, 0, st>>>(P, t);
     PCB_LAUNCH_CHECK();
     launches += 3;
     if (t > 0) {
       if (!P.fuse) {
-        if ((rc = jobs_launch_timed(a, P.jobsD, P.kidsD, N, d->prior, nullptr, nullptr, stream, P.nD))) return rc;
+        if ((rc = jobs_launch_timed(a, P.jobsD, P.kidsD, N, d->prior, nullptr, nullptr, stream, P.nD, jobs_mode)))
+          return rc;
         ++launches;
       }
       if ((rc = jobs_launch_timed(a, P.jobsE, P.kidsE, 2ll * N, d->prior, P.scE_lse, P.scE_last, stream, P.nE,
-                                  P.fuse != 0)))
+                                  jobs_mode | (P.fuse ? kJobsFused : 0))))
         return rc;
       ++launches;
     }

@@ -889,6 +889,308 @@ __global__ void __launch_bounds__(128) node_jobs_wide_kernel(const JobKernelPara
 }
 
 // ---------------------------------------------------------------------------------
+// node_jobs_rows_kernel: the same job, mapped for LATENCY.  One WARP per tile row, RB rows (warps) per CTA.
+// The lane-per-unit kernel above gives a row to P = 4-8 lanes, each walking the ~Q+1 bodies of its strip pair in
+// sequence: ~2000 instructions per fold step for a lone warp, ~3.3 us -- and a chain's launches are a few hundred jobs
+// whose fold chains are what the chain waits for.  Here every output strip q (q+1 bodies: block m of L multipliers x
+// window of 2L-1 values) is split over ceil((q+1)/T) neighbouring lanes, T = the fewest bodies per lane for which the
+// Q strips fit 32 lanes (T = 5 at G = 101, L = 7: 30 lanes busy); a lane keeps its partial strip sums in registers,
+// the first lane of a strip adds up the partials of its neighbours in lane order (shuffles: deterministic), floors,
+// and the warp re-normalises the row.  ~3x fewer instructions per lane and fold step.  The operands of the fold are
+// double-buffered two children ahead (the TMA latency of a child is a whole fold step here).
+// Same tiles, job records and epilogues as above (32 lanes per row); a strip's sum is associated as up to ceil(Q/T)
+// partial FMA chains instead of one, i.e. equal to the kernel above to rounding (every term is >= 0: an output is
+// zero in one iff it is zero in the other, so the floor pattern is the same).  Used for small launches of stores that
+// ask for it (layout.kernel & PCB_KERNEL_LATENCY: csrc/pcb_api.cu).
+// p.RB = rows per CTA (divides S), p.row_blocks = S / RB, p.Q = strips (<= 32).
+// Shared memory: [256 B mbarriers][A: RB*pitch][B0: RB*pitch][B1: RB*pitch][256 B].
+// ---------------------------------------------------------------------------------
+template <int L>
+__global__ void __launch_bounds__(128) node_jobs_rows_kernel(const JobKernelParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);  // [0]: running product, [1] [2]: operand buffers
+  const int S = p.S, G = p.G, pitch = p.pitch, lead = p.lead, RB = p.RB, Q = p.Q;
+  constexpr int P = 32;
+  double* bufA = reinterpret_cast<double*>(smem_raw + kSmemHead);
+  double* bufB0 = bufA + RB * pitch;
+  const int tid = threadIdx.x, lane = tid & 31, wrow = tid >> 5;
+  const int lir = lane;
+  const bool row_ok = true;
+  const uint32_t bytes = (uint32_t)RB * pitch * 8u;
+  // this lane's share: bodies m_lo .. m_hi-1 of strip q_l; lanes of a strip are neighbours, gidx = position among them
+  const int T = p.P;  // bodies per lane (host: the smallest T with sum_q ceil((q+1)/T) <= 32)
+  int q_l = 0, m_lo = 0, m_hi = 0, gidx = 0, gsize = 0;
+  for (int q = 0, l0 = 0, n = 1, left = T; q < Q; ++q) {  // n = ceil((q+1)/T), `left` = strips until it grows
+    if (lane >= l0 && lane < l0 + n) {
+      const int per = (q + n) / n;  // ceil((q+1)/n)
+      q_l = q;
+      gidx = lane - l0;
+      gsize = n;
+      m_lo = min(q + 1, gidx * per);
+      m_hi = min(q + 1, m_lo + per);
+    }
+    l0 += n;
+    if (--left == 0) {
+      ++n;
+      left = T;
+    }
+  }
+  const int max_group = (Q - 1 + T) / T;  // lanes of the last (longest) strip
+  const bool head = gsize > 0 && gidx == 0;
+  const int n_valid = head ? max(0, min(L, G - q_l * L)) : 0;  // outputs of this lane's strip that lie inside the grid
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const long long n_work = (p.n_jobs_dev ? (long long)*p.n_jobs_dev : p.n_jobs) * p.row_blocks;
+  uint32_t ph0 = 0, ph1 = 0, ph2 = 0;
+  for (long long work = blockIdx.x; work < n_work; work += gridDim.x) {
+  if (work != (long long)blockIdx.x) {
+    __syncthreads();
+    if (tid == 0) fence_proxy_async();
+  }
+  const long long job = work / p.row_blocks;
+  const int rb = (int)(work - job * p.row_blocks);
+  const int row = rb * RB + wrow;
+  const size_t blk = (size_t)rb * RB * pitch;  // this row block inside a tile
+  const int32_t* jr = p.jobs + (size_t)job * 8;
+  const int coff = jr[0], C = jr[1], base = jr[2], outt = jr[3], flags = jr[4], slot = jr[5], base2 = jr[6] - 1;
+  const bool scan = flags & 1;
+  const double addc = (flags & 2) ? p.prior : 0.0;
+  const bool shortcut = scan && base < 0 && outt < 0;
+  const bool then_score = (flags & 4) && !shortcut;
+  const int C2 = then_score ? jr[7] : 0;
+  const int Ctot = C + C2;
+  // operands of the fold, in the order they are consumed: children 1 .. C-1 (a single child: its log form, for the
+  // epilogue), then the second-stage children C .. Ctot-1.  Operand o lives in buffer o & 1.
+  const int n_ops = (C >= 2 ? C - 1 : (shortcut ? 0 : 1)) + C2;
+  const int shift = (C >= 2) ? 1 : 0;  // operand o is child o + shift (operand 0 of a single-child job is special)
+  int chunk = 0;
+  int my_child = (lane < Ctot) ? p.children[coff + lane] : 0;
+  auto child_at = [&](int idx) -> int {  // uniform over the CTA
+    if ((idx >> 5) != chunk) {
+      chunk = idx >> 5;
+      my_child = (chunk * 32 + lane < Ctot) ? p.children[coff + chunk * 32 + lane] : 0;
+    }
+    return __shfl_sync(0xffffffffu, my_child, idx & 31);
+  };
+  const int c0 = child_at(0);
+  if (tid == 0) {
+    mbar_expect_tx(&bars[0], bytes);
+    tma_load_1d(bufA, p.lin + (size_t)c0 * p.tile_elems + blk, bytes, &bars[0]);
+  }
+  int issued = 0, oc = 0;  // operands requested / consumed by every row of the CTA
+  auto top_up = [&]() {    // after a CTA barrier: keep two operands in flight
+    while (issued < n_ops && issued < oc + 2) {
+      const bool lg0 = (C == 1 && issued == 0);
+      const int cid = lg0 ? c0 : child_at(issued + shift);
+      if (tid == 0) {
+        uint64_t* bar = &bars[1 + (issued & 1)];
+        fence_proxy_async();
+        mbar_expect_tx(bar, bytes);
+        tma_load_1d(bufB0 + (size_t)(issued & 1) * RB * pitch, (lg0 ? p.lg : p.lin) + (size_t)cid * p.tile_elems + blk,
+                    bytes, bar);
+      }
+      ++issued;
+    }
+  };
+  auto wait_operand = [&]() -> const double* {
+    const int b = oc & 1;
+    if (b) {
+      mbar_wait(&bars[2], ph2 & 1);
+      ++ph2;
+    } else {
+      mbar_wait(&bars[1], ph1 & 1);
+      ++ph1;
+    }
+    return bufB0 + (size_t)b * RB * pitch + wrow * pitch + lead;
+  };
+  top_up();
+  double M = p.rmax[(size_t)c0 * S + row];
+  mbar_wait(&bars[0], ph0 & 1);
+  ++ph0;
+  double* a_row = bufA + wrow * pitch + lead;
+
+  bool sc = shortcut;
+  double add = addc;
+  int jb = 1, je = C;
+  double Mf = 1.0;  // product of the re-normalisers' mantissas, and the sum of their exponents
+  int Me = 0;
+  for (int stage = 0;; ++stage) {
+  for (int j = jb; j < je; ++j) {
+    const int cj = child_at(oc + shift);
+    const double mB = p.rmax[(size_t)cj * S + row];
+    const double* b_row = wait_operand();
+    // ---- partial strip sums: body (q, m) = strip q of L outputs x block m of L multipliers, window x of 2L-1 values
+    double acc[L];
+#pragma unroll
+    for (int i = 0; i < L; ++i) acc[i] = 0.0;
+#pragma unroll 1
+    for (int m = m_lo; m < m_hi; ++m) {
+      const double* ap = a_row + (q_l - m) * L - (L - 1);  // negative indices are the row's lead zeros
+      const double* bp = b_row + m * L;
+      double x[2 * L - 1];
+#pragma unroll
+      for (int r = 0; r < 2 * L - 1; ++r) x[r] = ap[r];
+#pragma unroll
+      for (int pp = 0; pp < L; ++pp) {
+        const double bj = bp[pp];
+#pragma unroll
+        for (int i = 0; i < L; ++i) acc[i] = fma(bj, x[i - pp + L - 1], acc[i]);
+      }
+    }
+    __syncthreads();  // every row of the CTA is done with this operand buffer (and this row with its running product)
+    ++oc;
+    top_up();
+    // ---- the first lane of a strip adds the partial sums of its neighbours, in lane order
+    double y[L];
+#pragma unroll
+    for (int i = 0; i < L; ++i) y[i] = acc[i];
+    for (int d = 1; d < max_group; ++d) {
+      const bool mine = gidx + d < gsize;
+#pragma unroll
+      for (int i = 0; i < L; ++i) {
+        const double v = __shfl_down_sync(0xffffffffu, acc[i], d);
+        y[i] += mine ? v : 0.0;
+      }
+    }
+    // ---- floor (tree/utils.py:77), row maximum.  Every value is >= 0, so doubles order like their bit patterns:
+    // the warp maximum is two integer reductions (high words, then low words among the lanes holding the top one)
+    double lmax = 0.0;
+#pragma unroll
+    for (int i = 0; i < L; ++i) {
+      const double v = (y[i] > 0.0) ? y[i] : kFloor;
+      y[i] = (i < n_valid) ? v : 0.0;
+      lmax = (y[i] > lmax) ? y[i] : lmax;
+    }
+    const unsigned hi = (unsigned)__double2hiint(lmax), lo = (unsigned)__double2loint(lmax);
+    const unsigned hi_max = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned lo_max = __reduce_max_sync(0xffffffffu, hi == hi_max ? lo : 0u);
+    const double ymax = __hiloint2double((int)hi_max, (int)lo_max);  // >= kFloor: output 0 is inside the grid
+    M += mB;
+    double scale = 1.0;
+    if (j < je - 1) {
+      // re-normalise the running product exactly where the reference re-max-shifts it; log(ymax) is added to the row's
+      // shift as exponent + mantissa product, the logarithm itself taken once per fold (fold_shift below)
+      const int e = (int)((hi_max >> 20) & 0x7ffu) - 1023;
+      Mf *= __hiloint2double((int)((hi_max & 0x800fffffu) | 0x3ff00000u), (int)lo_max);  // mantissa in [1, 2)
+      Me += e;
+      if (__double2hiint(Mf) >= 0x40000000) {  // keep the product in [1, 2)
+        Mf *= 0.5;
+        ++Me;
+      }
+      scale = 1.0 / ymax;
+    }
+    if (head) {
+#pragma unroll
+      for (int i = 0; i < L; ++i) a_row[q_l * L + i] = y[i] * scale;
+    }
+    __syncwarp();
+  }
+  M += log(Mf) + (double)Me * 0.693147180559945309417;  // fold_shift: the sum of log(ymax) over the fold's steps
+  Mf = 1.0;
+  Me = 0;
+
+  double* yrow = a_row;
+  // ---- epilogue 1: dummy-root scoring without materialising the tile
+  if (sc) {
+    double t1 = 0.0, t2 = 0.0;
+    for (int k = lir; k < G; k += P) {
+      const double y = yrow[k];
+      t1 += y;
+      t2 = fma((double)(G - k), y, t2);
+    }
+    t1 = group_sum(t1, P);
+    t2 = group_sum(t2, P);
+    if (lir == 0 && slot >= 0) {
+      p.sc_lse[(size_t)slot * S + row] = (M + add) + log(t2);
+      p.sc_last[(size_t)slot * S + row] = (M + add) + log(t1);
+    }
+    break;
+  }
+  // ---- epilogue 2: elementwise log_D / log_S, + log_p, store tile, optional scores
+  if (C >= 2) {
+    if (scan) {
+      const int chunk_k = (G + P - 1) / P;
+      const int kbeg = min(G, lir * chunk_k), kend = min(G, kbeg + chunk_k);
+      double loc = 0.0;
+      for (int k = kbeg; k < kend; ++k) loc += yrow[k];
+      double run = group_excl_scan(loc, P, lir);
+      for (int k = kbeg; k < kend; ++k) {
+        run += yrow[k];
+        yrow[k] = log(run) + M;
+      }
+    } else {
+      for (int k = lir; k < G; k += P) yrow[k] = log(yrow[k]) + M;
+    }
+  } else {
+    const double* b_row = wait_operand();  // the single child's log form
+    if (scan) {
+      row_prefix_lse(b_row, yrow, G, P, lir, row_ok);
+    } else {
+      for (int k = lir; k < G; k += P) yrow[k] = b_row[k];
+    }
+    ++oc;
+  }
+  __syncwarp();
+  double vmax = -INFINITY;
+  {
+    const double* bptr = (base >= 0) ? p.lg + (size_t)base * p.tile_elems + (size_t)row * pitch + lead : nullptr;
+    const double* b2ptr = (bptr && base2 >= 0) ? p.lg + (size_t)base2 * p.tile_elems + (size_t)row * pitch + lead : nullptr;
+    for (int k = lir; k < G; k += P) {
+      double v = yrow[k];
+      if (bptr) {
+        double b = bptr[k];
+        if (b2ptr) b += b2ptr[k];
+        v = b + v;
+      }
+      v += addc;
+      yrow[k] = v;
+      vmax = fmax(vmax, v);
+    }
+  }
+  vmax = group_max(vmax, P);
+  double esum = 0.0;
+  {
+    double* olg = (outt >= 0) ? p.lg + (size_t)outt * p.tile_elems + (size_t)row * pitch + lead : nullptr;
+    double* olin = (outt >= 0) ? p.lin + (size_t)outt * p.tile_elems + (size_t)row * pitch + lead : nullptr;
+    for (int k = lir; k < G; k += P) {
+      const double v = yrow[k];
+      const double e = (v == -INFINITY) ? 0.0 : exp(v - vmax);
+      esum += e;
+      if (olg) {
+        olg[k] = v;
+        olin[k] = e;
+      }
+      if (then_score) yrow[k] = e;
+    }
+  }
+  esum = group_sum(esum, P);
+  __syncwarp();
+  if (lir == 0) {
+    if (outt >= 0) p.rmax[(size_t)outt * S + row] = vmax;
+    if (slot >= 0 && !then_score) {
+      p.sc_lse[(size_t)slot * S + row] = (vmax == -INFINITY) ? -INFINITY : vmax + log(esum);
+      p.sc_last[(size_t)slot * S + row] = yrow[G - 1];
+    }
+  }
+  if (!then_score || stage == 1) break;
+  // ---- second stage: the tile just written is the first root of a dummy-root fold over children C .. Ctot-1
+  M = vmax;
+  __syncthreads();  // every row has left the operand buffer (a single-child first stage read it in its epilogue)
+  top_up();
+  sc = true;
+  add = p.prior;
+  jb = C;
+  je = Ctot;
+  }  // stages
+  }  // work items
+}
+
+// ---------------------------------------------------------------------------------
 // Elementwise tile kernels.  One P-lane... one warp per (tile, row).
 // ---------------------------------------------------------------------------------
 // dense [n][S][G] -> arena (lg, lin, rmax) at ids[n]

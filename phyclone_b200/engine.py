@@ -68,6 +68,17 @@ class DeviceArena:
         self._plan_synced = True
         self._plan_np = self._sums_np = None
 
+    LATENCY = 4  # PCB_KERNEL_LATENCY (include/phyclone_b200.h)
+
+    def set_latency(self, on=True):
+        """Ask for the warp-per-row mapping of small launches (layout.kernel bit 4: csrc/pcb_api.cu).  Results equal
+        the default mapping's to rounding (a different association of the same non-negative sums)."""
+        if on:
+            self.layout.kernel |= self.LATENCY
+        else:
+            self.layout.kernel &= ~self.LATENCY
+        self.c = _lib.Arena(self.layout, self.lg.data_ptr(), self.lin.data_ptr(), self.rmax.data_ptr(), self.capacity)
+
     def grow(self, new_capacity):
         """Enlarge the arena in place (tile ids stay valid): new zero-filled tensors, old content copied over."""
         new_capacity = int(new_capacity)

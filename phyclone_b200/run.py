@@ -61,6 +61,10 @@ class Chain(object):
             # a chain launches a handful of jobs at a time: the layout with the shortest launches (-2.7 % per step)
             store = TileStore(np.array([dp.value for dp in data]), device=device, variant=TileStore.LATENCY_LAYOUT)
         self.store = store
+        # a device-mode chain is defined up to rounding (uniform-driven draws): its launches of a few hundred jobs take
+        # the latency mapping of the job kernel.  Host mode keeps the default mapping (bit-exact golden traces).
+        if sweep == "device" and os.environ.get("PCB_LATENCY_KERNEL", "1") != "0" and hasattr(store.arena, "set_latency"):
+            store.arena.set_latency(True)
         self.tree_dist = TreeJointDistribution(FSCRPDistribution(concentration_value))
         self.kernel = setup_kernel(outlier_prob, proposal, rng, self.tree_dist, store, perm_dist=perm_dist)
         self.dp_sampler = DataPointSampler(self.tree_dist, rng, outliers=(outlier_prob > 0))

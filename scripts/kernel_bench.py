@@ -16,10 +16,12 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from phyclone_b200 import engine, ops  # noqa: E402
 
 
-def bench_variant(S, G, variant, n_jobs, C, n_tiles, reps, score_only=True):
+def bench_variant(S, G, variant, n_jobs, C, n_tiles, reps, score_only=True, latency=False):
     """score_only=True: dummy-root jobs (scores, no tile written, no log_p read).  score_only=False: full node
     refreshes -- every job reads a log_p tile and writes its log_r tile (log + lin + row maxima) to its own slot."""
     ar = engine.DeviceArena(S, G, n_tiles + 1 + (0 if score_only else n_jobs), variant=variant)
+    if latency:
+        ar.set_latency(True)  # the warp-per-row mapping for launches of <= PCB_ROWS_MAX_JOBS jobs
     rng = np.random.default_rng(0)
     dense = torch.log(torch.rand((n_tiles, S, G), dtype=torch.float64, device=ar.device) * 999.9 + 0.1)
     ar.import_tiles(dense, np.arange(n_tiles))

@@ -111,8 +111,12 @@ def _compare_chain(vals, probs, particles, outlier_prob, burnin, iters, seed, wh
     return st
 
 
+@pytest.mark.parametrize("mapping", ["latency", "default"])
 @pytest.mark.parametrize("name,particles,iters", [("syn12", 16, 6), ("mixing", 20, 8), ("syn8_outliers", 12, 6)])
-def test_device_sweep_matches_uniform_oracle(name, particles, iters):
+def test_device_sweep_matches_uniform_oracle(name, particles, iters, mapping, monkeypatch):
+    """Both mappings of the job kernel: device-mode chains take the warp-per-row one for their small launches
+    (run.py), PCB_LATENCY_KERNEL=0 keeps the lane-per-unit one."""
+    monkeypatch.setenv("PCB_LATENCY_KERNEL", "1" if mapping == "latency" else "0")
     g = load_chain(name)
     vals = g["values"]
     probs = None

@@ -251,8 +251,8 @@ def test_device_arena_jobs_match_oracle(golden):
     torch.cuda.synchronize()
 
 
-@pytest.mark.parametrize("variant", [-1, 1304, 708, 11304, 10704])
-@pytest.mark.parametrize("S,G,n_jobs", [(4, 101, 37), (8, 101, 21), (2, 64, 50), (16, 101, 5)])
+@pytest.mark.parametrize("variant", [-1, 1304, 708, 11304, 10704, "latency", "latency-2"])
+@pytest.mark.parametrize("S,G,n_jobs", [(4, 101, 37), (8, 101, 21), (2, 64, 50), (16, 101, 5), (8, 224, 9), (1, 7, 3)])
 def test_mixed_job_batches_match_oracle(variant, S, G, n_jobs):
     """One launch with jobs of every kind side by side -- 1..6 children, dummy-root scores, nodes with and without
     log_p / output tile / score slot -- which in the unit-per-warp kernel (variants >= 10000) share CTAs and warps."""
@@ -263,11 +263,19 @@ def test_mixed_job_batches_match_oracle(variant, S, G, n_jobs):
     tiles = np.log(rng.uniform(0.1, 1000, size=(n_in, S, G)))
     tiles[3] = -((np.arange(G)[None] - rng.uniform(0, G, (S, 1))) ** 2) * 4.0  # floors
     tiles[7, :, : G // 2] -= 900.0
+    # "latency": the warp-per-row mapping (node_jobs_rows_kernel) on the default / the chain's layout
+    latency = isinstance(variant, str)
+    if latency:
+        variant = -2 if variant.endswith("-2") else -1
     try:
         ar = engine.DeviceArena(S, G, n_in + n_jobs + 4, variant=variant)
     except _lib.PcbError as e:
         assert "layout" in str(e)
         pytest.skip("variant %d does not cover (%d, %d)" % (variant, S, G))
+    if latency:
+        if ar.layout.kernel & 3:
+            pytest.skip("the unit-per-warp layout has no latency mapping")
+        ar.set_latency(True)
     ar.import_tiles(tiles, list(range(n_in)))
     prior = ar.prior
     jobs, kids, want = [], [], []
