@@ -123,6 +123,25 @@ long long lane_slots(int G, int L, int P) {
   return P * ((U + P - 1) / P) * (Q + 1) * L * L;
 }
 
+// ---- programmatic dependent launch: inside the sweep's chain of ~300 small dependent kernels every launch is allowed
+// to start while its predecessor drains (the kernels hold at pdl_wait() before touching anything the predecessor
+// wrote; csrc/pcb_device.cuh).  Off everywhere else.  PCB_SWEEP_PDL=0 disables it.
+thread_local bool g_pdl = false;
+template <typename... KArgs, typename... Args>
+cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+
 // CTAs of a launch whose job count only the device knows: a pool that covers the device once at the kernel's occupancy
 int pool_ctas() {
   static int v = 0;
@@ -144,8 +163,8 @@ int launch_jobs_LF(const pcb::JobKernelParams& kp, long long n_jobs, int threads
   }
   const long long grid = kp.n_jobs_dev ? std::min<long long>(n_jobs * kp.row_blocks, pool_ctas()) : n_jobs * kp.row_blocks;
   if (grid > 2147483647ll) return fail(PCB_ERR_ARG, "too many jobs for one launch");
-  pcb::node_jobs_kernel<L, FUSE, MULTI><<<(unsigned)grid, threads, smem, st>>>(kp);
-  PCB_LAUNCH_CHECK();
+  PCB_CUDA(launch_k(pcb::node_jobs_kernel<L, FUSE, MULTI>, dim3((unsigned)grid), dim3(threads), smem, st, kp));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   return PCB_OK;
 }
 
@@ -180,8 +199,8 @@ int launch_wide_L(const pcb::JobKernelParams& kp, long long n_jobs, size_t smem,
   long long grid = (n_jobs * kp.S + 31) / 32;
   if (kp.n_jobs_dev) grid = std::min<long long>(grid, pool_ctas() / 4);
   if (grid > 2147483647ll) return fail(PCB_ERR_ARG, "too many jobs for one launch");
-  pcb::node_jobs_wide_kernel<L><<<(unsigned)grid, 32 * kp.P, smem, st>>>(kp);
-  PCB_LAUNCH_CHECK();
+  PCB_CUDA(launch_k(pcb::node_jobs_wide_kernel<L>, dim3((unsigned)grid), dim3(32 * kp.P), smem, st, kp));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   return PCB_OK;
 }
 
@@ -216,8 +235,8 @@ int launch_rows_L(const pcb::JobKernelParams& kp, long long n_jobs, size_t smem,
   // device-counted launches: a pool that covers the device a few times over
   const long long grid = kp.n_jobs_dev ? std::min<long long>(n_jobs * kp.row_blocks, pool_ctas() / 3) : n_jobs * kp.row_blocks;
   if (grid > 2147483647ll) return fail(PCB_ERR_ARG, "too many jobs for one launch");
-  pcb::node_jobs_rows_kernel<L><<<(unsigned)grid, 32 * kp.RB, smem, st>>>(kp);
-  PCB_LAUNCH_CHECK();
+  PCB_CUDA(launch_k(pcb::node_jobs_rows_kernel<L>, dim3((unsigned)grid), dim3(32 * kp.RB), smem, st, kp));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   return PCB_OK;
 }
 int launch_rows(pcb::JobKernelParams kp, const pcb_layout& l, long long n_jobs, cudaStream_t st) {
@@ -1249,23 +1268,32 @@ int pcb_smc_sweep_dev(const pcb_arena* a, const pcb_sweep_desc* d, void* stream)
   int64_t launches = 1;
   const unsigned grid_build = (unsigned)((N + sw::kBuildWarps - 1) / sw::kBuildWarps);
   const unsigned grid_decide = (unsigned)((N + sw::kDecideWarps - 1) / sw::kDecideWarps);
+  struct PdlScope {  // every launch of the loop below may overlap its predecessor's tail (launch_k)
+    PdlScope() {
+      const char* e = getenv("PCB_SWEEP_PDL");
+      g_pdl = !(e && atoi(e) == 0);
+    }
+    ~PdlScope() { g_pdl = false; }
+  };
+  {
+  PdlScope pdl_scope;
   for (int t = 0; t < T; ++t) {
-    sw::build_kernel<<<grid_build, 32 * sw::kBuildWarps, 0, st>>>(P, t);
-    PCB_LAUNCH_CHECK();
+    PCB_CUDA(launch_k(sw::build_kernel, dim3(grid_build), dim3(32 * sw::kBuildWarps), 0, st, P, t));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     if (t > 0) {
       const int wpb = 8;
       const long long max_rows = (long long)N * std::min(Rmax, t) * S;
       const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((max_rows + wpb - 1) / wpb, 148 * 8));
-      sw::add_list_kernel<<<grid, wpb * 32, 0, st>>>(P.addA, P.addB, P.addO, P.nAdd, a->lg, a->lin, a->rmax, l.S, l.G,
-                                                    l.pitch, l.lead, l.tile_elems);
-      PCB_LAUNCH_CHECK();
+      PCB_CUDA(launch_k(sw::add_list_kernel, dim3(grid), dim3(wpb * 32), 0, st, P.addA, P.addB, P.addO, P.nAdd, a->lg, a->lin,
+                        a->rmax, l.S, l.G, l.pitch, l.lead, (long long)l.tile_elems));
+      g_launches.fetch_add(1, std::memory_order_relaxed);
       ++launches;
     }
     const long long boundB = (long long)N * (std::min(Rmax, t) + 1);
     if ((rc = jobs_launch_timed(a, P.jobsB, P.kidsB, boundB, d->prior, P.scB_lse, P.scB_last, stream, P.nB, jobs_mode)))
       return rc;
-    sw::decide_kernel<<<grid_decide, 32 * sw::kDecideWarps, 0, st>>>(P, t);
-    PCB_LAUNCH_CHECK();
+    PCB_CUDA(launch_k(sw::decide_kernel, dim3(grid_decide), dim3(32 * sw::kDecideWarps), 0, st, P, t));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     launches += 3;
     if (t > 0) {
       if (!P.fuse) {
@@ -1278,9 +1306,10 @@ int pcb_smc_sweep_dev(const pcb_arena* a, const pcb_sweep_desc* d, void* stream)
         return rc;
       ++launches;
     }
-    sw::weigh_kernel<<<1, 1024, 0, st>>>(P, t, d->log_uniform, d->lw_uniform);
-    PCB_LAUNCH_CHECK();
+    PCB_CUDA(launch_k(sw::weigh_kernel, dim3(1), dim3(1024), 0, st, P, t, d->log_uniform, d->lw_uniform));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     ++launches;
+  }
   }
   PCB_CUDA(cudaEventRecord(g_sw.e1, st));
 

@@ -44,6 +44,11 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
 }
 
 // order earlier generic-proxy accesses to shared memory before later async-proxy (TMA) writes
+// Programmatic dependent launch (the sweep's kernel chain, csrc/pcb_api.cu): `pdl_trigger` lets the next kernel of the
+// stream start its prologue while this grid still runs, `pdl_wait` holds a kernel until everything before it in the
+// stream has completed and its writes are visible.  Both are no-ops in a launch without the attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // reductions over the P consecutive lanes (P power of two <= 32) that share one tile row

@@ -268,6 +268,8 @@ __global__ void __launch_bounds__(32, (L == 13 && !FUSE && !MULTI) ? 12 : 1) nod
   // A CTA walks work items blockIdx.x, blockIdx.x + gridDim.x, ...: a host-sized launch has one item per CTA; a launch
   // whose job count only the device knows (n_jobs_dev) runs a fixed pool of CTAs.  The mbarriers live across items,
   // so their phases are running counters.
+  pdl_trigger();  // a launch inside the sweep's chain: the prologue above overlapped the previous kernel's tail
+  pdl_wait();
   const long long n_work = (p.n_jobs_dev ? (long long)*p.n_jobs_dev : p.n_jobs) * p.row_blocks;
   uint32_t ph0 = 0, ph1 = 0, ph2 = 0;
   for (long long work = blockIdx.x; work < n_work; work += gridDim.x) {
@@ -639,6 +641,8 @@ __global__ void __launch_bounds__(128) node_jobs_wide_kernel(const JobKernelPara
   }
   __syncthreads();
   // a CTA walks 32-row blocks blockIdx.x, blockIdx.x + gridDim.x, ... (see node_jobs_kernel): running mbarrier phases
+  pdl_trigger();
+  pdl_wait();
   const long long n_jobs_all = p.n_jobs_dev ? (long long)*p.n_jobs_dev : p.n_jobs;
   const long long total_rows = n_jobs_all * S;
   const long long n_blocks = (total_rows + 31) / 32;
@@ -945,6 +949,8 @@ __global__ void __launch_bounds__(128) node_jobs_rows_kernel(const JobKernelPara
     mbar_fence_init();
   }
   __syncthreads();
+  pdl_trigger();  // a launch inside the sweep's chain: the prologue above overlapped the previous kernel's tail
+  pdl_wait();
   const long long n_work = (p.n_jobs_dev ? (long long)*p.n_jobs_dev : p.n_jobs) * p.row_blocks;
   uint32_t ph0 = 0, ph1 = 0, ph2 = 0;
   for (long long work = blockIdx.x; work < n_work; work += gridDim.x) {

@@ -162,6 +162,8 @@ __device__ inline void put_job(int* jobs, int j, int coff, int C, int base, int 
 constexpr int kBuildWarps = 8;
 
 __global__ void build_kernel(const Params p, const int t) {
+  pdl_trigger();
+  pdl_wait();
   // slot 0 of a conditional sweep is the retained particle: it builds candidates too (its own proposal probability
   // is needed for its weight, and every particle equal to it shares them), but its state comes from the path tables
   const int first = 0;
@@ -236,6 +238,8 @@ __global__ void build_kernel(const Params p, const int t) {
 __global__ void add_list_kernel(const int* __restrict__ a_ids, const int* __restrict__ b_ids,
                                 const int* __restrict__ out_ids, const int* __restrict__ n_dev, double* lg, double* lin,
                                 double* rmax, int S, int G, int pitch, int lead, long long tile_elems) {
+  pdl_trigger();
+  pdl_wait();
   const long long n_rows = (long long)(*n_dev) * S;
   const int lane = threadIdx.x & 31;
   const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
@@ -338,6 +342,8 @@ __global__ void decide_kernel(const Params p, const int t) {
   __shared__ double sh_lp[kDecideWarps][kMaxRoots + 2], sh_lp1[kDecideWarps][kMaxRoots + 2],
       sh_q[kDecideWarps][kMaxRoots + 2];
   __shared__ int4 sh_rec[kDecideWarps][2][kRec4];
+  pdl_trigger();
+  pdl_wait();
   const int first = 0;  // slot 0 of a conditional sweep: the retained particle, whose edit is given (see below)
   const int Rmax = p.Rmax;
   const int lane = threadIdx.x & 31, wslot = threadIdx.x >> 5;
@@ -809,6 +815,8 @@ __global__ void weigh_kernel(const Params p, const int t, const double log_unifo
   __shared__ double sh_w[1024];
   __shared__ int sh_cnt[1024];
   __shared__ int sh_anc[1024];
+  pdl_trigger();
+  pdl_wait();
   const int first = p.conditional ? 1 : 0;
   const int N = p.N, i = threadIdx.x;
   const bool last = t >= p.T - 1;
