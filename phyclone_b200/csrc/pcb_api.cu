@@ -127,6 +127,16 @@ long long lane_slots(int G, int L, int P) {
 // to start while its predecessor drains (the kernels hold at pdl_wait() before touching anything the predecessor
 // wrote; csrc/pcb_device.cuh).  Off everywhere else.  PCB_SWEEP_PDL=0 disables it.
 thread_local bool g_pdl = false;
+struct PdlScope {  // launches made while one is alive carry the attribute (PCB_SWEEP_PDL=0: never)
+  PdlScope() {
+    static const bool on = [] {
+      const char* e = getenv("PCB_SWEEP_PDL");
+      return !(e && atoi(e) == 0);
+    }();
+    g_pdl = on;
+  }
+  ~PdlScope() { g_pdl = false; }
+};
 template <typename... KArgs, typename... Args>
 cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
@@ -496,9 +506,10 @@ int pcb_tile_add_dev(const pcb_arena* a, const int32_t* a_ids, const int32_t* b_
   const long long warps = n * l.S;
   if ((warps + 3) / 4 > 2147483647ll) return fail(PCB_ERR_ARG, "tile_add: too many tiles for one launch");
   const int wpb = 4;
-  pcb::tile_add_kernel<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
-      a_ids, b_ids, out_ids, n, b_sign, addend, a->lg, a->lin, a->rmax, l.S, l.G, l.pitch, l.lead, l.tile_elems);
-  PCB_LAUNCH_CHECK();
+  PCB_CUDA(launch_k(pcb::tile_add_kernel, dim3((unsigned)((warps + wpb - 1) / wpb)), dim3(wpb * 32), 0, (cudaStream_t)stream,
+                    a_ids, b_ids, out_ids, (long long)n, b_sign, addend, a->lg, a->lin, a->rmax, l.S, l.G, l.pitch, l.lead,
+                    (long long)l.tile_elems));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   return PCB_OK;
 }
 
@@ -686,6 +697,7 @@ int pcb_run_plan_dev(const pcb_arena* a, const int32_t* packed_host, int64_t n_i
     }
   }
   PCB_CUDA(cudaMemcpyAsync(packed_dev, packed_host, (size_t)n_ints * 4, cudaMemcpyHostToDevice, st));
+  PdlScope pdl_scope;  // the plan's launches depend on each other level by level: let each start in its predecessor's tail
   for (int r = 0; r < n_rec; ++r) {
     const int32_t* rec = plan + 6 * r;
     const int64_t off = rec[1], n = rec[2];
@@ -702,9 +714,9 @@ int pcb_run_plan_dev(const pcb_arena* a, const int32_t* packed_host, int64_t n_i
     // one launch reduces both score kinds over the samples and writes the sums straight into the caller's pinned
     // (device-accessible) host buffer: no separate device-to-host copy; the synchronise below makes them visible
     (void)sums_dev;
-    pcb::reduce_rows2_kernel<<<(unsigned)((2 * n_slots + 127) / 128), 128, 0, st>>>(rows_lse, rows_last, n_slots,
-                                                                                  a->layout.S, sums_host);
-    PCB_LAUNCH_CHECK();
+    PCB_CUDA(launch_k(pcb::reduce_rows2_kernel, dim3((unsigned)((2 * n_slots + 127) / 128)), dim3(128), 0, st, rows_lse,
+                      rows_last, (long long)n_slots, a->layout.S, sums_host));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     const auto t_enq = std::chrono::steady_clock::now();
     PCB_CUDA(cudaStreamSynchronize(st));
     const auto t_end = std::chrono::steady_clock::now();
@@ -1268,13 +1280,6 @@ int pcb_smc_sweep_dev(const pcb_arena* a, const pcb_sweep_desc* d, void* stream)
   int64_t launches = 1;
   const unsigned grid_build = (unsigned)((N + sw::kBuildWarps - 1) / sw::kBuildWarps);
   const unsigned grid_decide = (unsigned)((N + sw::kDecideWarps - 1) / sw::kDecideWarps);
-  struct PdlScope {  // every launch of the loop below may overlap its predecessor's tail (launch_k)
-    PdlScope() {
-      const char* e = getenv("PCB_SWEEP_PDL");
-      g_pdl = !(e && atoi(e) == 0);
-    }
-    ~PdlScope() { g_pdl = false; }
-  };
   {
   PdlScope pdl_scope;
   for (int t = 0; t < T; ++t) {

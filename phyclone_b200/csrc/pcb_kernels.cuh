@@ -1239,6 +1239,8 @@ __global__ void tile_add_kernel(const int32_t* __restrict__ a_ids, const int32_t
                                 const int32_t* __restrict__ out_ids, long long n, double b_sign, double addend,
                                 double* lg,
                                 double* lin, double* rmax, int S, int G, int pitch, int lead, long long tile_elems) {
+  pdl_trigger();
+  pdl_wait();
   const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (wid >= n * S) return;
@@ -1282,6 +1284,8 @@ __global__ void reduce_rows_kernel(const double* __restrict__ rows, long long n,
 // reads them and a flush needs no device-to-host copy.
 __global__ void reduce_rows2_kernel(const double* __restrict__ lse_rows, const double* __restrict__ last_rows,
                                     long long n, int S, double* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 2 * n) return;
   const double* rows = (i < n) ? lse_rows + i * S : last_rows + (i - n) * S;
