@@ -377,7 +377,10 @@ def run_ours(args):
     # ---- timed region 1: inputs resident in HBM.  Iterations of an MCMC chain differ in cost (the forest changes), so
     # the chain is rewound after this leg: both legs run the SAME iterations and differ only in the host transfers
     snap = chain.snapshot()
-    ops.timing_begin(2000 * args.steps + 4096)
+    # every 3rd launch of the job kernel is bracketed by an event pair (odd: a sweep step launches the kernel twice, the
+    # sample must alternate between the two); see roofline.timing
+    TIMING_STRIDE = 3
+    ops.timing_begin(2000 * args.steps + 4096, stride=TIMING_STRIDE)
     s0 = dict(chain.stats)
     plan0 = ops.plan_stats()
     launches0 = ops.launch_count()
@@ -399,13 +402,18 @@ def run_ours(args):
     else:
         splits = [split]
     splits = [[float(x) for x in t.tolist()] for t in splits]
+    n_seen = ops.timing_seen()
     kernel_ms, n_timed = ops.timing_end()
+    ops.timing_begin(1, stride=1)  # back to the default stride for whoever times next
+    ops.timing_end()
     def all_pairs(st):  # pair convolutions folded by flushes of the tile store + by device-resident sweeps
         return st["conv_pairs"] + sum(st.get(k, {}).get("conv_pairs", 0) for k in ("sweep", "burnin_sweep"))
 
     conv_pairs = all_pairs(s1) - all_pairs(s0)
     flop = conv_pairs * CFG["samples"] * CFG["grid"] * (CFG["grid"] + 1)  # 2 flop x S*G*(G+1)/2 FMA per pair conv
     n_launch = max(n_timed, 1)
+    avg_launch_ms = kernel_ms / n_launch
+    kernel_ms = avg_launch_ms * max(n_seen, n_timed)  # all launches of the region at the sampled average duration
     achieved = flop / max(kernel_ms * 1e-3, 1e-12)
     value = world * args.steps / (ms * 1e-3)
 
@@ -474,8 +482,9 @@ def run_ours(args):
                                                 "writing its log_r tile (log + linear + row maxima)",
                                       "achieved": r3["tflops"], "frac": r3["tflops"] * 1e12 / fp64_peak},
                    "layout": "throughput layout (L=%d, P=%d): what a saturated batch would run with" % (r["L"], r["P"]),
-                   "chain_layout": {"layout": "latency layout (L=%d, P=%d): what the timed chain runs with, its launches "
-                                              "being ~20 jobs" % (r2["L"], r2["P"]),
+                   "chain_layout": {"layout": "the chain's tile layout (L=%d, P=%d) in the lane-per-unit mapping on a "
+                                              "saturated batch; the chain's own launches (<= 1024 jobs) run the "
+                                              "warp-per-row mapping, which trades throughput for latency" % (r2["L"], r2["P"]),
                                     "achieved": r2["tflops"], "frac": r2["tflops"] * 1e12 / fp64_peak}}
         except Exception as e:  # noqa: BLE001
             sat = {"error": str(e)}
@@ -546,10 +555,15 @@ def run_ours(args):
             "limiter": "host sampler logic (one Python thread per chain) + serial device latency: see "
                        "per_rank_split_ms_per_step; chains never exchange data",
             "cpu_pinning": pinned,
-            "roofline": {"bound": "fp64", "kernel": "node_jobs_kernel", "achieved": achieved / 1e12,
+            "roofline": {"bound": "fp64", "kernel": "node_jobs_rows_kernel / node_jobs_kernel (the job kernel's two mappings)", "achieved": achieved / 1e12,
                          "peak": fp64_peak / 1e12, "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": traffic, "traffic_source": traffic_src,
-                         "launches": int(n_timed), "avg_launch_us": 1e3 * kernel_ms / n_launch,
-                         "flop_per_launch": flop / n_launch, "kernel_share_of_step": kernel_ms / ms,
+                         "launches": int(max(n_seen, n_timed)), "avg_launch_us": 1e3 * avg_launch_ms,
+                         "flop_per_launch": flop / max(n_seen, n_timed, 1), "kernel_share_of_step": kernel_ms / ms,
+                         "timing": "CUDA event pairs (library-owned, on the launching stream) around every %d%s launch of the "
+                                   "job kernel inside the timed region: %d of %d launches; an event pair drains the stream "
+                                   "and keeps the next kernel from starting in its predecessor's tail, so bracketing every "
+                                   "launch slowed the chain it measured by 15 %%" % (
+                                       TIMING_STRIDE, "rd" if TIMING_STRIDE == 3 else "th", n_timed, max(n_seen, n_timed)),
                          "peak_source": "pcb_fp64_peak (dependent-DFMA-chain microbenchmark) measured in this run; "
                                         "MEASURED_PEAKS.json has no FP64 figure (hbm_gbs=%s)" % peaks.get("hbm_gbs"),
                          "saturated_batch": sat},

@@ -187,6 +187,11 @@ int pcb_plan_stats(double* enqueue_s, double* sync_s, int64_t* flushes);
  * durations and the number of launches recorded (at most max_launches). */
 int pcb_timing_begin(int32_t max_launches);
 int pcb_timing_end(double* total_ms, int64_t* n_launches);
+/* stride >= 1: from now on only every stride-th launch is bracketed (an event pair drains the stream and keeps the next
+ * kernel from starting in its predecessor's tail, so bracketing every launch slows what it measures); n_seen (may be
+ * NULL) receives the number of node-jobs launches since the last begin, bracketed or not.  Call it before
+ * pcb_timing_end to read the count. */
+int pcb_timing_sample(int32_t stride, int64_t* n_seen);
 
 /* MAP cellular prevalences of B trees: the max-plus twin of the node fold with back-pointers.
  *   process_trace/map.py:48-64 compute_max_likelihood, :67-93 compute_log_S (prefix max, ties to the earliest

@@ -56,6 +56,7 @@ SIGNATURES = {
     "pcb_plan_stats": (C.c_int, [C.POINTER(_f64), C.POINTER(_f64), C.POINTER(_i64)]),
     "pcb_timing_begin": (C.c_int, [_i32]),
     "pcb_timing_end": (C.c_int, [C.POINTER(_f64), C.POINTER(_i64)]),
+    "pcb_timing_sample": (C.c_int, [_i32, C.POINTER(_i64)]),
     "pcb_reduce_rows_dev": (C.c_int, [_P, _i64, _i32, _P, _P]),
     "pcb_np_conv_dims_host": (C.c_int, [_P, _P, _P, _i64, _i32, _i32]),
     "pcb_sub_compute_S_host": (C.c_int, [_P, _P, _i64, _i32, _i32]),

@@ -519,6 +519,8 @@ struct JobTiming {
   bool on = false;
   std::vector<cudaEvent_t> ev;  // 2 per recorded launch
   size_t used = 0, cap = 0;
+  int stride = 1;       // every stride-th launch is bracketed (pcb_timing_sample)
+  int64_t seen = 0;     // node-jobs launches since begin, bracketed or not
 };
 thread_local JobTiming g_timing;  // a chain is one host thread: its kernel timing is its own
 
@@ -532,7 +534,14 @@ int pcb_timing_begin(int32_t max_launches) {
   }
   g_timing.cap = want;
   g_timing.used = 0;
+  g_timing.seen = 0;
   g_timing.on = true;
+  return PCB_OK;
+}
+
+int pcb_timing_sample(int32_t stride, int64_t* n_seen) {
+  if (stride >= 1) g_timing.stride = stride;
+  if (n_seen) *n_seen = g_timing.seen;
   return PCB_OK;
 }
 
@@ -560,7 +569,7 @@ static int node_jobs_launch(const pcb_arena* a, const int32_t* jobs_dev, const i
 static int jobs_launch_timed(const pcb_arena* a, const int32_t* jobs_dev, const int32_t* children_dev, int64_t n_jobs,
                              double prior, double* rows_lse, double* rows_last, void* stream, const int* n_jobs_dev,
                              int mode = 0) {
-  const bool timed = g_timing.on && n_jobs > 0 && g_timing.used + 2 <= g_timing.cap;
+  const bool timed = g_timing.on && n_jobs > 0 && (g_timing.seen++ % g_timing.stride) == 0 && g_timing.used + 2 <= g_timing.cap;
   if (timed) PCB_CUDA(cudaEventRecord(g_timing.ev[g_timing.used], (cudaStream_t)stream));
   const int rc = node_jobs_launch(a, jobs_dev, children_dev, n_jobs, prior, rows_lse, rows_last, stream, n_jobs_dev, mode);
   if (timed && rc == PCB_OK) {

@@ -222,9 +222,18 @@ def launch_count():
     return int(_lib.load().pcb_launch_count())
 
 
-def timing_begin(max_launches=1 << 16):
-    """Bracket every node-jobs launch with a CUDA event pair (library-owned) until `timing_end`."""
-    _lib.check(_lib.require_device().pcb_timing_begin(int(max_launches)))
+def timing_begin(max_launches=1 << 16, stride=1):
+    """Bracket every `stride`-th node-jobs launch with a CUDA event pair (library-owned) until `timing_end`."""
+    lib = _lib.require_device()
+    _lib.check(lib.pcb_timing_sample(int(stride), None))
+    _lib.check(lib.pcb_timing_begin(int(max_launches)))
+
+
+def timing_seen():
+    """Node-jobs launches since `timing_begin`, bracketed or not (read it before `timing_end`)."""
+    n = C.c_int64(0)
+    _lib.check(_lib.require_device().pcb_timing_sample(0, C.byref(n)))
+    return n.value
 
 
 def timing_end():
