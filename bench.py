@@ -263,6 +263,8 @@ def cpu_rate(kind, iters, warmup, n_chains=1, max_seconds=420.0):
     # iterations is the slowest chain's, times the number of waves
     waves = -(-n_chains // cores)
     elapsed = max(t[warm_done + timed] - t[warm_done] for t in traces) * waves
+    if not elapsed > 0:  # the wall cap cut the run inside an iteration: the trace's last stamps coincide
+        return None, 0, warm_done, wall, cores
     return n_chains * timed / elapsed, timed, warm_done, wall, cores
 
 
