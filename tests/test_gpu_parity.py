@@ -310,3 +310,56 @@ def test_mixed_job_batches_match_oracle(variant, S, G, n_jobs):
             assert sc[0, j] == pytest.approx(lse, rel=1e-9), j
             if np.isfinite(last) and tile[:, -1].min() > tile.max() - 600:
                 assert sc[1, j] == pytest.approx(last, rel=1e-9), j
+
+
+@pytest.mark.parametrize("S", [1, 3, 8])
+def test_latency_mapping_across_grid_sizes(S):
+    """The warp-per-row mapping deals the strips of a row to lanes by a rule that depends on the number of strips
+    (csrc/pcb_kernels.cuh node_jobs_rows_kernel): every strip count 1 .. 32 at L = 7, plus wider strips, against the
+    oracle and against the lane-per-unit mapping of the same layout."""
+    from phyclone_b200 import _lib, engine
+
+    rng = np.random.default_rng(7 + S)
+    cases = [(-2, G) for G in (1, 2, 6, 7, 8, 13, 14, 15, 49, 50, 97, 98, 99, 105, 106, 111, 112, 113, 150, 196, 217, 224)]
+    cases += [(1308, 101), (1308, 201), (1316, 300), (1732, 400), (1732, 540)]
+    ran = 0
+    for variant, G in cases:
+        try:
+            ar = engine.DeviceArena(S, G, 16, variant=variant)
+        except _lib.PcbError:
+            continue
+        if ar.layout.kernel & 3:
+            continue
+        n_in = 6
+        tiles = np.log(rng.uniform(0.1, 1000, size=(n_in, S, G)))
+        tiles[2] = -((np.arange(G)[None] - rng.uniform(0, G, (S, 1))) ** 2) * 3.0  # floors
+        ar.import_tiles(tiles, list(range(n_in)))
+        kids = [0, 1, 2, 3, 4, 5, 3, 1]
+        jobs = [
+            engine.make_job(0, 5, base=-1, out=-1, flags=engine.JOB_SCAN | engine.JOB_ADD_PRIOR, slot=0),
+            engine.make_job(2, 4, base=0, out=8, flags=engine.JOB_SCAN, slot=1),
+            engine.make_job(5, 1, base=1, out=9, flags=engine.JOB_SCAN, slot=2),
+            engine.make_job(6, 2, base=-1, out=10, flags=0, slot=-1),
+        ]
+        want = [
+            (None, ar.prior + onum.log_s([tiles[c] for c in kids[0:5]])),
+            (8, onum.node_log_r(tiles[0], [tiles[c] for c in kids[2:6]])),
+            (9, onum.node_log_r(tiles[1], [tiles[5]])),
+            (10, onum.log_d_chain([tiles[3], tiles[1]])),
+        ]
+        got = {}
+        for latency in (False, True):
+            ar.set_latency(latency)
+            sc = ar.run_jobs(np.array(jobs), np.array(kids), n_slots=3).cpu().numpy()
+            out = ar.export_tiles([8, 9, 10]).cpu().numpy()
+            got[latency] = (sc, out)
+            for j, (o, tile) in enumerate(want):
+                if o is not None:
+                    assert_close_bucketed(out[o - 8], tile, what="G=%d job %d latency=%s" % (G, j, latency), max_boundary=16)
+                if jobs[j][5] >= 0:
+                    lse, last = onum.root_terms(tile)
+                    assert sc[0, jobs[j][5]] == pytest.approx(lse, rel=1e-9), (G, j, latency)
+        # the two mappings differ by rounding only
+        np.testing.assert_allclose(got[True][0][0], got[False][0][0], rtol=1e-12)
+        ran += 1
+    assert ran >= 20
