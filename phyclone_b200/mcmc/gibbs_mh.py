@@ -185,7 +185,9 @@ class PruneRegraphSampler(object):
             new_tree = pruned_tree.copy()
             nc = new_tree.get_number_of_children(new_tree.root_node_name if parent is None else parent)
             new_tree.add_subtree(subtree, parent=parent)
-            new_tree.update()
+            # the reference refreshes the whole tree here (gibbs_mh.py:108); add_subtree has already refreshed the
+            # path from `parent` to the root and every other node holds the tile a refresh would look up again
+            # (node tiles are memoised by log_p tile and child tiles), so the full walk is skipped
             trees.append((nc, new_tree))
         pending = [self.tree_dist.prepare(x) for _, x in trees]
         log_p = np.array([np.log(n + 1) + p.resolve()[1] for (n, _), p in zip(trees, pending)])
