@@ -139,7 +139,8 @@ class RetainedPath(object):
         for k in range(done, t):
             dp = self.sigma[k]
             kind, arg = self.args[k]
-            tree = tree.copy()
+            # edited in place: `tree` is fresh, or the previous step's thawed copy, or the cached replay that the
+            # assignment below supersedes
             if kind == ATTACH:
                 tree.add_data_point_to_node(dp, arg)
             elif kind == NEW:
