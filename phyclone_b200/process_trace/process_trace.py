@@ -66,11 +66,41 @@ def create_topology_dict_from_trace(trace, store):
     """process_trace.py:64-71.  Rebuilding a tree only records its node refreshes (memoised per distinct
     subtree); nothing is evaluated unless a value is read, so counting topologies costs no kernel time."""
     topologies = dict()
+    top = lambda: store.book.counters()["top"]  # noqa: E731 -- arena slots handed out so far
+    permanent = store.arena.alloc.permanent
+    # every rebuilt tree takes arena slots for its distinct node ops, and only the trees kept in the dictionary are
+    # read again: when the slots in use are many times what the kept trees need, start a new arena generation and
+    # re-derive the kept trees in it (a long trace would otherwise double the arena up to its cap).  Only if the
+    # store held nothing but its permanent tiles on entry -- a caller's own live trees must not be invalidated.
+    compact_ok = hasattr(store, "book") and top() == permanent
+    seen_entries = 0
     for chain_num, chain_result in trace.items():
         for i, x in enumerate(chain_result["trace"]):
             curr_tree = Tree.from_dict(x["tree"], store)
             count_topology(topologies, x, i, curr_tree, chain_num)
+            seen_entries += 1
+            if compact_ok and seen_entries % TOPOLOGY_COMPACT_EVERY == 0:
+                kept = sum(2 * (len(t._lr) + len(info["topology"]._lr)) for t, info in topologies.items())
+                if top() - permanent > max(TOPOLOGY_COMPACT_MIN_SLOTS, TOPOLOGY_COMPACT_FACTOR * kept):
+                    topologies = _compact_topologies(topologies, store)
     return topologies
+
+
+TOPOLOGY_COMPACT_EVERY = 256      # trace entries between checks
+TOPOLOGY_COMPACT_MIN_SLOTS = 8192  # never compact below this many slots in use
+TOPOLOGY_COMPACT_FACTOR = 8  # ... nor below this multiple of the kept trees' own slots
+
+
+def _compact_topologies(topologies, store):
+    """New arena generation holding only the trees of `topologies` (same insertion order, same trees structurally)."""
+    store.flush()
+    store.reset()
+    fresh = dict()
+    for key, info in topologies.items():
+        new_key = Tree.from_dict(key.to_dict(), store)
+        info["topology"] = new_key if info["topology"] is key else Tree.from_dict(info["topology"].to_dict(), store)
+        fresh[new_key] = info
+    return fresh
 
 
 def count_topology(topologies, x, i, x_top, chain_num=0):
