@@ -363,3 +363,34 @@ def test_latency_mapping_across_grid_sizes(S):
         np.testing.assert_allclose(got[True][0][0], got[False][0][0], rtol=1e-12)
         ran += 1
     assert ran >= 20
+
+
+@pytest.mark.parametrize("latency", [False, True])
+def test_jobs_with_more_children_than_a_warp_holds(latency):
+    """Child ids are handed out by shuffles from one coalesced load per 32 children: folds of 33, 64 and 70 children
+    cross that boundary (forests with many roots do)."""
+    from phyclone_b200 import engine
+
+    S, G, n_in = 8, 101, 12
+    rng = np.random.default_rng(3)
+    tiles = np.log(rng.uniform(0.5, 2.0, size=(n_in, S, G)))
+    ar = engine.DeviceArena(S, G, n_in + 8, variant=-2)
+    ar.set_latency(latency)
+    ar.import_tiles(tiles, list(range(n_in)))
+    jobs, kids, want = [], [], []
+    for j, C in enumerate((33, 64, 70, 32)):
+        ch = [int(c) for c in rng.integers(0, n_in, C)]
+        jobs.append(engine.make_job(len(kids), C, base=-1, out=-1, flags=engine.JOB_SCAN | engine.JOB_ADD_PRIOR, slot=j))
+        kids.extend(ch)
+        want.append(onum.root_terms(ar.prior + onum.log_s([tiles[c] for c in ch])))
+    base = 5
+    ch = [int(c) for c in rng.integers(0, n_in, 40)]
+    jobs.append(engine.make_job(len(kids), 40, base=base, out=n_in, flags=engine.JOB_SCAN, slot=4))
+    kids.extend(ch)
+    node = onum.node_log_r(tiles[base], [tiles[c] for c in ch])
+    want.append(onum.root_terms(node))
+    sc = ar.run_jobs(np.array(jobs), np.array(kids), n_slots=5).cpu().numpy()
+    for j, (lse, last) in enumerate(want):
+        assert sc[0, j] == pytest.approx(lse, rel=1e-9), j
+        assert sc[1, j] == pytest.approx(last, rel=1e-9), j
+    assert_close_bucketed(ar.export_tiles([n_in]).cpu().numpy()[0], node, what="40-child node", max_boundary=16)
