@@ -215,8 +215,13 @@ int launch_wide_L(const pcb::JobKernelParams& kp, long long n_jobs, size_t smem,
 }
 
 // ---- the latency mapping (node_jobs_rows_kernel): one warp per row, the bodies of a strip pair split over H lanes
-int rows_rb(int S) {  // rows (warps) per CTA: the largest divisor of S up to 4
-  for (int rb = 4; rb > 1; --rb)
+int rows_rb(int S) {  // rows (warps) per CTA: the largest divisor of S up to 4 (PCB_ROWS_RB: up to that many)
+  static int cap = 0;
+  if (!cap) {
+    const char* e = getenv("PCB_ROWS_RB");
+    cap = (e && atoi(e) >= 1 && atoi(e) <= 4) ? atoi(e) : 4;
+  }
+  for (int rb = cap; rb > 1; --rb)
     if (S % rb == 0) return rb;
   return 1;
 }
