@@ -1325,7 +1325,7 @@ int pcb_smc_sweep_dev(const pcb_arena* a, const pcb_sweep_desc* d, void* stream)
         return rc;
       ++launches;
     }
-    PCB_CUDA(launch_k(sw::weigh_kernel, dim3(1), dim3(1024), 0, st, P, t, d->log_uniform, d->lw_uniform));
+    PCB_CUDA(launch_k(sw::weigh_kernel, dim3(1), dim3(threads1), 0, st, P, t, d->log_uniform, d->lw_uniform));  // a thread per particle
     g_launches.fetch_add(1, std::memory_order_relaxed);
     ++launches;
   }
