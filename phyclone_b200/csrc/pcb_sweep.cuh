@@ -270,9 +270,14 @@ __device__ inline double row_sum(const double* rows, int slot, int S) {
   return acc;
 }
 
+// beyond the host's tables (never in practice: they cover T + 2 entries).  Out of line on purpose: inlined, every one of
+// the ~25 look-ups of decide_kernel carried its own lgamma + log expansion -- 12 k static instructions, 189 KB, with
+// the hot path scattered between cold blocks (a third of the kernel's stall samples were instruction fetches)
+__device__ __noinline__ double tab_beyond(int n, bool lf) { return lf ? lgamma((double)n + 1.0) : log((double)n); }
+
 __device__ inline double tab(const double* t, int n, int n_tab, bool lf) {
   if (n < n_tab) return t[n];
-  return lf ? lgamma((double)n + 1.0) : log((double)n);
+  return tab_beyond(n, lf);
 }
 
 // (log_p prior, log_p_one prior) from running statistics: csrc/pcb_hostmod.cpp::priors (tree/distributions.py:39-133);
