@@ -161,7 +161,7 @@ __device__ __forceinline__ void conv_unit(const double* __restrict__ a, const do
   }
   // warp-uniform: bodies 0..Q-1 in full, body Q as a triangle
   int it = 0;
-  if (UNIFORM) {
+  if constexpr (UNIFORM) {
     // unit-per-warp mapping: u (hence every strip length) is the same for all lanes, so the diagonal body of the
     // FIRST strip (body number u) can run as a triangle too
     for (; it + 2 <= Q; it += 2) {
@@ -183,17 +183,17 @@ __device__ __forceinline__ void conv_unit(const double* __restrict__ a, const do
     } else {
       conv_step_last<L>(st, X, bv, y2);
     }
-    return;
-  }
-  for (; it + 2 <= Q; it += 2) {
-    conv_step<L>(st, X, Y, bv, y1, y2);
-    conv_step<L>(st, Y, X, bv, y1, y2);
-  }
-  if (it < Q) {  // Q odd: one more full body, then the triangle reads the window that body left in Y
-    conv_step<L>(st, X, Y, bv, y1, y2);
-    conv_step_last<L>(st, Y, bv, y2);
   } else {
-    conv_step_last<L>(st, X, bv, y2);
+    for (; it + 2 <= Q; it += 2) {
+      conv_step<L>(st, X, Y, bv, y1, y2);
+      conv_step<L>(st, Y, X, bv, y1, y2);
+    }
+    if (it < Q) {  // Q odd: one more full body, then the triangle reads the window that body left in Y
+      conv_step<L>(st, X, Y, bv, y1, y2);
+      conv_step_last<L>(st, Y, bv, y2);
+    } else {
+      conv_step_last<L>(st, X, bv, y2);
+    }
   }
 }
 

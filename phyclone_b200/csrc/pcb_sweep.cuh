@@ -658,14 +658,12 @@ __global__ void decide_kernel(const Params p, const int t) {
       const int e_shift = fused ? k - 1 : 0;  // stage-2 children start at index k of the fused list
       int sz = 1;
       u64 key = s_key ^ edge_hash(pe, 0, ps) ^ data_hash(pn, 0, dpidx);
-      double ways_keep = 0.0;
       for (int r = 0; r < R; ++r) {
         if (take >> r & 1ull) {
           sz += s_sz[r];
           key ^= edge_hash(s_sl[r], 0, s_gi[r]) ^ edge_hash(s_sl[r], ps, s_gi[r]);
         }
       }
-      (void)ways_keep;
       for (int r = lane; r < R; r += 32) {
         const u64 below = (r == 0) ? 0ull : (take & ((1ull << r) - 1ull));
         if (take >> r & 1ull) {
