@@ -4,6 +4,8 @@ Every candidate tree of a move is built first (host bookkeeping + recorded tile 
 candidate scores are read afterwards, so one Gibbs step is one batched device evaluation.
 """
 
+import os
+
 import numpy as np
 
 from .._hostmod import load as _load_hostmod
@@ -13,7 +15,8 @@ _hm = _load_hostmod()
 
 
 class DataPointSampler(object):
-    LOOKAHEAD = 8  # moves scored per device round trip (see sample_tree)
+    # moves scored per device round trip (see sample_tree); any value gives the same chain
+    LOOKAHEAD = int(os.environ.get("PCB_GIBBS_LOOKAHEAD", "8"))
 
     def __init__(self, tree_dist, rng, outliers=False):
         self.tree_dist = tree_dist
