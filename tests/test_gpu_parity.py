@@ -361,6 +361,12 @@ def test_latency_mapping_across_grid_sizes(S):
                     assert sc[0, jobs[j][5]] == pytest.approx(lse, rel=1e-9), (G, j, latency)
         # the two mappings differ by rounding only
         np.testing.assert_allclose(got[True][0][0], got[False][0][0], rtol=1e-12)
+        # the arena invariant both kernels rely on: nothing is ever written outside the G payload columns of a row
+        import torch
+
+        pad = torch.ones(ar.layout.pitch, dtype=torch.bool, device=ar.lg.device)
+        pad[ar.layout.lead: ar.layout.lead + G] = False
+        assert bool((ar.lin[:, :, pad] == 0).all()) and bool((ar.lg[:, :, pad] == 0).all()), (variant, G)
         ran += 1
     assert ran >= 20
 
